@@ -1,0 +1,132 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle.  Bit-exact (integer work): best score,
+best node, tie index, number of optimal placements, sibling/child flag, the full optimal set and every
+per-node score."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+import small_synth
+from oracle import port, ref
+from usher_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    n = capi.lib().ub200_device_count()
+    assert n > 0, "no CUDA device: the product has no CPU path, -m gpu tests must run on the B200 box"
+
+
+@pytest.mark.parametrize("path", common.golden_cases(), ids=lambda p: p.split("/")[-1])
+def test_golden_vectors(path):
+    g = common.load(path)
+    m = capi.Mat(g["parent"], g["row_ptr"], g["muts"])
+    res = m.place_batch(g["s_ptr"], g["calls"], node_scores=True, best_set=True)
+    common.assert_matches_expected(g, common.placements_to_dict(res), path)
+    m.close()
+
+
+@pytest.mark.parametrize("pass_samples", [32, 64, 256])
+def test_pass_width_does_not_change_results(pass_samples):
+    g = common.load(common.GOLDEN + "/random_07.npz")
+    m = capi.Mat(g["parent"], g["row_ptr"], g["muts"])
+    m.set_pass_samples(pass_samples)
+    res = m.place_batch(g["s_ptr"], g["calls"], best_set=True)
+    common.assert_matches_expected(g, common.placements_to_dict(res), f"pass={pass_samples}")
+    m.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_vs_port(seed):
+    n = [3000, 8000, 20000][seed % 3]
+    L = [60, 500, 4000][(seed + 1) % 3]
+    mu = [1.0, 4.0, 9.0][seed % 3]
+    shape = ["uniform", "chain", "uniform"][seed % 3]
+    parent, row_ptr, muts, refg = small_synth.random_mat(900 + seed, n, L, mu, shape=shape)
+    s_ptr, calls = small_synth.random_samples(950 + seed, parent, row_ptr, muts, refg, 70)
+    pt = port.PortTree(parent, row_ptr, muts)
+    q = pt.search(s_ptr, calls)
+    m = capi.Mat(parent, row_ptr, muts)
+    res = common.placements_to_dict(m.place_batch(s_ptr, calls, best_set=True))
+    for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
+        assert np.array_equal(np.asarray(res[k]).astype(np.int64), q[k].astype(np.int64)), (seed, k)
+    m.close()
+    pt.close()
+
+
+def test_deep_tree_spills_the_stack():
+    """A 300-level chain exceeds the in-shared-memory stack and exercises the HBM spill path."""
+    parent, row_ptr, muts, refg = small_synth.random_mat(77, 2500, 300, 2.0, shape="chain")
+    s_ptr, calls = small_synth.random_samples(78, parent, row_ptr, muts, refg, 40)
+    pt = port.PortTree(parent, row_ptr, muts)
+    q = pt.search(s_ptr, calls)
+    m = capi.Mat(parent, row_ptr, muts)
+    assert m.info.max_level > 64
+    res = common.placements_to_dict(m.place_batch(s_ptr, calls, best_set=True, node_scores=True))
+    for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
+        assert np.array_equal(np.asarray(res[k]).astype(np.int64), q[k].astype(np.int64)), k
+    assert np.array_equal(res["node_scores"], pt.search(s_ptr, calls, per_node=True)["node_scores"])
+    m.close()
+    pt.close()
+
+
+def test_config2_shape_vs_reference_and_batch_invariance():
+    """BASELINE config 2 (100k-node MAT, ~30 mutations/node, 30 kb genome).  (a) a few samples against the
+    reference's own mapper2_body when oracle/_ref is present; (b) size-independent property: the placement of a
+    sample does not depend on which other samples share its launch (different groups => different position
+    bitmaps and tables)."""
+    s = capi.Synth(100_000, 30.0, 30_000, capi.Synth.UNIFORM, 20260927)
+    p, r, mu = s.arrays()
+    m = capi.Mat.from_flat_struct(s.flat)
+    out = {}
+    for fam in (capi.Synth.SNV40, capi.Synth.LEAF, capi.Synth.AMBIG):
+        sp, sc, so = s.samples(256, fam, 99 + fam)
+        a = m.place_batch(sp, sc)["placements"]
+        perm = np.random.default_rng(fam).permutation(256)
+        lens = np.diff(sp.astype(np.int64))
+        sp2 = np.concatenate([[0], np.cumsum(lens[perm])]).astype(np.uint64)
+        sc2 = np.concatenate([sc[int(sp[i]):int(sp[i + 1])] for i in perm])
+        b = m.place_batch(sp2, sc2)["placements"]
+        for k in ("score", "best_node", "best_j", "num_best", "has_unique"):
+            assert np.array_equal(a[k][perm], b[k]), (fam, k)
+        assert np.all(a["score"] >= 0)
+        out[fam] = (sp, sc, a)
+    if ref.available():
+        rt = ref.RefTree.from_flat(p, r, mu)
+        for fam in out:
+            sp, sc, a = out[fam]
+            k = 3
+            o = rt.search(sp[: k + 1], sc[: int(sp[k])], len(p), threads=os.cpu_count() or 1, want_set=False)
+            for key, mine in (("score", "score"), ("best_dfs", "best_node"), ("best_j", "best_j"),
+                              ("num_best", "num_best"), ("has_unique", "has_unique")):
+                assert np.array_equal(o[key].astype(np.int64), a[mine][:k].astype(np.int64)), (fam, key)
+        rt.close()
+    m.close()
+    s.close()
+
+
+def test_resident_api_matches_batch_api_and_times():
+    g = common.load(common.GOLDEN + "/random_15.npz")
+    m = capi.Mat(g["parent"], g["row_ptr"], g["muts"])
+    S = m.upload(g["s_ptr"], g["calls"])
+    S.place()
+    a = S.download()
+    t = m.timing()
+    assert t.score_launches >= 1 and t.score_ms > 0 and t.score_bytes > 0
+    b = m.place_batch(g["s_ptr"], g["calls"])["placements"]
+    assert np.array_equal(a, b)
+    S.close()
+    m.close()
+
+
+def test_bad_samples_are_rejected():
+    g = common.load(common.GOLDEN + "/random_04.npz")
+    m = capi.Mat(g["parent"], g["row_ptr"], g["muts"])
+    calls = np.array([(9, 1, 1, 2, 0), (5, 1, 1, 2, 0)], capi.MUT_DTYPE)
+    with pytest.raises(capi.UB200Error) as e:
+        m.place_batch(np.array([0, 2], np.uint64), calls)
+    assert e.value.code == -5
+    m.close()

@@ -1,0 +1,121 @@
+"""CPU: host logic of the product.  The C++ derivation (usher_b200/csrc/derive.cpp) is run through the
+host-only ub200_debug_derive hook and its arrays are pushed through a plain-Python model of the kernel's
+arithmetic (tests/kernel_model.py); the result must reproduce the golden vectors.  Also: the C-ABI library
+loads and exports every symbol include/usher_b200.h declares, input validation rejects malformed trees and
+samples, and without a GPU the compute entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+
+import common
+import kernel_model
+import small_synth
+from usher_b200 import capi
+
+
+@pytest.mark.parametrize("path", common.golden_cases(), ids=lambda p: p.split("/")[-1])
+def test_derivation_and_closed_form_match_golden(path):
+    g = common.load(path)
+    d = capi.debug_derive(g["parent"], g["row_ptr"], g["muts"], target_tiles=7)
+    n = len(g["parent"])
+    if n > 600:  # keep the pure-Python model quick
+        sel = np.arange(0, len(g["s_ptr"]) - 1)[:12]
+    else:
+        sel = np.arange(0, len(g["s_ptr"]) - 1)
+    s_ptr = g["s_ptr"].astype(np.int64)
+    sub_ptr = np.concatenate([[0], np.cumsum(np.diff(s_ptr)[sel])]).astype(np.uint64)
+    sub_calls = np.concatenate([g["calls"][s_ptr[s]:s_ptr[s + 1]] for s in sel]) if len(sel) else g["calls"][:0]
+    res, ns = kernel_model.place(d, sub_ptr, sub_calls, per_node=True)
+    for i, s in enumerate(sel):
+        r = res[i]
+        assert (r["score"], r["best_node"], r["best_j"], r["num_best"], r["has_unique"]) == (
+            int(g["exp_score"][s]), int(g["exp_best_dfs"][s]), int(g["exp_best_j"][s]), int(g["exp_num_best"][s]),
+            int(g["exp_has_unique"][s])), (path, s)
+        a, b = int(g["exp_best_set_ptr"][s]), int(g["exp_best_set_ptr"][s + 1])
+        assert [x for x, _ in r["optimal"]] == g["exp_best_set"][a:b].tolist()
+        assert [h for _, h in r["optimal"]] == g["exp_best_set_unique"][a:b].tolist()
+        assert np.array_equal(ns[i], g["exp_node_scores"][s])
+
+
+def test_derive_structure():
+    parent, row_ptr, muts, _ = small_synth.random_mat(1, 400, 100, 3.0)
+    d = capi.debug_derive(parent, row_ptr, muts, target_tiles=16)
+    n = d["n"]
+    # tiles partition the DFS order; ancestor chains are root-first paths
+    ts = d["tile_start"]
+    assert ts[0] == 0 and ts[-1] == n and np.all(np.diff(ts.astype(np.int64)) > 0)
+    for t in range(len(ts) - 1):
+        chain = d["anc"][d["anc_ptr"][t]:d["anc_ptr"][t + 1]].tolist()
+        exp = []
+        a = parent[ts[t]]
+        while a >= 0:
+            exp.append(int(a))
+            a = parent[a]
+        assert chain == exp[::-1]
+    # tiekey is a permutation; key order = (num_leaves desc, j desc)
+    order = d["key_to_node"]
+    assert sorted(order.tolist()) == list(range(n))
+    k = [(int(d["num_leaves"][v]), int(d["tie_index"][v])) for v in order]
+    assert k == sorted(k, reverse=True)
+    # BFS index is a permutation starting at the root; levels consistent
+    assert d["tie_index"][0] == 0 and sorted(d["tie_index"].tolist()) == list(range(n))
+    assert all(d["level"][i] == d["level"][parent[i]] + 1 for i in range(1, n))
+
+
+def test_header_declares_only_exported_symbols():
+    hdr = open(os.path.join(os.path.dirname(common.HERE), "include", "usher_b200.h")).read()
+    declared = set(re.findall(r"\b(ub200_[a-z_0-9]+)\s*\(", hdr))
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/usher_b200.h but not exported"
+    assert declared >= set(capi.EXPORTS)
+    assert L.ub200_abi_version() == 1
+    S = capi.synth_lib()
+    shdr = open(os.path.join(os.path.dirname(common.HERE), "include", "usher_b200_synth.h")).read()
+    for name in set(re.findall(r"\b(ub200_synth_[a-z_0-9]+)\s*\(", shdr)):
+        assert hasattr(S, name)
+
+
+def _derive_err(parent, row_ptr, muts):
+    with pytest.raises(capi.UB200Error) as e:
+        capi.debug_derive(parent, row_ptr, muts)
+    return e.value.code
+
+
+def test_validation_rejects_bad_trees():
+    M = capi.MUT_DTYPE
+    ok_m = np.array([(5, 1, 1, 2, 0)], M)
+    assert _derive_err([-1, 0, 0, 1], [0, 0, 0, 0, 1], ok_m) == -2          # node 3 under node 1 after node 2: not pre-order
+    assert _derive_err([0, 0], [0, 0, 1], ok_m) == -2                        # root must have parent -1
+    assert _derive_err([-1, 0], [0, 0, 1], np.array([(5, 1, 1, 3, 0)], M)) == -3   # multi-bit tree allele
+    assert _derive_err([-1, 0], [0, 0, 2], np.array([(9, 1, 1, 2, 0), (5, 1, 1, 2, 0)], M)) == -4  # unsorted row
+    assert _derive_err([-1, 0], [0, 0, 1], np.array([(1 << 27, 1, 1, 2, 0)], M)) == -4  # position too large
+    assert _derive_err([-1, 0, 0], [0, 0, 1, 2], np.array([(5, 1, 1, 2, 0), (5, 2, 2, 4, 0)], M)) == -1  # ref disagreement
+
+
+def test_no_device_fails_loudly(has_gpu):
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    parent, row_ptr, muts, _ = small_synth.random_mat(3, 20, 30, 1.0)
+    with pytest.raises(capi.UB200Error) as e:
+        capi.Mat(parent, row_ptr, muts)
+    assert e.value.code == capi.E_NO_DEVICE
+
+
+def test_synth_generator_is_a_valid_mat():
+    s = capi.Synth(3000, 4.0, 2000, capi.Synth.SC2, 11)
+    p, r, m = s.arrays()
+    d = capi.debug_derive(p, r, m)
+    assert d["n"] == 3000 and d["m"] == len(m)
+    # par_nuc recorded by the generator == the path state the derivation reconstructs
+    prev = (d["mutw"] >> 2) & 3
+    assert np.array_equal(1 << prev, m["par_nuc"])
+    for fam in (0, 1, 2):
+        sp, sc, so = s.samples(50, fam, 5)
+        for i in range(50):
+            pos = sc["position"][int(sp[i]):int(sp[i + 1])]
+            assert np.all(np.diff(pos) > 0)
+    s.close()

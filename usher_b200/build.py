@@ -1,0 +1,59 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel with the repo to the GPU box).
+
+  usher_b200/libusher_b200.so   C-ABI + sm_100a kernels (nvcc -gencode arch=compute_100a,code=sm_100a)
+  usher_b200/libub200_synth.so  synthetic MAT / sample generator (host only)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+INC = os.path.join(ROOT, "include")
+LIB = os.path.join(PKG, "libusher_b200.so")
+SYNTH = os.path.join(PKG, "libub200_synth.so")
+# The image exports CXX=/opt/gcc/bin/g++, a wrapper that links libstdc++ statically; a second libstdc++ in a
+# python process that already loaded the shared one crashes.  Pin the system compiler.
+HOSTCXX = "/usr/bin/g++"
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdrs += [os.path.join(INC, f) for f in os.listdir(INC)]
+    srcs = [os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "derive.cpp")]
+    if force or _stale(LIB, srcs + hdrs):
+        cmd = [
+            _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC", "-shared", "-I", INC, "-I", CSRC,
+            "-Xptxas", "-v" if verbose else "-warn-spills", "-o", LIB,
+        ] + srcs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed")
+    ssrc = [os.path.join(CSRC, "synth.cpp")]
+    if force or _stale(SYNTH, ssrc + hdrs):
+        subprocess.check_call([HOSTCXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-I", INC, "-o", SYNTH] + ssrc)
+    return LIB, SYNTH
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

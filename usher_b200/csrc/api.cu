@@ -1,0 +1,555 @@
+// C-ABI of the placement engine (include/usher_b200.h): handles, device memory, launches, timing.
+// No CPU fallback lives here: every compute entry point needs a CUDA device and fails loudly without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "score_kernel.cuh"
+#include "ub200_internal.h"
+#include "usher_b200.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return (int)e_ > 0 ? (int)e_ : 1;                                                      \
+        }                                                                                          \
+    } while (0)
+
+template <class T>
+int dev_upload(T** dst, const T* src, size_t count, cudaStream_t st) {
+    *dst = nullptr;
+    CU(cudaMalloc((void**)dst, std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) CU(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+}  // namespace
+
+struct ub200_mat {
+    int device = 0;
+    ub200::Derived d;           // host copies of the small derived arrays (big ones are freed after upload)
+    uint32_t n = 0, n_tiles = 0, L = 0;
+    uint64_t m = 0;
+    // device
+    uint32_t* mutw = nullptr;
+    ub200::NodeHdr* hdr = nullptr;
+    uint32_t *row32 = nullptr, *tile_start = nullptr, *anc_ptr = nullptr, *anc = nullptr;
+    uint32_t *key_to_node = nullptr, *tie_index = nullptr, *num_leaves = nullptr;
+    int32_t* gstack = nullptr;
+    uint32_t gstack_levels = 0;
+    uint64_t device_bytes = 0;
+    int num_sms = 0;
+    uint32_t grid = 0;          // CTAs per scoring launch
+    uint32_t pass_groups = 1;   // sample groups (x32 samples) per pass over the tree
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::vector<cudaEvent_t> ev;
+    // timing of the last place call
+    ub200_timing last = {};
+    struct Span { int a, b, kind; };
+    std::vector<Span> spans;
+    int ev_used = 0;
+};
+
+struct ub200_samples {
+    ub200_mat* mat = nullptr;
+    uint32_t n_samples = 0, n_groups = 0;
+    uint64_t n_calls = 0;
+    ub200_mutation* calls = nullptr;
+    unsigned long long* sample_ptr = nullptr;
+    uint32_t* call_sample = nullptr;
+    uint32_t* bitmap = nullptr;
+    uint32_t bitmap_words = 0;
+    uint8_t* tab = nullptr;
+    int32_t* base = nullptr;
+    ub200_placement* results = nullptr;
+    int32_t* best_rel = nullptr;
+    unsigned long long* part_key = nullptr;
+    uint32_t* part_cnt = nullptr;
+    uint32_t part_groups = 0, part_wpg = 0;
+    int32_t* node_scores = nullptr;
+    uint32_t* set_out = nullptr;
+    unsigned long long* set_ptr = nullptr;
+    uint32_t* set_fill = nullptr;
+    uint64_t set_total = 0;
+    bool have_results = false, have_node_scores = false, have_set = false;
+    float prep_ms = 0.f;
+};
+
+namespace {
+
+int ensure_events(ub200_mat* M, int need) {
+    while ((int)M->ev.size() < need) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        M->ev.push_back(e);
+    }
+    return 0;
+}
+
+int span_begin(ub200_mat* M, int kind) {
+    int rc = ensure_events(M, M->ev_used + 2);
+    if (rc) return rc;
+    CU(cudaEventRecord(M->ev[M->ev_used], M->stream));
+    M->spans.push_back({M->ev_used, M->ev_used + 1, kind});
+    M->ev_used += 2;
+    return 0;
+}
+int span_end(ub200_mat* M) {
+    CU(cudaEventRecord(M->ev[M->spans.back().b], M->stream));
+    return 0;
+}
+
+__global__ void k_prefix_numbest(const ub200_placement* r, uint32_t n, unsigned long long* ptr) {
+    // single thread: n is the batch size (<= a few 100k); runs once per BEST_SET request
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (uint32_t i = 0; i < n; i++) { ptr[i] = acc; acc += r[i].num_best; }
+        ptr[n] = acc;
+    }
+}
+
+template <int MODE>
+int launch_score(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, bool smem_bitmap) {
+    using namespace ub200;
+    ScoreParams p;
+    p.mutw = M->mutw; p.hdr = M->hdr; p.row32 = M->row32;
+    p.tile_start = M->tile_start; p.anc_ptr = M->anc_ptr; p.anc = M->anc;
+    p.n_nodes = M->n; p.n_tiles = M->n_tiles; p.L = M->L;
+    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.base = S->base;
+    p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups;
+    p.part_key = S->part_key; p.part_cnt = S->part_cnt;
+    p.gstack = M->gstack; p.gstack_levels = M->gstack_levels;
+    p.node_scores = S->node_scores; p.target_rel = S->best_rel;
+    p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
+    const uint32_t grid = std::max<uint32_t>(ngroups, (M->grid / ngroups) * ngroups);
+    const uint32_t bm_bytes = smem_bitmap ? ((S->bitmap_words * 4u + 127u) & ~127u) : 0u;
+    const size_t smem = bm_bytes + (size_t)kWarpsPerCta * kWarpSmemBytes;
+    if (smem_bitmap) {
+        auto k = k_score<MODE, true>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads, smem, M->stream>>>(p);
+    } else {
+        auto k = k_score<MODE, false>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads, smem, M->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Build the per-group position bitmap + position-major cost table + per-sample base count on the device.
+// Part of every place call (it is sample-side work of the hot path), timed as "prep".
+int run_prep(ub200_mat* M, ub200_samples* S) {
+    cudaStream_t st = M->stream;
+    int rc = span_begin(M, 0);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(S->bitmap, 0, (size_t)S->n_groups * S->bitmap_words * 4, st));
+    CU(cudaMemsetAsync(S->tab, 0, (size_t)S->n_groups * M->L * 32, st));
+    CU(cudaMemsetAsync(S->base, 0, (size_t)S->n_groups * 32 * 4, st));
+    if (S->n_calls) {
+        ub200::PrepParams pp;
+        pp.calls = S->calls; pp.sample_ptr = S->sample_ptr; pp.call_sample = S->call_sample;
+        pp.n_calls = S->n_calls; pp.L = M->L; pp.bitmap_words = S->bitmap_words;
+        pp.bitmap = S->bitmap; pp.tab = S->tab; pp.base = S->base;
+        const uint32_t blocks = (uint32_t)((S->n_calls + 255) / 256);
+        ub200::k_prep_scatter<<<blocks, 256, 0, st>>>(pp);
+        CU(cudaGetLastError());
+    }
+    return span_end(M);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ub200_last_error(void) { return g_err.c_str(); }
+int ub200_abi_version(void) { return UB200_ABI_VERSION; }
+
+int ub200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void ub200_mat_destroy(ub200_mat* M) {
+    if (!M) return;
+    cudaSetDevice(M->device);
+    cudaFree(M->mutw); cudaFree(M->hdr); cudaFree(M->row32); cudaFree(M->tile_start); cudaFree(M->anc_ptr);
+    cudaFree(M->anc); cudaFree(M->key_to_node); cudaFree(M->tie_index); cudaFree(M->num_leaves);
+    cudaFree(M->gstack);
+    for (auto e : M->ev) cudaEventDestroy(e);
+    if (M->own_stream) cudaStreamDestroy(M->own_stream);
+    delete M;
+}
+
+int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
+    if (!flat || !out) return fail(UB200_E_ARG, "ub200_mat_create: NULL argument");
+    *out = nullptr;
+    int ndev = ub200_device_count();
+    if (ndev <= 0) return fail(UB200_E_NO_DEVICE, "ub200_mat_create: no CUDA device (there is no CPU path)");
+    if (device < 0 || device >= ndev) return fail(UB200_E_ARG, "ub200_mat_create: bad device ordinal");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    auto* M = new ub200_mat();
+    M->device = device;
+    M->num_sms = prop.multiProcessorCount;
+    M->grid = (uint32_t)M->num_sms * 2u;
+    const uint32_t total_warps = M->grid * ub200::kWarpsPerCta;
+    std::string err;
+    int rc = ub200::derive(*flat, total_warps * 8u, M->d, err);
+    if (rc != UB200_OK) { delete M; return fail(rc, err); }
+    auto& d = M->d;
+    M->n = d.n; M->m = d.m; M->L = d.L; M->n_tiles = (uint32_t)d.tile_start.size() - 1;
+    rc = 0;
+    auto guard = [&](int r) { if (r && !rc) rc = r; };
+    CU(cudaStreamCreateWithFlags(&M->own_stream, cudaStreamNonBlocking));
+    M->stream = M->own_stream;
+    guard(dev_upload(&M->mutw, d.mutw.data(), d.mutw.size(), M->stream));
+    guard(dev_upload(&M->hdr, d.hdr.data(), d.hdr.size(), M->stream));
+    guard(dev_upload(&M->row32, d.row32.data(), d.row32.size(), M->stream));
+    guard(dev_upload(&M->tile_start, d.tile_start.data(), d.tile_start.size(), M->stream));
+    guard(dev_upload(&M->anc_ptr, d.anc_ptr.data(), d.anc_ptr.size(), M->stream));
+    guard(dev_upload(&M->anc, d.anc.data(), d.anc.size(), M->stream));
+    guard(dev_upload(&M->key_to_node, d.key_to_node.data(), d.key_to_node.size(), M->stream));
+    guard(dev_upload(&M->tie_index, d.tie_index.data(), d.tie_index.size(), M->stream));
+    guard(dev_upload(&M->num_leaves, d.num_leaves.data(), d.num_leaves.size(), M->stream));
+    M->device_bytes = d.mutw.size() * 4 + d.hdr.size() * 16 + d.row32.size() * 4 + d.tile_start.size() * 4 +
+                      d.anc_ptr.size() * 4 + d.anc.size() * 4 + (uint64_t)d.n * 12;
+    if (!rc && d.max_level + 1 > (uint32_t)ub200::kStackDepth) {
+        M->gstack_levels = d.max_level + 1 - ub200::kStackDepth;
+        const size_t bytes = (size_t)total_warps * M->gstack_levels * 32 * sizeof(int32_t);
+        if (bytes > (size_t)16 << 30) {
+            rc = fail(UB200_E_LIMIT, "tree too deep for the spill stack (" + std::to_string(d.max_level) + " levels)");
+        } else {
+            cudaError_t e = cudaMalloc((void**)&M->gstack, bytes);
+            if (e != cudaSuccess) rc = fail((int)e, std::string("cudaMalloc spill stack: ") + cudaGetErrorString(e));
+            M->device_bytes += bytes;
+        }
+    }
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(M->stream);
+        if (e != cudaSuccess) rc = fail((int)e, std::string("upload: ") + cudaGetErrorString(e));
+    }
+    if (rc) { ub200_mat_destroy(M); return rc; }
+    // the big host arrays are no longer needed
+    std::vector<uint32_t>().swap(d.mutw);
+    std::vector<ub200::NodeHdr>().swap(d.hdr);
+    std::vector<uint32_t>().swap(d.anc);
+    *out = M;
+    return UB200_OK;
+}
+
+int ub200_mat_info_get(const ub200_mat* M, ub200_mat_info* o) {
+    if (!M || !o) return fail(UB200_E_ARG, "ub200_mat_info_get: NULL argument");
+    o->n_nodes = M->n; o->max_level = M->d.max_level; o->n_mutations = M->m; o->genome_len = M->L;
+    o->n_tiles = M->n_tiles; o->device_bytes = M->device_bytes;
+    o->algorithmic_bytes = 4ull * M->m + 16ull * M->n;
+    o->device = M->device; o->reserved = 0;
+    return UB200_OK;
+}
+
+int ub200_mat_node_arrays(const ub200_mat* M, uint32_t* bfs_index, uint32_t* num_leaves, uint32_t* level) {
+    if (!M) return fail(UB200_E_ARG, "ub200_mat_node_arrays: NULL handle");
+    if (bfs_index) memcpy(bfs_index, M->d.tie_index.data(), sizeof(uint32_t) * M->n);
+    if (num_leaves) memcpy(num_leaves, M->d.num_leaves.data(), sizeof(uint32_t) * M->n);
+    if (level) memcpy(level, M->d.level.data(), sizeof(uint32_t) * M->n);
+    return UB200_OK;
+}
+
+int ub200_mat_set_pass_samples(ub200_mat* M, uint32_t spp) {
+    if (!M) return fail(UB200_E_ARG, "NULL handle");
+    if (spp == 0) spp = 32;
+    if (spp % 32 || spp > 256 || (spp & (spp - 1))) return fail(UB200_E_ARG, "samples per pass must be 32, 64, 128 or 256");
+    M->pass_groups = spp / 32;
+    return UB200_OK;
+}
+
+int ub200_mat_set_stream(ub200_mat* M, void* s) {
+    if (!M) return fail(UB200_E_ARG, "NULL handle");
+    M->stream = s ? (cudaStream_t)s : M->own_stream;
+    return UB200_OK;
+}
+
+int ub200_mat_synchronize(ub200_mat* M) {
+    if (!M) return fail(UB200_E_ARG, "NULL handle");
+    CU(cudaSetDevice(M->device));
+    CU(cudaStreamSynchronize(M->stream));
+    return UB200_OK;
+}
+
+void ub200_samples_free(ub200_samples* S) {
+    if (!S) return;
+    cudaSetDevice(S->mat->device);
+    cudaFree(S->calls); cudaFree(S->sample_ptr); cudaFree(S->call_sample); cudaFree(S->bitmap); cudaFree(S->tab);
+    cudaFree(S->base); cudaFree(S->results); cudaFree(S->best_rel); cudaFree(S->part_key); cudaFree(S->part_cnt);
+    cudaFree(S->node_scores); cudaFree(S->set_out); cudaFree(S->set_ptr); cudaFree(S->set_fill);
+    delete S;
+}
+
+int ub200_samples_upload(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_ptr, const ub200_mutation* calls,
+                         ub200_samples** out) {
+    if (!M || !out || !sample_ptr || n_samples == 0) return fail(UB200_E_ARG, "ub200_samples_upload: bad argument");
+    *out = nullptr;
+    const uint64_t n_calls = sample_ptr[n_samples];
+    if (n_calls && !calls) return fail(UB200_E_ARG, "ub200_samples_upload: NULL calls");
+    if (sample_ptr[0] != 0) return fail(UB200_E_ARG, "ub200_samples_upload: sample_ptr[0] != 0");
+    // ---- host validation (the reference's merge-scan assumes sorted calls, usher_mapper.cpp:191,239)
+    std::vector<uint32_t> owner(n_calls);
+    for (uint32_t s = 0; s < n_samples; s++) {
+        if (sample_ptr[s + 1] < sample_ptr[s]) return fail(UB200_E_ARG, "sample_ptr not monotone");
+        int64_t last = -1;
+        for (uint64_t k = sample_ptr[s]; k < sample_ptr[s + 1]; k++) {
+            const ub200_mutation& c = calls[k];
+            if (c.position < 0 || (int64_t)c.position <= last)
+                return fail(UB200_E_SAMPLE_ORDER, "sample " + std::to_string(s) +
+                                                      ": calls must be strictly position-increasing and >= 0");
+            last = c.position;
+            if ((c.mut_nuc & 15u) == 0 || c.mut_nuc > 15u)
+                return fail(UB200_E_ARG, "sample " + std::to_string(s) + ": mut_nuc must be a non-empty 4-bit set");
+            if (ub200::nuc_code(c.ref_nuc) < 0)
+                return fail(UB200_E_NOT_ONE_HOT, "sample " + std::to_string(s) + ": ref_nuc must be one-hot");
+            if ((uint32_t)c.position < M->L && M->d.ref_of[c.position] && M->d.ref_of[c.position] != c.ref_nuc)
+                return fail(UB200_E_ARG, "sample " + std::to_string(s) + " position " + std::to_string(c.position) +
+                                             ": reference allele differs from the tree's");
+            owner[k] = s;
+        }
+    }
+    CU(cudaSetDevice(M->device));
+    auto* S = new ub200_samples();
+    S->mat = M;
+    S->n_samples = n_samples;
+    S->n_groups = (n_samples + 31) / 32;
+    S->n_calls = n_calls;
+    S->bitmap_words = ((M->L + 31) / 32 + 3) & ~3u;
+    const size_t tab_bytes = (size_t)S->n_groups * M->L * 32;
+    if (tab_bytes > ((size_t)24 << 30)) {
+        delete S;
+        return fail(UB200_E_LIMIT, "sample batch too large for one resident table; split the batch");
+    }
+    int rc = 0;
+    auto guard = [&](int r) { if (r && !rc) rc = r; };
+    cudaStream_t st = M->stream;
+    guard(dev_upload(&S->calls, calls, n_calls, st));
+    guard(dev_upload(&S->call_sample, owner.data(), n_calls, st));
+    guard(dev_upload(&S->sample_ptr, (const unsigned long long*)sample_ptr, (size_t)n_samples + 1, st));
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc) return;
+        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) rc = fail((int)e, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    };
+    alloc((void**)&S->bitmap, (size_t)S->n_groups * S->bitmap_words * 4);
+    alloc((void**)&S->tab, tab_bytes);
+    alloc((void**)&S->base, (size_t)S->n_groups * 32 * 4);
+    alloc((void**)&S->results, (size_t)S->n_groups * 32 * sizeof(ub200_placement));
+    alloc((void**)&S->best_rel, (size_t)S->n_groups * 32 * 4);
+    if (rc) { ub200_samples_free(S); return rc; }
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail((int)e, std::string("sample upload: ") + cudaGetErrorString(e));
+    }
+    if (rc) { ub200_samples_free(S); return rc; }
+    *out = S;
+    return UB200_OK;
+}
+
+int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int sync) {
+    if (!M || !S || S->mat != M) return fail(UB200_E_ARG, "ub200_place_resident: bad handles");
+    CU(cudaSetDevice(M->device));
+    const bool smem_bitmap = S->bitmap_words * 4u <= ub200::kMaxSmemBitmapBytes;
+    const uint32_t NG = M->pass_groups;
+    const uint32_t wpg_max = (std::max<uint32_t>(NG, (M->grid / 1))) * ub200::kWarpsPerCta;  // ngroups==1 bound
+    if (S->part_groups < NG || S->part_wpg < wpg_max) {
+        cudaFree(S->part_key); cudaFree(S->part_cnt);
+        S->part_key = nullptr; S->part_cnt = nullptr;
+        CU(cudaMalloc((void**)&S->part_key, (size_t)NG * wpg_max * 32 * 8));
+        CU(cudaMalloc((void**)&S->part_cnt, (size_t)NG * wpg_max * 32 * 4));
+        S->part_groups = NG; S->part_wpg = wpg_max;
+    }
+    M->spans.clear(); M->ev_used = 0;
+    M->last = {};
+    { int rc = run_prep(M, S); if (rc) return rc; }
+    M->last.total_launches += 4;
+    for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
+        const uint32_t ng = std::min(NG, S->n_groups - g0);
+        int rc = span_begin(M, 1); if (rc) return rc;
+        rc = launch_score<ub200::kModeBest>(M, S, g0, ng, smem_bitmap); if (rc) return rc;
+        rc = span_end(M); if (rc) return rc;
+        const uint32_t grid = std::max<uint32_t>(ng, (M->grid / ng) * ng);
+        ub200::ReduceParams rp;
+        rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = (grid / ng) * ub200::kWarpsPerCta;
+        rp.group0 = g0; rp.n_samples = S->n_samples; rp.base = S->base; rp.key_to_node = M->key_to_node;
+        rp.tie_index = M->tie_index; rp.num_leaves = M->num_leaves; rp.out = S->results; rp.best_rel = S->best_rel;
+        rc = span_begin(M, 2); if (rc) return rc;
+        ub200::k_reduce<<<ng, 256, 0, M->stream>>>(rp);
+        CU(cudaGetLastError());
+        rc = span_end(M); if (rc) return rc;
+        M->last.score_launches++;
+        M->last.total_launches += 2;
+        M->last.score_bytes += 4ull * M->m + 16ull * M->n;
+    }
+    S->have_results = true;
+    if (flags & UB200_WANT_NODE_SCORES) {
+        const size_t bytes = (size_t)S->n_samples * M->n * sizeof(int32_t);
+        if (!S->node_scores) CU(cudaMalloc((void**)&S->node_scores, bytes));
+        for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
+            const uint32_t ng = std::min(NG, S->n_groups - g0);
+            int rc = launch_score<ub200::kModeNodeScores>(M, S, g0, ng, smem_bitmap); if (rc) return rc;
+            M->last.total_launches++;
+        }
+        S->have_node_scores = true;
+    }
+    if (flags & UB200_WANT_BEST_SET) {
+        if (!S->set_ptr) CU(cudaMalloc((void**)&S->set_ptr, ((size_t)S->n_samples + 1) * 8));
+        if (!S->set_fill) CU(cudaMalloc((void**)&S->set_fill, (size_t)S->n_groups * 32 * 4));
+        k_prefix_numbest<<<1, 1, 0, M->stream>>>(S->results, S->n_samples, S->set_ptr);
+        CU(cudaGetLastError());
+        unsigned long long total = 0;
+        CU(cudaMemcpyAsync(&total, S->set_ptr + S->n_samples, 8, cudaMemcpyDeviceToHost, M->stream));
+        CU(cudaStreamSynchronize(M->stream));
+        cudaFree(S->set_out); S->set_out = nullptr;
+        CU(cudaMalloc((void**)&S->set_out, std::max<size_t>((size_t)total, 1) * 4));
+        S->set_total = total;
+        CU(cudaMemsetAsync(S->set_fill, 0, (size_t)S->n_groups * 32 * 4, M->stream));
+        for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
+            const uint32_t ng = std::min(NG, S->n_groups - g0);
+            int rc = launch_score<ub200::kModeCollect>(M, S, g0, ng, smem_bitmap); if (rc) return rc;
+            M->last.total_launches++;
+        }
+        M->last.total_launches++;
+        S->have_set = true;
+    }
+    if (sync) CU(cudaStreamSynchronize(M->stream));
+    return UB200_OK;
+}
+
+int ub200_last_timing(ub200_mat* M, ub200_timing* out) {
+    if (!M || !out) return fail(UB200_E_ARG, "ub200_last_timing: NULL argument");
+    CU(cudaSetDevice(M->device));
+    CU(cudaStreamSynchronize(M->stream));
+    if (M->spans.empty()) { *out = M->last; return UB200_OK; }   // already folded (ub200_place_batch)
+    float sc = 0.f, rd = 0.f, pr = 0.f;
+    for (auto& s : M->spans) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, M->ev[s.a], M->ev[s.b]));
+        if (s.kind == 1) sc += ms; else if (s.kind == 2) rd += ms; else pr += ms;
+    }
+    M->last.prep_ms = pr;
+    M->last.score_ms = sc;
+    M->last.reduce_ms = rd;
+    *out = M->last;
+    return UB200_OK;
+}
+
+int ub200_results_download(ub200_mat* M, ub200_samples* S, ub200_placement* out) {
+    if (!M || !S || !out || !S->have_results) return fail(UB200_E_ARG, "ub200_results_download: nothing to download");
+    CU(cudaSetDevice(M->device));
+    CU(cudaMemcpyAsync(out, S->results, (size_t)S->n_samples * sizeof(ub200_placement), cudaMemcpyDeviceToHost, M->stream));
+    CU(cudaStreamSynchronize(M->stream));
+    return UB200_OK;
+}
+
+int ub200_results_device_ptr(ub200_samples* S, void** p, size_t* bytes) {
+    if (!S || !p) return fail(UB200_E_ARG, "ub200_results_device_ptr: NULL argument");
+    *p = S->results;
+    if (bytes) *bytes = (size_t)S->n_samples * sizeof(ub200_placement);
+    return UB200_OK;
+}
+
+int ub200_node_scores_download(ub200_mat* M, ub200_samples* S, int32_t* out) {
+    if (!M || !S || !out || !S->have_node_scores) return fail(UB200_E_ARG, "node scores were not requested");
+    CU(cudaSetDevice(M->device));
+    CU(cudaMemcpyAsync(out, S->node_scores, (size_t)S->n_samples * M->n * 4, cudaMemcpyDeviceToHost, M->stream));
+    CU(cudaStreamSynchronize(M->stream));
+    return UB200_OK;
+}
+
+int ub200_best_set_download(ub200_mat* M, ub200_samples* S, uint32_t* best_set, uint64_t* best_set_ptr, uint64_t cap) {
+    if (!M || !S || !best_set_ptr || !S->have_set) return fail(UB200_E_ARG, "best set was not requested");
+    CU(cudaSetDevice(M->device));
+    CU(cudaMemcpyAsync(best_set_ptr, S->set_ptr, ((size_t)S->n_samples + 1) * 8, cudaMemcpyDeviceToHost, M->stream));
+    CU(cudaStreamSynchronize(M->stream));
+    if (S->set_total > cap || !best_set) return fail(UB200_E_CAPACITY, "best_set capacity too small");
+    CU(cudaMemcpyAsync(best_set, S->set_out, (size_t)S->set_total * 4, cudaMemcpyDeviceToHost, M->stream));
+    CU(cudaStreamSynchronize(M->stream));
+    // ascending DFS index within each sample (bit 31 carries node_has_unique)
+    for (uint32_t s = 0; s < S->n_samples; s++)
+        std::sort(best_set + best_set_ptr[s], best_set + best_set_ptr[s + 1],
+                  [](uint32_t a, uint32_t b) { return (a & 0x7fffffffu) < (b & 0x7fffffffu); });
+    return UB200_OK;
+}
+
+int ub200_place_batch(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_ptr, const ub200_mutation* calls,
+                      uint32_t flags, ub200_placement* out, int32_t* node_scores, uint32_t* best_set,
+                      uint64_t* best_set_ptr, uint64_t best_set_cap) {
+    if (!M || !out || !sample_ptr) return fail(UB200_E_ARG, "ub200_place_batch: NULL argument");
+    if ((flags & UB200_WANT_NODE_SCORES) && !node_scores) return fail(UB200_E_ARG, "node_scores is NULL");
+    if ((flags & UB200_WANT_BEST_SET) && !best_set_ptr) return fail(UB200_E_ARG, "best_set_ptr is NULL");
+    if (n_samples == 0) { if (best_set_ptr) best_set_ptr[0] = 0; return UB200_OK; }
+    // sub-batches bounded by the resident table size
+    const size_t per_group = (size_t)M->L * 32;
+    uint32_t max_groups = (uint32_t)std::max<size_t>(1, ((size_t)4 << 30) / std::max<size_t>(per_group, 1));
+    const uint32_t step = max_groups * 32;
+    uint64_t set_off = 0;
+    bool overflow = false;
+    if (best_set_ptr) best_set_ptr[0] = 0;
+    float prep = 0, sc = 0, rd = 0;
+    ub200_timing acc = {};
+    for (uint32_t s0 = 0; s0 < n_samples; s0 += step) {
+        const uint32_t ns = std::min(step, n_samples - s0);
+        std::vector<uint64_t> ptr(ns + 1);
+        for (uint32_t i = 0; i <= ns; i++) ptr[i] = sample_ptr[s0 + i] - sample_ptr[s0];
+        ub200_samples* S = nullptr;
+        int rc = ub200_samples_upload(M, ns, ptr.data(), calls ? calls + sample_ptr[s0] : nullptr, &S);
+        if (rc) return rc;
+        rc = ub200_place_resident(M, S, overflow ? (flags & ~UB200_WANT_BEST_SET) : flags, 0);
+        if (!rc) rc = ub200_results_download(M, S, out + s0);
+        if (!rc && (flags & UB200_WANT_NODE_SCORES)) rc = ub200_node_scores_download(M, S, node_scores + (size_t)s0 * M->n);
+        if (!rc && (flags & UB200_WANT_BEST_SET) && !overflow) {
+            std::vector<uint64_t> lp(ns + 1);
+            rc = ub200_best_set_download(M, S, best_set ? best_set + set_off : nullptr, lp.data(),
+                                         best_set_cap > set_off ? best_set_cap - set_off : 0);
+            if (rc == UB200_E_CAPACITY) { overflow = true; rc = 0; }
+            else if (!rc) {
+                for (uint32_t i = 1; i <= ns; i++) best_set_ptr[s0 + i] = set_off + lp[i];
+                set_off += lp[ns];
+            }
+        }
+        ub200_timing t;
+        if (!rc && ub200_last_timing(M, &t) == UB200_OK) {
+            prep += t.prep_ms; sc += t.score_ms; rd += t.reduce_ms;
+            acc.score_launches += t.score_launches; acc.total_launches += t.total_launches;
+            acc.score_bytes += t.score_bytes;
+        }
+        ub200_samples_free(S);
+        if (rc) return rc;
+    }
+    if (overflow) {
+        // every out[] record is valid; the required capacity is the sum of num_best
+        uint64_t need = 0;
+        for (uint32_t i = 0; i < n_samples; i++) need += out[i].num_best;
+        best_set_ptr[n_samples] = need;
+        return fail(UB200_E_CAPACITY, "best_set capacity too small: need " + std::to_string(need));
+    }
+    acc.prep_ms = prep; acc.score_ms = sc; acc.reduce_ms = rd;
+    M->last = acc;
+    M->spans.clear();
+    return UB200_OK;
+}
+
+}  // extern "C"

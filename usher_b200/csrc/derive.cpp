@@ -1,0 +1,258 @@
+// Host-side derivation: caller's flat MAT (include/usher_b200.h) -> the SoA the scoring kernel streams.
+//
+// What is precomputed here is exactly the sample-INDEPENDENT part of mapper2_body
+// (reference src/usher_mapper.cpp:167-504), i.e. its result for a sample that carries no call at any
+// position of the node's root path:
+//   * prev(m): the true path state just above the branch at m's position (what the reference finds by
+//     walking parents and keeping the most recent mutation per position, :275-286);
+//   * Dref(n): number of path positions whose state differs from the reference allele = what LOOP 3
+//     (:393-445) counts for such a sample;
+//   * A0(n), c0(n): LOOP 1 (:190-264) outcome for such a sample: a branch mutation is "common" iff it
+//     mutates back to the reference allele (:244-259); A0 = how many of those undo a non-reference state;
+//   * valid0(n): the placement-validity predicate (:454-455) for such a sample;
+//   * tiekey(n): total order of the tie-break (:483-486): more leaves first, then larger index j;
+//   * num_leaves (mutation_annotated_tree.cpp:866-879), BFS index (:1225-1251), level.
+// The kernel then only has to correct these for the few mutations that hit a position the sample calls.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "ub200_internal.h"
+
+namespace ub200 {
+
+int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::string& err) {
+    const uint32_t n = f.n_nodes;
+    if (n == 0 || !f.parent || !f.row_ptr || (f.n_mutations && !f.mutations)) {
+        err = "flat MAT: empty tree or NULL array";
+        return UB200_E_ARG;
+    }
+    if (n >= (1u << 31)) { err = "flat MAT: more than 2^31-1 nodes"; return UB200_E_LIMIT; }
+    if (f.row_ptr[0] != 0 || f.row_ptr[n] != f.n_mutations) {
+        err = "flat MAT: row_ptr does not span [0, n_mutations]";
+        return UB200_E_ARG;
+    }
+    d.n = n;
+    // ---- topology checks: DFS pre-order <=> parent[i] lies on the root path of node i-1
+    d.level.assign(n, 0);
+    if (f.parent[0] != -1) { err = "flat MAT: node 0 must be the root (parent -1)"; return UB200_E_TREE_ORDER; }
+    {
+        std::vector<uint32_t> path;
+        path.push_back(0);
+        for (uint32_t i = 1; i < n; i++) {
+            int32_t p = f.parent[i];
+            if (p < 0 || (uint32_t)p >= i) {
+                err = "flat MAT: parent[" + std::to_string(i) + "] is not an earlier node";
+                return UB200_E_TREE_ORDER;
+            }
+            while (!path.empty() && path.back() != (uint32_t)p) path.pop_back();
+            if (path.empty()) {
+                err = "flat MAT: nodes are not in DFS pre-order at node " + std::to_string(i);
+                return UB200_E_TREE_ORDER;
+            }
+            d.level[i] = d.level[p] + 1;
+            if (d.level[i] > kMaxLevel) { err = "flat MAT: tree deeper than 2^24-1"; return UB200_E_LIMIT; }
+            path.push_back(i);
+        }
+    }
+    d.max_level = *std::max_element(d.level.begin(), d.level.end());
+    // ---- leaves, leaf counts (reverse sweep), BFS index
+    std::vector<uint32_t> nchild(n + 1, 0);
+    for (uint32_t i = 1; i < n; i++) nchild[f.parent[i] + 1]++;
+    d.num_leaves.assign(n, 0);
+    for (uint32_t i = n; i-- > 0;) {
+        if (nchild[i + 1] == 0) d.num_leaves[i] = 1;
+        if (i) d.num_leaves[f.parent[i]] += d.num_leaves[i];
+    }
+    d.tie_index.resize(n);
+    if (f.tie_index) {
+        std::memcpy(d.tie_index.data(), f.tie_index, sizeof(uint32_t) * n);
+    } else {
+        std::vector<uint32_t> off(nchild);
+        for (uint32_t i = 0; i < n; i++) off[i + 1] += off[i];
+        std::vector<uint32_t> kids(n > 1 ? n - 1 : 1), fill(off.begin(), off.end() - 1);
+        for (uint32_t i = 1; i < n; i++) kids[fill[f.parent[i]]++] = i;
+        std::vector<uint32_t> q(n);
+        uint32_t head = 0, tail = 0;
+        q[tail++] = 0;
+        while (head < tail) {
+            uint32_t u = q[head];
+            d.tie_index[u] = head++;
+            for (uint32_t k = off[u]; k < off[u + 1]; k++) q[tail++] = kids[k];
+        }
+    }
+    // ---- tie-break order: preferred = more leaves, then larger j  -> tiekey 0 is the most preferred
+    {
+        std::vector<uint64_t> keys(n);
+        for (uint32_t i = 0; i < n; i++) keys[i] = ((uint64_t)d.num_leaves[i] << 32) | d.tie_index[i];
+        std::vector<uint32_t> ord(n);
+        std::iota(ord.begin(), ord.end(), 0u);
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+            return keys[a] != keys[b] ? keys[a] > keys[b] : a < b;
+        });
+        d.tiekey.resize(n);
+        d.key_to_node = ord;
+        for (uint32_t r = 0; r < n; r++) d.tiekey[ord[r]] = r;
+    }
+    // ---- mutation checks, genome extent
+    int64_t maxpos = 0;
+    uint64_t kept = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (f.row_ptr[i + 1] < f.row_ptr[i]) { err = "flat MAT: row_ptr not monotone"; return UB200_E_ARG; }
+        int32_t last = INT32_MIN;
+        uint64_t row_kept = 0;
+        for (uint64_t k = f.row_ptr[i]; k < f.row_ptr[i + 1]; k++) {
+            const ub200_mutation& m = f.mutations[k];
+            if (m.position < last) {
+                err = "flat MAT: row " + std::to_string(i) + " is not position-sorted";
+                return UB200_E_POSITION;
+            }
+            if (m.position >= 0 && m.position == last) {
+                err = "flat MAT: row " + std::to_string(i) + " repeats position " + std::to_string(last);
+                return UB200_E_POSITION;
+            }
+            last = m.position;
+            if (m.position < 0) continue;
+            if ((uint32_t)m.position > kMaxPos) { err = "flat MAT: position >= 2^26-1"; return UB200_E_POSITION; }
+            if (nuc_code(m.mut_nuc) < 0 || nuc_code(m.ref_nuc) < 0) {
+                err = "flat MAT: node " + std::to_string(i) + " position " + std::to_string(m.position) +
+                      " has a non-one-hot ref/mut nucleotide";
+                return UB200_E_NOT_ONE_HOT;
+            }
+            maxpos = std::max<int64_t>(maxpos, m.position);
+            row_kept++;
+        }
+        if (row_kept > kMaxRow) { err = "flat MAT: a branch with more than 65534 mutations"; return UB200_E_LIMIT; }
+        kept += row_kept;
+    }
+    if (kept >= (1ull << 32) - kMutChunk) { err = "flat MAT: more than 2^32 mutations"; return UB200_E_LIMIT; }
+    d.m = kept;
+    d.L = (uint32_t)maxpos + 1;
+    d.ref_of.assign(d.L, 0);
+    d.root_init_extra = (int32_t)(f.row_ptr[1] - f.row_ptr[0]);
+
+    // ---- one DFS with a live state array
+    d.row32.assign((size_t)n + 1, 0);
+    d.mutw.assign(((kept + kMutChunk - 1) / kMutChunk + 1) * kMutChunk, 0);
+    d.hdr.assign(((size_t)n + kHdrChunk - 1) / kHdrChunk * kHdrChunk + kHdrChunk, NodeHdr{0, 0, 0, 0});
+    std::vector<uint8_t> state(d.L, 0);  // 0 = never mutated on the current path, else one-hot
+    std::vector<int32_t> dref(n, 0);
+    struct Undo { uint32_t node; uint32_t pos; uint8_t old; };
+    std::vector<Undo> undo;
+    std::vector<uint32_t> path;
+    uint64_t w = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        while (!path.empty() && (int32_t)path.back() != f.parent[i]) {
+            uint32_t top = path.back();
+            path.pop_back();
+            while (!undo.empty() && undo.back().node == top) {
+                state[undo.back().pos] = undo.back().old;
+                undo.pop_back();
+            }
+        }
+        const bool is_root = (i == 0);
+        const bool leaf = nchild[i + 1] == 0;
+        bool masked = false;
+        int32_t dd = 0, a0 = 0;
+        uint32_t c0 = 0, nm = 0;
+        d.row32[i] = (uint32_t)w;
+        for (uint64_t k = f.row_ptr[i]; k < f.row_ptr[i + 1]; k++) {
+            const ub200_mutation& m = f.mutations[k];
+            if (m.position < 0) { masked = true; continue; }
+            const uint32_t pos = (uint32_t)m.position;
+            if (d.ref_of[pos] == 0) d.ref_of[pos] = m.ref_nuc;
+            else if (d.ref_of[pos] != m.ref_nuc) {
+                err = "flat MAT: tree mutations disagree on the reference allele at position " + std::to_string(pos);
+                return UB200_E_ARG;
+            }
+            const uint8_t prev = state[pos] ? state[pos] : m.ref_nuc;
+            const int rp = prev != m.ref_nuc, rm = m.mut_nuc != m.ref_nuc;
+            dd += rm - rp;
+            if (!rm) { c0++; a0 += rp; }   // LOOP 1 for an absent position: common iff back to ref (:244-259)
+            d.mutw[w++] = pack_mut(pos, (uint32_t)nuc_code(m.ref_nuc), (uint32_t)nuc_code(prev),
+                                   (uint32_t)nuc_code(m.mut_nuc));
+            undo.push_back({i, pos, state[pos]});
+            state[pos] = m.mut_nuc;
+            nm++;
+        }
+        const int32_t dpar = is_root ? 0 : dref[f.parent[i]];
+        dref[i] = dpar + dd;
+        if (masked || is_root) { a0 = 0; c0 = 0; }  // masked: LOOP 1 breaks before taking anything (:197-200)
+        const bool hu0 = masked || (nm > c0);
+        const bool valid0 = is_root || (leaf ? c0 > 0 : (!hu0 || c0 > 0));
+        NodeHdr h;
+        h.g = is_root ? dref[i] : dpar - a0;
+        h.tiekey = d.tiekey[i];
+        h.level_flags = (d.level[i] << 8) | (leaf ? kFlagLeaf : 0) | (masked ? kFlagMasked : 0) |
+                        (is_root ? kFlagRoot : 0) | (valid0 ? kFlagValid0 : 0);
+        h.nmut_c0 = (nm << 16) | c0;
+        d.hdr[i] = h;
+        path.push_back(i);
+    }
+    d.row32[n] = (uint32_t)w;
+
+    // ---- tiles: contiguous DFS ranges of roughly equal cost (mutations + per-node overhead)
+    {
+        const uint64_t node_cost = 4;
+        const uint64_t total = kept + node_cost * n;
+        uint64_t per = total / (target_tiles ? target_tiles : 1);
+        per = std::min<uint64_t>(std::max<uint64_t>(per, 1024), 1u << 16);
+        d.tile_start.clear();
+        d.tile_start.push_back(0);
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            acc += (d.row32[i + 1] - d.row32[i]) + node_cost;
+            if (acc >= per && i + 1 < n) {
+                d.tile_start.push_back(i + 1);
+                acc = 0;
+            }
+        }
+        d.tile_start.push_back(n);
+        const size_t T = d.tile_start.size() - 1;
+        d.anc_ptr.assign(T + 1, 0);
+        d.anc.clear();
+        std::vector<uint32_t> chain;
+        for (size_t t = 0; t < T; t++) {
+            chain.clear();
+            for (int32_t a = f.parent[d.tile_start[t]]; a >= 0; a = f.parent[a]) chain.push_back((uint32_t)a);
+            d.anc.insert(d.anc.end(), chain.rbegin(), chain.rend());
+            d.anc_ptr[t + 1] = (uint32_t)d.anc.size();
+        }
+    }
+    return UB200_OK;
+}
+
+}  // namespace ub200
+
+// ---- host-only inspection hooks (used by the CPU test-suite to check the derivation without a GPU) ----
+extern "C" {
+
+struct ub200_derived_view {
+    uint32_t n_nodes, genome_len, max_level, n_tiles;
+    uint64_t n_mutations;
+    const uint32_t* level; const uint32_t* tie_index; const uint32_t* num_leaves; const uint32_t* tiekey;
+    const uint32_t* key_to_node; const uint32_t* row32; const uint32_t* mutw; const void* hdr;
+    const uint8_t* ref_of; const uint32_t* tile_start; const uint32_t* anc_ptr; const uint32_t* anc;
+};
+
+int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, void** handle, ub200_derived_view* view,
+                       char* errbuf, size_t errlen) {
+    auto* d = new ub200::Derived();
+    std::string err;
+    int rc = ub200::derive(*flat, target_tiles, *d, err);
+    if (rc != UB200_OK) {
+        if (errbuf && errlen) { std::strncpy(errbuf, err.c_str(), errlen - 1); errbuf[errlen - 1] = 0; }
+        delete d;
+        return rc;
+    }
+    view->n_nodes = d->n; view->genome_len = d->L; view->max_level = d->max_level;
+    view->n_tiles = (uint32_t)d->tile_start.size() - 1; view->n_mutations = d->m;
+    view->level = d->level.data(); view->tie_index = d->tie_index.data(); view->num_leaves = d->num_leaves.data();
+    view->tiekey = d->tiekey.data(); view->key_to_node = d->key_to_node.data(); view->row32 = d->row32.data();
+    view->mutw = d->mutw.data(); view->hdr = d->hdr.data(); view->ref_of = d->ref_of.data();
+    view->tile_start = d->tile_start.data(); view->anc_ptr = d->anc_ptr.data(); view->anc = d->anc.data();
+    *handle = d;
+    return UB200_OK;
+}
+void ub200_debug_derive_free(void* handle) { delete (ub200::Derived*)handle; }
+}

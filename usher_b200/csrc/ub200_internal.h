@@ -1,0 +1,81 @@
+// Internal layout shared by the host-side derivation (derive.cpp), the kernels (score_kernel.cu) and the
+// C-ABI glue (api.cu).  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "usher_b200.h"
+
+#ifdef __CUDACC__
+#define UB200_HD __host__ __device__
+#else
+#define UB200_HD
+#endif
+
+namespace ub200 {
+
+// ---- packed tree mutation: pos:26 | ref:2 | prev:2 | mut:2 (nucleotide codes = log2 of the one-hot) ----
+constexpr uint32_t kPosBits = 26;
+constexpr uint32_t kMaxPos = (1u << kPosBits) - 2;  // positions are < 2^26-1
+UB200_HD inline uint32_t pack_mut(uint32_t pos, uint32_t refc, uint32_t prevc, uint32_t mutc) {
+    return (pos << 6) | (refc << 4) | (prevc << 2) | mutc;
+}
+
+// ---- per-node header (16 B) ----
+//   x = G        : int32  Dref(parent) - A0(node)      (root: Dref(root))
+//   y = tiekey   : uint32 N-1-rank of (num_leaves, tie_index): smaller = preferred on equal score
+//   z = level<<8 | flags
+//   w = nmut<<16 | c0   (unmasked row length, number of row mutations that are "common" with a sample
+//                        lacking every position of the row; both < 65535)
+constexpr uint32_t kFlagLeaf = 1u;
+constexpr uint32_t kFlagMasked = 2u;   // row holds a masked mutation: LOOP 1 takes nothing (usher_mapper.cpp:197-200)
+constexpr uint32_t kFlagRoot = 4u;
+constexpr uint32_t kFlagValid0 = 8u;   // validity predicate for a sample that hits no position of the row
+constexpr uint32_t kMaxRow = 65534;
+constexpr uint32_t kMaxLevel = (1u << 24) - 1;
+
+struct NodeHdr {
+    int32_t g;
+    uint32_t tiekey;
+    uint32_t level_flags;
+    uint32_t nmut_c0;
+};
+static_assert(sizeof(NodeHdr) == 16, "header must be 16 bytes");
+
+// ring geometry of the scoring kernel (absolute-aligned chunks)
+constexpr uint32_t kMutChunk = 256;   // mutation words per bulk copy (1 KB)
+constexpr uint32_t kHdrChunk = 32;    // headers per bulk copy (512 B)
+
+struct Derived {
+    uint32_t n = 0;
+    uint64_t m = 0;          // unmasked mutations kept on the device
+    uint32_t L = 0;          // 1 + largest tree position
+    uint32_t max_level = 0;
+    std::vector<uint32_t> level, tie_index, num_leaves, tiekey, key_to_node;
+    std::vector<uint32_t> row32;      // [n+1] offsets into mutw
+    std::vector<uint32_t> mutw;       // padded to kMutChunk
+    std::vector<NodeHdr> hdr;         // padded to kHdrChunk
+    std::vector<uint8_t> ref_of;      // [L] one-hot reference allele where the tree mutates, else 0
+    // tiles = contiguous DFS ranges; anc = root..parent chain of each tile's first node
+    std::vector<uint32_t> tile_start; // [T+1]
+    std::vector<uint32_t> anc_ptr;    // [T+1]
+    std::vector<uint32_t> anc;        // node ids, root first
+    int32_t root_init_extra = 0;      // |root row| (incl. masked) for the reference's initial bound
+};
+
+// Validate the caller's flat tree and derive everything the kernels need.  Returns UB200_* status and
+// fills err on failure.
+int derive(const ub200_flat_mat& flat, uint32_t target_tiles, Derived& out, std::string& err);
+
+inline int nuc_code(uint8_t one_hot) {
+    switch (one_hot) {
+        case 1: return 0;
+        case 2: return 1;
+        case 4: return 2;
+        case 8: return 3;
+        default: return -1;
+    }
+}
+
+}  // namespace ub200

@@ -503,7 +503,7 @@ int ub200_place_batch(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_p
     if (n_samples == 0) { if (best_set_ptr) best_set_ptr[0] = 0; return UB200_OK; }
     // sub-batches bounded by the resident table size
     const size_t per_group = (size_t)M->L * 32;
-    uint32_t max_groups = (uint32_t)std::max<size_t>(1, ((size_t)4 << 30) / std::max<size_t>(per_group, 1));
+    uint32_t max_groups = (uint32_t)std::min<size_t>(1u << 16, std::max<size_t>(1, ((size_t)4 << 30) / std::max<size_t>(per_group, 1)));
     const uint32_t step = max_groups * 32;
     uint64_t set_off = 0;
     bool overflow = false;

@@ -73,18 +73,25 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug must trap (-> CUDA error through the C ABI), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA unit, no tensor map)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
                 hc_wait = hc + 1;
                 // the previous chunk's stage is now free: refill it
                 if (hc_issue < hc_end && hc_issue < hc + kHdrStages) {
+                    __syncwarp();   // every lane is done with the chunk whose stage is refilled
                     if (lane == 0) {
                         const uint32_t c = hc_issue, s2 = c % kHdrStages;
                         mbar_expect_tx(bars_a + 8 * (kMutStages + s2), kHdrChunk * 16);

@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — sample placements/sec of the placement hot path on the BASELINE.json workload.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; N>1 under torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU path, rank 0 only)
+
+Workload (config.workload = "c4"): synthetic 10M-node MAT, ~30 mutations/node, 30 kb genome
+(G(1e7, 30, 30000, uniform, seed 20260929)); samples = the "40-SNV" family of config 2/4.
+A step = every rank places `samples_per_rank` fresh samples against the whole tree (weak scaling: the per-GPU
+batch is fixed; at 8 GPUs one step is the 10k-sample job of BASELINE config 4), followed by ONE NCCL
+allgather of the 32-byte per-sample records.  `value` times the steps with the samples' calls already
+resident in HBM; `e2e` times the same steps through ub200_place_batch with HOST (pinned) buffers, H2D and
+D2H inside the timed region.  The tree (1.36 GB) is far larger than L2 (126 MB), so no L2 flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nodes, mu, genome_len, shape, seed, family)
+    "c4": (10_000_000, 30.0, 30_000, 0, 20260929, 0),
+    "c2": (100_000, 30.0, 30_000, 0, 20260927, 0),
+    "c3": (2_000_000, 1.2, 29_903, 1, 20260928, 1),
+    "mid": (2_000_000, 30.0, 30_000, 0, 20260930, 0),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (profiling guide recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for t, line in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def usable_cpus():
+    """CPUs this process may really use: affinity mask, capped by the cgroup quota (os.cpu_count() reports the
+    host's cores, which oversubscribes a quota-limited container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_rate(synth, calls_list, threads, target_seconds, log_prefix):
+    """Time the reference's own mapper2_body search (oracle/_ref) on this host's cores.
+    Returns (placements_per_s, description)."""
+    from oracle import ref
+    if not ref.available():
+        raise RuntimeError("oracle/_ref/libusher_ref.so missing")
+    p, r, m = synth.arrays()
+    t = time.time()
+    rt = ref.RefTree.from_flat(p, r, m)
+    log(f"{log_prefix} reference MAT::Tree built in {time.time() - t:.1f}s")
+    n = len(p)
+    # calibrate: a thin slice first, then pick the stride that fits the budget
+    sec, _ = rt.search_strided(calls_list[0], 256, 0, threads)
+    est_full = sec * 256
+    stride = 1
+    while est_full / stride > target_seconds and stride < 256:
+        stride *= 2
+    return rt, stride, est_full, n
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's TBB-style CPU search (verbatim mapper2_body) on the host cores."""
+    if rank != 0:
+        return
+    from usher_b200 import capi
+    nodes, mu, L, shape, seed, fam = WORKLOADS[wl]
+    threads = usable_cpus()
+    t = time.time()
+    synth = capi.Synth(nodes, mu, L, shape, seed)
+    log(f"[ref] synthetic MAT: {nodes} nodes, {synth.m} mutations in {time.time() - t:.1f}s")
+    sp, sc, _ = synth.samples(args.steps + args.warmup, fam, 777)
+    calls = [sc[int(sp[i]):int(sp[i + 1])] for i in range(args.steps + args.warmup)]
+    rt, stride, est_full, n = cpu_reference_rate(synth, calls, threads, 3.0, "[ref]")
+    log(f"[ref] one full search ~{est_full:.1f}s on {threads} threads -> stride {stride}")
+    for i in range(args.warmup):
+        rt.search_strided(calls[i], stride, 0, threads)
+    t0 = time.time()
+    tot = 0.0
+    for i in range(args.steps):
+        sec, _ = rt.search_strided(calls[args.warmup + i], stride, i % stride, threads)
+        tot += sec
+    wall = time.time() - t0
+    per_sample = (tot / args.steps) * stride
+    value = 1.0 / per_sample
+    sample = (f"{args.steps} samples x every {stride}-th BFS node of the {n}-node tree, two-pass search "
+              f"(usher_common.cpp:389-449), seconds x {stride}" if stride > 1 else
+              f"{args.steps} full two-pass searches of the {n}-node tree")
+    line = {
+        "impl": "reference", "metric": "sample placements/sec", "value": value, "unit": "placements/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": wl, "nodes": nodes, "mutations": int(synth.m), "genome_len": L,
+                   "sample_family": "snv40" if fam == 0 else "leaf", "threading": "std::thread shim of tbb::parallel_for"},
+        "cpu_baseline": {"value": value, "unit": "placements/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("UB200_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
+    ap.add_argument("--samples-per-rank", type=int, default=1280)
+    ap.add_argument("--pass-samples", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = args.workload
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from usher_b200 import capi
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    nodes, mu, L, shape, seed, fam = WORKLOADS[wl]
+    t = time.time()
+    synth = capi.Synth(nodes, mu, L, shape, seed)
+    t_gen = time.time() - t
+    t = time.time()
+    mat = capi.Mat.from_flat_struct(synth.flat, device=local_rank)
+    t_create = time.time() - t
+    mat.set_pass_samples(args.pass_samples)
+    stream = torch.cuda.current_stream()
+    mat.set_stream(stream.cuda_stream)
+    if rank == 0:
+        log(f"[bench] {wl}: {nodes} nodes, {synth.m} mutations; generate {t_gen:.1f}s, flatten+upload {t_create:.1f}s, "
+            f"{mat.info.n_tiles} tiles, depth {mat.info.max_level}, MAT {mat.info.algorithmic_bytes / 1e9:.3f} GB")
+
+    B = args.samples_per_rank
+    nsteps = args.warmup + args.steps
+    # fresh samples every step, distinct per rank
+    batches = [synth.samples(B, fam, 1_000_003 * (rank + 1) + i) for i in range(nsteps)]
+    rec_words = capi.PLACEMENT_DTYPE.itemsize // 4
+    local = torch.empty(B * rec_words, dtype=torch.int32, device=dev)
+    gathered = torch.empty(world * B * rec_words, dtype=torch.int32, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return float(tt.item())
+
+    # ------------------------------------------------------------------ resident-input timing ("value")
+    resident = [mat.upload(sp, sc) for sp, sc, _ in batches]
+
+    def step_resident(i):
+        S = resident[i]
+        S.place(0, sync=False)
+        S.copy_results_to(local.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    score_ms = prep_ms = reduce_ms = 0.0
+    score_bytes = launches = score_launches = 0
+    tw0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+        # per-step kernel timings come from CUDA events the library recorded on this same stream
+        tm = mat.timing()   # synchronises the stream: the kernels of this step are done
+        score_ms += tm.score_ms; prep_ms += tm.prep_ms; reduce_ms += tm.reduce_ms
+        score_bytes += tm.score_bytes; launches += tm.total_launches; score_launches += tm.score_launches
+    ev1.record()
+    barrier()
+    tw1 = time.time()
+    clocks = sampler.stop(tw0, tw1)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    value = world * B * args.steps / (ms_total / 1000.0)
+    total_launches = sum_over_ranks(launches)
+
+    # parity spot check against an independent launch path (host-buffer API) on the last batch
+    sp, sc, _ = batches[-1]
+    chk = mat.place_batch(sp, sc)["placements"]
+    got = np.frombuffer(local.cpu().numpy().tobytes(), dtype=capi.PLACEMENT_DTYPE)
+    assert np.array_equal(chk, got), "resident and host-buffer paths disagree"
+
+    # ------------------------------------------------------------------ end-to-end timing ("e2e")
+    pinned = []
+    for sp, sc, _ in batches:
+        tp = torch.from_numpy(sp.view(np.int64).copy()).pin_memory()
+        tc = torch.from_numpy(sc.view(np.int64).copy()).pin_memory()
+        pinned.append((tp, tc))
+    out_host = torch.empty(B * rec_words, dtype=torch.int32).pin_memory()
+    lib = capi.lib()
+    h2d = d2h = 0
+
+    def step_e2e(i):
+        tp, tc = pinned[i]
+        rc = lib.ub200_place_batch(mat.h, B, tp.data_ptr(), tc.data_ptr(), 0, out_host.data_ptr(), None, None, None, 0)
+        if rc != 0:
+            raise RuntimeError(lib.ub200_last_error().decode())
+        if world > 1:
+            local.copy_(out_host, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, local)
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.time()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+        tp, tc = pinned[args.warmup + i]
+        h2d += tp.numel() * 8 + tc.numel() * 8 + tc.numel() * 4   # sample_ptr + calls + call->sample index
+        d2h += B * capi.PLACEMENT_DTYPE.itemsize
+    barrier()
+    e2e_s = max_over_ranks(time.time() - t0)
+    e2e_value = world * B * args.steps / e2e_s
+
+    # ------------------------------------------------------------------ roofline of the scoring kernel
+    peak, peak_src = measured_peak()
+    achieved = (score_bytes / 1e9) / (score_ms / 1000.0) if score_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(wl)
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "kernel": "ub200::k_score<0,true>", "peak_source": peak_src,
+        "bytes_per_launch": int(mat.info.algorithmic_bytes), "launches": int(score_launches),
+        "us_per_launch": 1000.0 * score_ms / max(score_launches, 1),
+        "share_of_step": score_ms / (ev0.elapsed_time(ev1)) if ms_total > 0 else None,
+        "prep_ms": prep_ms, "reduce_ms": reduce_ms, "score_ms": score_ms,
+    }
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = usable_cpus()
+            calls = [batches[0][1][int(batches[0][0][i]):int(batches[0][0][i + 1])] for i in range(2)]
+            rt, stride, est_full, n = cpu_reference_rate(synth, calls, threads, 8.0, "[bench]")
+            secs = [rt.search_strided(c, stride, 0, threads)[0] * stride for c in calls]
+            v = 1.0 / float(np.mean(secs))
+            cpu = {"value": v, "unit": "placements/s", "cores": threads, "kind": "reference",
+                   "sample": f"{len(calls)} samples x every {stride}-th BFS node of the {n}-node tree, reference two-pass "
+                             f"search (verbatim mapper2_body, std::thread shim of tbb::parallel_for), seconds x {stride}"}
+            rt.close()
+        except Exception as e:  # the baseline is reported, never required for the GPU numbers
+            cpu = {"value": None, "unit": "placements/s", "cores": os.cpu_count(), "kind": "reference",
+                   "sample": f"unavailable: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": "sample placements/sec", "value": value, "unit": "placements/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": wl, "nodes": nodes, "mutations": int(synth.m), "genome_len": L,
+                       "sample_family": "snv40" if fam == 0 else "leaf", "samples_per_rank_per_step": B,
+                       "samples_per_launch": args.pass_samples, "parallelism": f"samples sharded x{world}, 1 allgather/step",
+                       "l2": "inputs (%.2f GB MAT) exceed the 126 MB L2; no flush needed" % (mat.info.algorithmic_bytes / 1e9)},
+            "e2e": {"value": e2e_value, "unit": "placements/s", "h2d_bytes_per_step": int(h2d / args.steps),
+                    "d2h_bytes_per_step": int(d2h / args.steps)},
+            "gpu_launches": int(total_launches),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,9 @@ int ub200_place_resident(ub200_mat* mat, ub200_samples* s, uint32_t flags, int s
 int ub200_results_download(ub200_mat* mat, ub200_samples* s, ub200_placement* out);
 /* Device pointer to the n_samples ub200_placement records of a resident batch (for a collective on them). */
 int ub200_results_device_ptr(ub200_samples* s, void** dev_ptr, size_t* bytes);
+/* Device-to-device copy of the n_samples result records into caller-owned device memory, ordered on the
+ * handle's stream (e.g. straight into the send buffer of an allgather). */
+int ub200_results_copy_device(ub200_mat* mat, ub200_samples* s, void* dst_dev);
 int ub200_node_scores_download(ub200_mat* mat, ub200_samples* s, int32_t* node_scores);
 int ub200_best_set_download(ub200_mat* mat, ub200_samples* s, uint32_t* best_set, uint64_t* best_set_ptr,
                             uint64_t best_set_cap);

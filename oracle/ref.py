@@ -48,6 +48,8 @@ def lib():
         L.usher_ref_usher_common.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
         L.usher_ref_search.restype = C.c_int
         L.usher_ref_search.argtypes = [vp, u32, vp, vp, C.c_int, C.c_int] + [vp] * 9 + [u64, vp]
+        L.usher_ref_search_strided.restype = C.c_double
+        L.usher_ref_search_strided.argtypes = [vp, u64, vp, u32, u32, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -111,6 +113,13 @@ class RefTree:
         return lib().usher_ref_usher_common(
             self.h, outdir.encode(), threads, int(print_parsimony_scores), int(no_add)
         )
+
+    def search_strided(self, calls, stride, offset=0, threads=1):
+        """Seconds the reference's two-pass search of one sample takes over every `stride`-th BFS node."""
+        calls = np.ascontiguousarray(calls, dtype=MUT_DTYPE)
+        best = C.c_int32()
+        sec = lib().usher_ref_search_strided(self.h, len(calls), _p(calls), stride, offset, threads, C.byref(best))
+        return float(sec), int(best.value)
 
     def search(self, s_ptr, sm, n_nodes, threads=1, per_node=False, want_set=True, set_cap=None):
         """Reference two-pass search (or -p single pass when per_node) of each sample on the frozen tree."""

@@ -88,9 +88,9 @@ void* usher_ref_tree_from_flat(uint32_t n_nodes, const int32_t* parent, const ui
         if (parent[i] < 0) nodes[i] = h->T.create_node(id, -1.0f, 0);
         else nodes[i] = h->T.create_node(id, nodes[parent[i]], -1.0f);
         auto& v = nodes[i]->mutations;
+        v.reserve((size_t)(row_ptr[i + 1] - row_ptr[i]));
         for (uint64_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
             MAT::Mutation m;
-            m.chrom = "c";
             m.position = muts[k].position;
             m.ref_nuc = (int8_t)muts[k].ref_nuc;
             m.par_nuc = (int8_t)muts[k].par_nuc;
@@ -330,6 +330,80 @@ int usher_ref_search(void* hv, uint32_t n_samples, const uint64_t* s_ptr, const 
         }
     }
     return set_fill > best_set_cap && best_set ? 1 : 0;
+}
+
+// Timing aid for trees where one full search is minutes of CPU: run the reference's two-pass search of ONE
+// sample over every `stride`-th BFS node (k = offset, offset+stride, ...) with `threads` workers and return
+// the seconds spent.  mapper2_body's cost per node does not depend on which other nodes are visited (its
+// work before the early-exit tests is the ancestor gather), so seconds*stride estimates the full search.
+double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, uint32_t stride, uint32_t offset,
+                                int threads, int32_t* best_score_seen) {
+    auto* h = (RefTree*)hv;
+    MAT::Tree* T = &h->T;
+    tbb::oracle_threads = threads < 1 ? 1 : threads;
+    std::vector<MAT::Mutation> sample;
+    for (uint64_t k = 0; k < n_calls; k++) {
+        MAT::Mutation m;
+        m.position = sm[k].position;
+        m.ref_nuc = (int8_t)sm[k].ref_nuc;
+        m.par_nuc = (int8_t)sm[k].par_nuc;
+        m.mut_nuc = (int8_t)sm[k].mut_nuc;
+        m.is_missing = sm[k].is_missing != 0;
+        sample.push_back(m);
+    }
+    static std::vector<MAT::Node*> bfs;   // the O(N) expansion is done once per tree, outside the timed part
+    static MAT::Tree* bfs_of = nullptr;
+    if (bfs_of != T) { bfs = T->breadth_first_expansion(); bfs_of = T; }
+    if (stride < 1) stride = 1;
+    const size_t total_nodes = bfs.size();
+    const size_t visits = (total_nodes > offset) ? (total_nodes - offset + stride - 1) / stride : 0;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::vector<MAT::Mutation>> node_excess_mutations(visits);
+    std::vector<std::vector<MAT::Mutation>> node_imputed_mutations(visits);
+    size_t best_node_num_leaves = 0;
+    int best_set_difference = (int)(sample.size() + T->root->mutations.size() + 1);
+    size_t best_j = 0;
+    bool best_node_has_unique = false;
+    std::vector<bool> node_has_unique(total_nodes, false);
+    std::vector<size_t> best_j_vec;
+    best_j_vec.emplace_back(0);
+    size_t num_best = 1;
+    MAT::Node* best_node = T->root;
+    auto body = [&](bool second, const std::vector<size_t>* only) {
+        const size_t cnt = only ? only->size() : visits;
+        tbb::parallel_for(tbb::blocked_range<size_t>(0, cnt), [&](tbb::blocked_range<size_t> r) {
+            for (size_t q = r.begin(); q < r.end(); ++q) {
+                const size_t k = only ? (*only)[q] : offset + q * stride;
+                const size_t slot = only ? (k - offset) / stride : q;
+                mapper2_input inp;
+                inp.T = T;
+                inp.node = bfs[k];
+                inp.missing_sample_mutations = &sample;
+                inp.excess_mutations = &node_excess_mutations[slot];
+                inp.imputed_mutations = &node_imputed_mutations[slot];
+                inp.best_node_num_leaves = &best_node_num_leaves;
+                inp.best_set_difference = &best_set_difference;
+                inp.best_node = &best_node;
+                inp.best_j = &best_j;
+                inp.num_best = &num_best;
+                inp.j = k;
+                inp.has_unique = &best_node_has_unique;
+                inp.best_j_vec = &best_j_vec;
+                inp.node_has_unique = &node_has_unique;
+                if (second) mapper2_body(inp, false);
+                else mapper2_body(inp, false, false);
+            }
+        });
+    };
+    body(false, nullptr);
+    best_set_difference += 1;
+    auto tmp_vec = std::vector<size_t>(best_j_vec.begin(), best_j_vec.end());
+    num_best = 0;
+    best_j_vec.clear();
+    body(true, &tmp_vec);
+    auto t1 = std::chrono::steady_clock::now();
+    if (best_score_seen) *best_score_seen = best_set_difference;
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 }  // extern "C"

@@ -62,7 +62,7 @@ EXPORTS = [
     "ub200_mat_info_get", "ub200_mat_node_arrays", "ub200_mat_set_pass_samples", "ub200_place_batch",
     "ub200_samples_upload", "ub200_samples_free", "ub200_place_resident", "ub200_results_download",
     "ub200_results_device_ptr", "ub200_node_scores_download", "ub200_best_set_download", "ub200_mat_set_stream",
-    "ub200_mat_synchronize", "ub200_last_timing",
+    "ub200_mat_synchronize", "ub200_last_timing", "ub200_results_copy_device",
 ]
 
 
@@ -87,6 +87,7 @@ def lib():
         L.ub200_place_resident.argtypes = [vp, vp, u32, C.c_int]
         L.ub200_results_download.argtypes = [vp, vp, vp]
         L.ub200_results_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.ub200_results_copy_device.argtypes = [vp, vp, vp]
         L.ub200_node_scores_download.argtypes = [vp, vp, vp]
         L.ub200_best_set_download.argtypes = [vp, vp, vp, vp, u64]
         L.ub200_mat_set_stream.argtypes = [vp, vp]
@@ -266,6 +267,9 @@ class Samples:
         out = np.zeros(self.n, PLACEMENT_DTYPE)
         _check(lib().ub200_results_download(self.mat.h, self.h, _p(out)))
         return out
+
+    def copy_results_to(self, dev_ptr):
+        _check(lib().ub200_results_copy_device(self.mat.h, self.h, dev_ptr))
 
     def device_ptr(self):
         p, b = C.c_void_p(), C.c_size_t()

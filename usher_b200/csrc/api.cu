@@ -63,6 +63,7 @@ struct ub200_mat {
     struct Span { int a, b, kind; };
     std::vector<Span> spans;
     int ev_used = 0;
+    struct ub200_samples* scratch = nullptr;   // reused by ub200_place_batch
 };
 
 struct ub200_samples {
@@ -88,6 +89,9 @@ struct ub200_samples {
     uint64_t set_total = 0;
     bool have_results = false, have_node_scores = false, have_set = false;
     float prep_ms = 0.f;
+    uint32_t cap_groups = 0;   // allocation capacities (scratch batches are reused by ub200_place_batch)
+    uint64_t cap_calls = 0;
+    size_t node_scores_cap = 0;
 };
 
 namespace {
@@ -192,6 +196,7 @@ void ub200_mat_destroy(ub200_mat* M) {
     cudaFree(M->mutw); cudaFree(M->hdr); cudaFree(M->row32); cudaFree(M->tile_start); cudaFree(M->anc_ptr);
     cudaFree(M->anc); cudaFree(M->key_to_node); cudaFree(M->tie_index); cudaFree(M->num_leaves);
     cudaFree(M->gstack);
+    if (M->scratch) ub200_samples_free(M->scratch);
     for (auto e : M->ev) cudaEventDestroy(e);
     if (M->own_stream) cudaStreamDestroy(M->own_stream);
     delete M;
@@ -302,10 +307,9 @@ void ub200_samples_free(ub200_samples* S) {
     delete S;
 }
 
-int ub200_samples_upload(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_ptr, const ub200_mutation* calls,
-                         ub200_samples** out) {
-    if (!M || !out || !sample_ptr || n_samples == 0) return fail(UB200_E_ARG, "ub200_samples_upload: bad argument");
-    *out = nullptr;
+// Validate a host batch and copy it into `S` (allocating or growing its device buffers as needed).
+static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, const uint64_t* sample_ptr,
+                        const ub200_mutation* calls) {
     const uint64_t n_calls = sample_ptr[n_samples];
     if (n_calls && !calls) return fail(UB200_E_ARG, "ub200_samples_upload: NULL calls");
     if (sample_ptr[0] != 0) return fail(UB200_E_ARG, "ub200_samples_upload: sample_ptr[0] != 0");
@@ -331,40 +335,69 @@ int ub200_samples_upload(ub200_mat* M, uint32_t n_samples, const uint64_t* sampl
         }
     }
     CU(cudaSetDevice(M->device));
+    const uint32_t n_groups = (n_samples + 31) / 32;
+    S->bitmap_words = ((M->L + 31) / 32 + 3) & ~3u;
+    if ((size_t)n_groups * M->L * 32 > ((size_t)24 << 30))
+        return fail(UB200_E_LIMIT, "sample batch too large for one resident table; split the batch");
+    auto alloc = [&](void** p, size_t bytes) -> int {
+        cudaFree(*p);
+        *p = nullptr;
+        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return fail((int)e, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        return 0;
+    };
+    int rc = 0;
+    if (n_groups > S->cap_groups) {
+        const uint32_t g = n_groups;
+        if (!rc) rc = alloc((void**)&S->bitmap, (size_t)g * S->bitmap_words * 4);
+        if (!rc) rc = alloc((void**)&S->tab, (size_t)g * M->L * 32);
+        if (!rc) rc = alloc((void**)&S->base, (size_t)g * 32 * 4);
+        if (!rc) rc = alloc((void**)&S->results, (size_t)g * 32 * sizeof(ub200_placement));
+        if (!rc) rc = alloc((void**)&S->best_rel, (size_t)g * 32 * 4);
+        if (!rc) rc = alloc((void**)&S->sample_ptr, ((size_t)g * 32 + 1) * 8);
+        if (!rc) rc = alloc((void**)&S->set_ptr, ((size_t)g * 32 + 1) * 8);
+        if (!rc) rc = alloc((void**)&S->set_fill, (size_t)g * 32 * 4);
+        if (rc) { S->cap_groups = 0; return rc; }
+        S->cap_groups = g;
+    }
+    if (n_calls > S->cap_calls) {
+        const uint64_t c = n_calls + n_calls / 4;
+        if (!rc) rc = alloc((void**)&S->calls, (size_t)c * sizeof(ub200_mutation));
+        if (!rc) rc = alloc((void**)&S->call_sample, (size_t)c * 4);
+        if (rc) { S->cap_calls = 0; return rc; }
+        S->cap_calls = c;
+    }
+    S->n_samples = n_samples;
+    S->n_groups = n_groups;
+    S->n_calls = n_calls;
+    S->have_results = S->have_node_scores = S->have_set = false;
+    cudaStream_t st = M->stream;
+    if (n_calls) {
+        CU(cudaMemcpyAsync(S->calls, calls, n_calls * sizeof(ub200_mutation), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(S->call_sample, owner.data(), n_calls * 4, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(S->sample_ptr, sample_ptr, ((size_t)n_samples + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // `owner` is a local; the caller's buffers may be reused after return
+    return UB200_OK;
+}
+
+int ub200_samples_upload(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_ptr, const ub200_mutation* calls,
+                         ub200_samples** out) {
+    if (!M || !out || !sample_ptr || n_samples == 0) return fail(UB200_E_ARG, "ub200_samples_upload: bad argument");
+    *out = nullptr;
     auto* S = new ub200_samples();
     S->mat = M;
-    S->n_samples = n_samples;
-    S->n_groups = (n_samples + 31) / 32;
-    S->n_calls = n_calls;
-    S->bitmap_words = ((M->L + 31) / 32 + 3) & ~3u;
-    const size_t tab_bytes = (size_t)S->n_groups * M->L * 32;
-    if (tab_bytes > ((size_t)24 << 30)) {
-        delete S;
-        return fail(UB200_E_LIMIT, "sample batch too large for one resident table; split the batch");
-    }
-    int rc = 0;
-    auto guard = [&](int r) { if (r && !rc) rc = r; };
-    cudaStream_t st = M->stream;
-    guard(dev_upload(&S->calls, calls, n_calls, st));
-    guard(dev_upload(&S->call_sample, owner.data(), n_calls, st));
-    guard(dev_upload(&S->sample_ptr, (const unsigned long long*)sample_ptr, (size_t)n_samples + 1, st));
-    auto alloc = [&](void** p, size_t bytes) {
-        if (rc) return;
-        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
-        if (e != cudaSuccess) rc = fail((int)e, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    };
-    alloc((void**)&S->bitmap, (size_t)S->n_groups * S->bitmap_words * 4);
-    alloc((void**)&S->tab, tab_bytes);
-    alloc((void**)&S->base, (size_t)S->n_groups * 32 * 4);
-    alloc((void**)&S->results, (size_t)S->n_groups * 32 * sizeof(ub200_placement));
-    alloc((void**)&S->best_rel, (size_t)S->n_groups * 32 * 4);
-    if (rc) { ub200_samples_free(S); return rc; }
-    if (!rc) {
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) rc = fail((int)e, std::string("sample upload: ") + cudaGetErrorString(e));
-    }
+    int rc = samples_fill(M, S, n_samples, sample_ptr, calls);
     if (rc) { ub200_samples_free(S); return rc; }
     *out = S;
+    return UB200_OK;
+}
+
+int ub200_results_copy_device(ub200_mat* M, ub200_samples* S, void* dst_dev) {
+    if (!M || !S || !dst_dev || !S->have_results) return fail(UB200_E_ARG, "ub200_results_copy_device: nothing to copy");
+    CU(cudaSetDevice(M->device));
+    CU(cudaMemcpyAsync(dst_dev, S->results, (size_t)S->n_samples * sizeof(ub200_placement), cudaMemcpyDeviceToDevice,
+                       M->stream));
     return UB200_OK;
 }
 
@@ -392,7 +425,7 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
         rc = span_end(M); if (rc) return rc;
         const uint32_t grid = std::max<uint32_t>(ng, (M->grid / ng) * ng);
         ub200::ReduceParams rp;
-        rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = (grid / ng) * ub200::kWarpsPerCta;
+        rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = grid / ng;   // one partial row per CTA
         rp.group0 = g0; rp.n_samples = S->n_samples; rp.base = S->base; rp.key_to_node = M->key_to_node;
         rp.tie_index = M->tie_index; rp.num_leaves = M->num_leaves; rp.out = S->results; rp.best_rel = S->best_rel;
         rc = span_begin(M, 2); if (rc) return rc;
@@ -406,7 +439,11 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
     S->have_results = true;
     if (flags & UB200_WANT_NODE_SCORES) {
         const size_t bytes = (size_t)S->n_samples * M->n * sizeof(int32_t);
-        if (!S->node_scores) CU(cudaMalloc((void**)&S->node_scores, bytes));
+        if (bytes > S->node_scores_cap) {
+            cudaFree(S->node_scores); S->node_scores = nullptr; S->node_scores_cap = 0;
+            CU(cudaMalloc((void**)&S->node_scores, bytes));
+            S->node_scores_cap = bytes;
+        }
         for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
             const uint32_t ng = std::min(NG, S->n_groups - g0);
             int rc = launch_score<ub200::kModeNodeScores>(M, S, g0, ng, smem_bitmap); if (rc) return rc;
@@ -415,8 +452,6 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
         S->have_node_scores = true;
     }
     if (flags & UB200_WANT_BEST_SET) {
-        if (!S->set_ptr) CU(cudaMalloc((void**)&S->set_ptr, ((size_t)S->n_samples + 1) * 8));
-        if (!S->set_fill) CU(cudaMalloc((void**)&S->set_fill, (size_t)S->n_groups * 32 * 4));
         k_prefix_numbest<<<1, 1, 0, M->stream>>>(S->results, S->n_samples, S->set_ptr);
         CU(cudaGetLastError());
         unsigned long long total = 0;
@@ -514,8 +549,9 @@ int ub200_place_batch(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_p
         const uint32_t ns = std::min(step, n_samples - s0);
         std::vector<uint64_t> ptr(ns + 1);
         for (uint32_t i = 0; i <= ns; i++) ptr[i] = sample_ptr[s0 + i] - sample_ptr[s0];
-        ub200_samples* S = nullptr;
-        int rc = ub200_samples_upload(M, ns, ptr.data(), calls ? calls + sample_ptr[s0] : nullptr, &S);
+        if (!M->scratch) { M->scratch = new ub200_samples(); M->scratch->mat = M; }
+        ub200_samples* S = M->scratch;
+        int rc = samples_fill(M, S, ns, ptr.data(), calls ? calls + sample_ptr[s0] : nullptr);
         if (rc) return rc;
         rc = ub200_place_resident(M, S, overflow ? (flags & ~UB200_WANT_BEST_SET) : flags, 0);
         if (!rc) rc = ub200_results_download(M, S, out + s0);
@@ -536,7 +572,6 @@ int ub200_place_batch(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_p
             acc.score_launches += t.score_launches; acc.total_launches += t.total_launches;
             acc.score_bytes += t.score_bytes;
         }
-        ub200_samples_free(S);
         if (rc) return rc;
     }
     if (overflow) {

@@ -196,7 +196,7 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
         const uint64_t node_cost = 4;
         const uint64_t total = kept + node_cost * n;
         uint64_t per = total / (target_tiles ? target_tiles : 1);
-        per = std::min<uint64_t>(std::max<uint64_t>(per, 1024), 1u << 16);
+        per = std::min<uint64_t>(std::max<uint64_t>(per, 6144), 1u << 16);   // >= ~180 nodes: keeps root-path seeding < 10%
         d.tile_start.clear();
         d.tile_start.push_back(0);
         uint64_t acc = 0;

@@ -53,7 +53,7 @@ struct ScoreParams {
     uint32_t n_samples;
     uint32_t group0;              // first group of this launch
     uint32_t ngroups;             // groups in this launch; gridDim.x % ngroups == 0
-    unsigned long long* part_key; // [ngroups][warps_per_group][32]
+    unsigned long long* part_key; // [ngroups][ctas_per_group][32]
     uint32_t* part_cnt;
     int32_t* gstack;              // spill: [total warps][gstack_levels][32]
     uint32_t gstack_levels;
@@ -334,9 +334,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
     }
 
     if (MODE == kModeBest) {
-        const size_t o = ((size_t)group * wpg + wig) * 32u + lane;
-        p.part_key[o] = bkey;
-        p.part_cnt[o] = cnt;
+        // fold the CTA's 8 warps in shared memory (the rings are dead now), one partial row per CTA
+        __syncthreads();
+        unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
+        uint32_t* scnt = reinterpret_cast<uint32_t*>(smem + kWarpsPerCta * 32 * 8);
+        skey[warp * 32 + lane] = bkey;
+        scnt[warp * 32 + lane] = cnt;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long best = ~0ull;
+            for (int w = 0; w < kWarpsPerCta; w++) best = min(best, skey[w * 32 + lane]);
+            uint32_t c = 0;
+            for (int w = 0; w < kWarpsPerCta; w++)
+                if ((skey[w * 32 + lane] >> 33) == (best >> 33)) c += scnt[w * 32 + lane];
+            const size_t o = ((size_t)group * ctas_per_group + cta_in_group) * 32u + lane;
+            p.part_key[o] = best;
+            p.part_cnt[o] = c;
+        }
     }
 }
 

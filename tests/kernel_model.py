@@ -29,7 +29,7 @@ def place(d, s_ptr, calls, per_node=False):
         optimal = []
         for i in range(n):
             h = hdr[i]
-            level, flags = int(h["level_flags"]) >> 8, int(h["level_flags"]) & 255
+            level, flags = int(h["level_flags"]) >> 14, int(h["level_flags"]) & 255
             nmut, c0 = int(h["nmut_c0"]) >> 16, int(h["nmut_c0"]) & 0xFFFF
             root = bool(flags & F_ROOT)
             cpar = 0 if root else stack[level - 1]

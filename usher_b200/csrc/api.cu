@@ -8,7 +8,10 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "score_kernel.cuh"
+#include "score_kernel2.cuh"
 #include "ub200_internal.h"
 #include "usher_b200.h"
 
@@ -75,8 +78,9 @@ struct ub200_samples {
     uint32_t* call_sample = nullptr;
     uint32_t* bitmap = nullptr;
     uint32_t bitmap_words = 0;
-    uint8_t* tab = nullptr;
+    uint32_t* tab = nullptr;
     int32_t* base = nullptr;
+    int32_t* gbest = nullptr;
     ub200_placement* results = nullptr;
     int32_t* best_rel = nullptr;
     unsigned long long* part_key = nullptr;
@@ -89,6 +93,7 @@ struct ub200_samples {
     uint64_t set_total = 0;
     bool have_results = false, have_node_scores = false, have_set = false;
     float prep_ms = 0.f;
+    uint64_t max_calls = 0;    // longest call list in the batch
     uint32_t cap_groups = 0;   // allocation capacities (scratch batches are reused by ub200_place_batch)
     uint64_t cap_calls = 0;
     size_t node_scores_cap = 0;
@@ -134,7 +139,7 @@ int launch_score(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngrou
     p.mutw = M->mutw; p.hdr = M->hdr; p.row32 = M->row32;
     p.tile_start = M->tile_start; p.anc_ptr = M->anc_ptr; p.anc = M->anc;
     p.n_nodes = M->n; p.n_tiles = M->n_tiles; p.L = M->L;
-    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.base = S->base;
+    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.base = S->base; p.gbest = S->gbest;
     p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups;
     p.part_key = S->part_key; p.part_cnt = S->part_cnt;
     p.gstack = M->gstack; p.gstack_levels = M->gstack_levels;
@@ -151,6 +156,35 @@ int launch_score(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngrou
         auto k = k_score<MODE, false>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, kThreads, smem, M->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Block-parallel best-placement kernel (score_kernel2.cuh); same parameters, one 12-warp CTA per SM.
+int launch_score2(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, bool smem_bitmap, uint32_t* grid_out) {
+    using namespace ub200;
+    ScoreParams p;
+    p.mutw = M->mutw; p.hdr = M->hdr; p.row32 = M->row32;
+    p.tile_start = M->tile_start; p.anc_ptr = M->anc_ptr; p.anc = M->anc;
+    p.n_nodes = M->n; p.n_tiles = M->n_tiles; p.L = M->L;
+    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.base = S->base; p.gbest = S->gbest;
+    p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups;
+    p.part_key = S->part_key; p.part_cnt = S->part_cnt;
+    p.gstack = M->gstack; p.gstack_levels = M->gstack_levels;
+    p.node_scores = nullptr; p.target_rel = nullptr; p.set_out = nullptr; p.set_ptr = nullptr; p.set_fill = nullptr;
+    const uint32_t grid = std::max<uint32_t>(ngroups, ((uint32_t)M->num_sms / ngroups) * ngroups);
+    *grid_out = grid;
+    const uint32_t bm_bytes = smem_bitmap ? ((S->bitmap_words * 4u + 127u) & ~127u) : 0u;
+    const size_t smem = bm_bytes + kLutBytes + (size_t)kWarps2 * kWarpSmem2;
+    if (smem_bitmap) {
+        auto k = k_score2<true>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads2, smem, M->stream>>>(p);
+    } else {
+        auto k = k_score2<false>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads2, smem, M->stream>>>(p);
     }
     CU(cudaGetLastError());
     return 0;
@@ -174,6 +208,9 @@ int run_prep(ub200_mat* M, ub200_samples* S) {
         ub200::k_prep_scatter<<<blocks, 256, 0, st>>>(pp);
         CU(cudaGetLastError());
     }
+    ub200::k_prep_bound<<<(S->n_samples + 255) / 256, 256, 0, st>>>(S->sample_ptr, S->base, S->n_samples,
+                                                                     M->d.root_init_extra, S->gbest);
+    CU(cudaGetLastError());
     return span_end(M);
 }
 
@@ -302,7 +339,7 @@ void ub200_samples_free(ub200_samples* S) {
     if (!S) return;
     cudaSetDevice(S->mat->device);
     cudaFree(S->calls); cudaFree(S->sample_ptr); cudaFree(S->call_sample); cudaFree(S->bitmap); cudaFree(S->tab);
-    cudaFree(S->base); cudaFree(S->results); cudaFree(S->best_rel); cudaFree(S->part_key); cudaFree(S->part_cnt);
+    cudaFree(S->base); cudaFree(S->gbest); cudaFree(S->results); cudaFree(S->best_rel); cudaFree(S->part_key); cudaFree(S->part_cnt);
     cudaFree(S->node_scores); cudaFree(S->set_out); cudaFree(S->set_ptr); cudaFree(S->set_fill);
     delete S;
 }
@@ -315,8 +352,10 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
     if (sample_ptr[0] != 0) return fail(UB200_E_ARG, "ub200_samples_upload: sample_ptr[0] != 0");
     // ---- host validation (the reference's merge-scan assumes sorted calls, usher_mapper.cpp:191,239)
     std::vector<uint32_t> owner(n_calls);
+    uint64_t max_calls = 0;
     for (uint32_t s = 0; s < n_samples; s++) {
         if (sample_ptr[s + 1] < sample_ptr[s]) return fail(UB200_E_ARG, "sample_ptr not monotone");
+        max_calls = std::max<uint64_t>(max_calls, sample_ptr[s + 1] - sample_ptr[s]);
         int64_t last = -1;
         for (uint64_t k = sample_ptr[s]; k < sample_ptr[s + 1]; k++) {
             const ub200_mutation& c = calls[k];
@@ -352,6 +391,7 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
         if (!rc) rc = alloc((void**)&S->bitmap, (size_t)g * S->bitmap_words * 4);
         if (!rc) rc = alloc((void**)&S->tab, (size_t)g * M->L * 32);
         if (!rc) rc = alloc((void**)&S->base, (size_t)g * 32 * 4);
+        if (!rc) rc = alloc((void**)&S->gbest, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->results, (size_t)g * 32 * sizeof(ub200_placement));
         if (!rc) rc = alloc((void**)&S->best_rel, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->sample_ptr, ((size_t)g * 32 + 1) * 8);
@@ -370,6 +410,7 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
     S->n_samples = n_samples;
     S->n_groups = n_groups;
     S->n_calls = n_calls;
+    S->max_calls = max_calls;
     S->have_results = S->have_node_scores = S->have_set = false;
     cudaStream_t st = M->stream;
     if (n_calls) {
@@ -405,6 +446,11 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
     if (!M || !S || S->mat != M) return fail(UB200_E_ARG, "ub200_place_resident: bad handles");
     CU(cudaSetDevice(M->device));
     const bool smem_bitmap = S->bitmap_words * 4u <= ub200::kMaxSmemBitmapBytes;
+    // the block-parallel kernel packs per-(node,sample) deltas in 10-bit fields and path corrections in int16
+    const bool smem_bitmap_v2 = S->bitmap_words * 4u <= 12u * 1024u;
+    const char* force = getenv("UB200_KERNEL");
+    const bool use_v2 = !(force && force[0] == '1') && M->d.max_row <= ub200::kMaxRowV2 &&
+                        S->max_calls <= ub200::kMaxCallsV2;
     const uint32_t NG = M->pass_groups;
     const uint32_t wpg_max = (std::max<uint32_t>(NG, (M->grid / 1))) * ub200::kWarpsPerCta;  // ngroups==1 bound
     if (S->part_groups < NG || S->part_wpg < wpg_max) {
@@ -417,13 +463,15 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
     M->spans.clear(); M->ev_used = 0;
     M->last = {};
     { int rc = run_prep(M, S); if (rc) return rc; }
-    M->last.total_launches += 4;
+    M->last.total_launches += 5;
     for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
         const uint32_t ng = std::min(NG, S->n_groups - g0);
         int rc = span_begin(M, 1); if (rc) return rc;
-        rc = launch_score<ub200::kModeBest>(M, S, g0, ng, smem_bitmap); if (rc) return rc;
+        uint32_t grid = std::max<uint32_t>(ng, (M->grid / ng) * ng);
+        if (use_v2) rc = launch_score2(M, S, g0, ng, smem_bitmap_v2, &grid);
+        else rc = launch_score<ub200::kModeBest>(M, S, g0, ng, smem_bitmap);
+        if (rc) return rc;
         rc = span_end(M); if (rc) return rc;
-        const uint32_t grid = std::max<uint32_t>(ng, (M->grid / ng) * ng);
         ub200::ReduceParams rp;
         rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = grid / ng;   // one partial row per CTA
         rp.group0 = g0; rp.n_samples = S->n_samples; rp.base = S->base; rp.key_to_node = M->key_to_node;

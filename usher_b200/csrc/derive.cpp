@@ -51,7 +51,7 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
                 return UB200_E_TREE_ORDER;
             }
             d.level[i] = d.level[p] + 1;
-            if (d.level[i] > kMaxLevel) { err = "flat MAT: tree deeper than 2^24-1"; return UB200_E_LIMIT; }
+            if (d.level[i] > kMaxLevel) { err = "flat MAT: tree deeper than 2^18-1"; return UB200_E_LIMIT; }
             path.push_back(i);
         }
     }
@@ -122,6 +122,7 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
             maxpos = std::max<int64_t>(maxpos, m.position);
             row_kept++;
         }
+        d.max_row = std::max<uint32_t>(d.max_row, (uint32_t)row_kept);
         if (row_kept > kMaxRow) { err = "flat MAT: a branch with more than 65534 mutations"; return UB200_E_LIMIT; }
         kept += row_kept;
     }
@@ -183,8 +184,9 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
         NodeHdr h;
         h.g = is_root ? dref[i] : dpar - a0;
         h.tiekey = d.tiekey[i];
-        h.level_flags = (d.level[i] << 8) | (leaf ? kFlagLeaf : 0) | (masked ? kFlagMasked : 0) |
-                        (is_root ? kFlagRoot : 0) | (valid0 ? kFlagValid0 : 0);
+        const uint32_t plane = (!is_root && (uint32_t)f.parent[i] >= (i & ~31u)) ? 1u + ((uint32_t)f.parent[i] & 31u) : 0u;
+        h.level_flags = (d.level[i] << kLevelShift) | (plane << 8) | (leaf ? kFlagLeaf : 0) | (masked ? kFlagMasked : 0) |
+                        (is_root ? kFlagRoot : 0) | (valid0 ? kFlagValid0 : 0) | ((hu0 && !is_root) ? kFlagHu0 : 0);
         h.nmut_c0 = (nm << 16) | c0;
         d.hdr[i] = h;
         path.push_back(i);

@@ -48,7 +48,8 @@ struct ScoreParams {
     uint32_t L;
     uint32_t bitmap_words;        // per group (multiple of 4)
     const uint32_t* bitmap;       // [all groups][bitmap_words]
-    const uint8_t* tab;           // [all groups][L][32]
+    const uint32_t* tab;          // [all groups][L][8]: w0 = lanes that call the position, w1..w4 = cost nibbles
+    int32_t* gbest;               // [samples] running upper bound of the best relative score (pruning only)
     const int32_t* base;          // [samples] LOOP-2 count against the pure reference genome
     uint32_t n_samples;
     uint32_t group0;              // first group of this launch
@@ -116,6 +117,14 @@ __device__ __forceinline__ void apply_hit(uint32_t m, uint32_t e, int& dcorr, in
     }
 }
 
+// this lane's table entry (present<<4 | cost nibble) from the position's 32-byte row
+__device__ __forceinline__ uint32_t tab_entry(const uint32_t* tabg, uint32_t pos, uint32_t lane) {
+    const uint32_t* row = tabg + (size_t)pos * 8u;
+    const uint32_t pm = __ldg(row);
+    const uint32_t nw = __ldg(row + 1 + (lane >> 3));
+    return (((pm >> lane) & 1u) << 4) | ((nw >> ((lane & 7u) * 4u)) & 15u);
+}
+
 template <bool SMEM_BITMAP>
 __device__ __forceinline__ bool bitmap_test(const uint32_t* bm_s, const uint32_t* bm_g, uint32_t pos) {
     const uint32_t w = SMEM_BITMAP ? bm_s[pos >> 5] : __ldg(bm_g + (pos >> 5));
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
     }
     __syncthreads();
 
-    const uint8_t* tabg = p.tab + (size_t)ggroup * p.L * 32u;
+    const uint32_t* tabg = p.tab + (size_t)ggroup * p.L * 8u;
     const uint32_t wig = cta_in_group * kWarpsPerCta + warp;     // warp index within the group
     const uint32_t wpg = ctas_per_group * kWarpsPerCta;          // warps per group
     int32_t* gstk = p.gstack ? p.gstack + ((size_t)(blockIdx.x * kWarpsPerCta + warp) * p.gstack_levels) * 32u : nullptr;
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
         // ---- seed the stack with the running corrections of the tile's root path (rows read straight from HBM/L2)
         for (uint32_t ai = p.anc_ptr[t]; ai < p.anc_ptr[t + 1]; ai++) {
             const uint32_t a = p.anc[ai];
-            const uint32_t lvl = p.hdr[a].level_flags >> 8;
+            const uint32_t lvl = hdr_level(p.hdr[a].level_flags);
             const uint32_t r0 = p.row32[a], r1 = p.row32[a + 1];
             int dcorr = 0, da = 0, dcom = 0;
             for (uint32_t i = r0; i < r1; i += 32) {
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
                     const int j = __ffs(hm) - 1;
                     hm &= hm - 1;
                     const uint32_t mm = __shfl_sync(FULL, m, j);
-                    apply_hit(mm, tabg[(size_t)(mm >> 6) * 32u + lane], dcorr, da, dcom);
+                    apply_hit(mm, tab_entry(tabg, mm >> 6, lane), dcorr, da, dcom);
                 }
             }
             const int up = lvl ? stack_read(lvl - 1) : 0;
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
                 }
             }
             const uint4 h = hring[n % kHdrRingNodes];
-            const uint32_t level = h.z >> 8, flags = h.z & 0xffu;
+            const uint32_t level = hdr_level(h.z), flags = hdr_flags(h.z);
             const uint32_t nmut = h.w >> 16, c0 = h.w & 0xffffu;
             const bool root = flags & kFlagRoot;
 
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
                     const int j = __ffs(hm) - 1;
                     hm &= hm - 1;
                     const uint32_t mm = __shfl_sync(FULL, m, j);
-                    apply_hit(mm, tabg[(size_t)(mm >> 6) * 32u + lane], dcorr, da, dcom);
+                    apply_hit(mm, tab_entry(tabg, mm >> 6, lane), dcorr, da, dcom);
                 }
             }
             rs = re;
@@ -421,7 +430,7 @@ struct PrepParams {
     uint32_t L;
     uint32_t bitmap_words;
     uint32_t* bitmap;
-    uint8_t* tab;
+    uint32_t* tab;
     int32_t* base;
 };
 
@@ -437,8 +446,17 @@ __global__ void k_prep_scatter(const PrepParams p) {
     if (pos < p.L) {
         atomicOr(p.bitmap + (size_t)g * p.bitmap_words + (pos >> 5), 1u << (pos & 31u));
         const uint32_t cost = c.is_missing ? 0u : (~set & 15u);
-        p.tab[((size_t)g * p.L + pos) * 32u + lane] = (uint8_t)(0x10u | cost);
+        uint32_t* row = p.tab + ((size_t)g * p.L + pos) * 8u;
+        atomicOr(row, 1u << lane);
+        if (cost) atomicOr(row + 1 + (lane >> 3), cost << ((lane & 7u) * 4u));
     }
+}
+
+// gbest[s] = the reference's initial bound (usher_common.cpp:374: |S| + |root row| + 1) relative to base[s]
+__global__ void k_prep_bound(const unsigned long long* sample_ptr, const int32_t* base, uint32_t n_samples,
+                             int32_t root_extra, int32_t* gbest) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_samples) gbest[s] = (int32_t)(sample_ptr[s + 1] - sample_ptr[s]) + root_extra + 1 - base[s];
 }
 
 }  // namespace ub200

@@ -25,15 +25,21 @@ UB200_HD inline uint32_t pack_mut(uint32_t pos, uint32_t refc, uint32_t prevc, u
 // ---- per-node header (16 B) ----
 //   x = G        : int32  Dref(parent) - A0(node)      (root: Dref(root))
 //   y = tiekey   : uint32 N-1-rank of (num_leaves, tie_index): smaller = preferred on equal score
-//   z = level<<8 | flags
+//   z = level:18 | plane:6 | flags:8   (plane = 1 + (parent & 31) when the parent lies in the node's own
+//                                       aligned 32-node block, else 0)
 //   w = nmut<<16 | c0   (unmasked row length, number of row mutations that are "common" with a sample
 //                        lacking every position of the row; both < 65535)
 constexpr uint32_t kFlagLeaf = 1u;
 constexpr uint32_t kFlagMasked = 2u;   // row holds a masked mutation: LOOP 1 takes nothing (usher_mapper.cpp:197-200)
 constexpr uint32_t kFlagRoot = 4u;
 constexpr uint32_t kFlagValid0 = 8u;   // validity predicate for a sample that hits no position of the row
+constexpr uint32_t kFlagHu0 = 16u;     // has_unique for such a sample
 constexpr uint32_t kMaxRow = 65534;
-constexpr uint32_t kMaxLevel = (1u << 24) - 1;
+constexpr uint32_t kLevelShift = 14;
+constexpr uint32_t kMaxLevel = (1u << 18) - 1;
+UB200_HD inline uint32_t hdr_level(uint32_t z) { return z >> kLevelShift; }
+UB200_HD inline uint32_t hdr_plane(uint32_t z) { return (z >> 8) & 63u; }
+UB200_HD inline uint32_t hdr_flags(uint32_t z) { return z & 255u; }
 
 struct NodeHdr {
     int32_t g;
@@ -52,6 +58,7 @@ struct Derived {
     uint64_t m = 0;          // unmasked mutations kept on the device
     uint32_t L = 0;          // 1 + largest tree position
     uint32_t max_level = 0;
+    uint32_t max_row = 0;    // longest unmasked mutation row
     std::vector<uint32_t> level, tie_index, num_leaves, tiekey, key_to_node;
     std::vector<uint32_t> row32;      // [n+1] offsets into mutw
     std::vector<uint32_t> mutw;       // padded to kMutChunk

@@ -26,27 +26,42 @@
 
 namespace ub200 {
 
-constexpr int kWarps2 = 12;
+constexpr int kWarps2 = 13;
 constexpr int kThreads2 = kWarps2 * 32;
 constexpr uint32_t kHitCap = 256;
 // per-warp shared memory (bytes)
 constexpr uint32_t kOffMring = 0;       // u32[1024]
-constexpr uint32_t kOffHring = 4096;    // uint4[128]
-constexpr uint32_t kOffDnode = 6144;    // i32[32][32] packed deltas
-constexpr uint32_t kOffCval = 10240;    // i16[32][32] materialised rows
-constexpr uint32_t kOffStk = 12288;     // i16[32][32] stack levels 0..31
-constexpr uint32_t kOffHit = 14336;     // uint2[256]
-constexpr uint32_t kOffInfo = 16384;    // per-block node info (see Info* below)
-constexpr uint32_t kOffBars = 17408;    // 8 mbarriers
-constexpr uint32_t kWarpSmem2 = 17536;
-constexpr uint32_t kInfoG = 0, kInfoTie = 32, kInfoMisc = 64, kInfoNc0 = 96, kInfoPsrc = 128, kInfoRs = 160, kInfoHm = 200;
+constexpr uint32_t kOffHring = 4096;    // uint4[64]  (2 stages)
+constexpr uint32_t kOffDnode = 5120;    // i32[32][32] packed deltas
+constexpr uint32_t kOffVals = 9216;     // i16[66][32]: rows 0..31 materialised block rows, 32..63 stack levels
+                                        //              0..31, 64 = the all-zero row
+constexpr uint32_t kOffHit = 13440;     // uint2[256]
+constexpr uint32_t kOffInfo = 15488;    // per-block node info (see kInfo* below)
+constexpr uint32_t kOffBars = 16512;    // mbarriers
+constexpr uint32_t kWarpSmem2 = 16640;
+constexpr int kHdrStages2 = 2;
+constexpr uint32_t kInfoG = 0, kInfoTie = 32, kInfoMisc = 64, kInfoNc0 = 96, kInfoPsrc = 128, kInfoRs = 160,
+                   kInfoHm = 200, kInfoH = 232;
+// value-source codes: < 65 = row of `vals`; >= kSrcSpill = stack level (code - kSrcSpill + 32) in HBM
+constexpr uint32_t kRowStack = 32, kRowZero = 64, kSrcSpill = 128;
 constexpr uint32_t kLutBytes = 4096;
 constexpr uint32_t kMaxRowV2 = 500;     // packed 10-bit delta fields; longer rows take the k_score path
 constexpr uint32_t kMaxCallsV2 = 32000; // |corr| <= calls per sample must fit int16
 
-constexpr uint32_t kSrcOut = 0x80000000u;   // value lives on the stack: low bits = level
-constexpr uint32_t kSrcZero = 0x40000000u;  // value is 0 (above the root)
 constexpr uint32_t kSrcPtr = 0x20000000u;   // unresolved: inherit from block lane (low 5 bits)
+__device__ __forceinline__ uint32_t src_level(uint32_t level) {
+    return level < (uint32_t)kStackDepth ? kRowStack + level : kSrcSpill + (level - kStackDepth);
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 
 __device__ __forceinline__ int lut_delta(uint32_t i) {
     const uint32_t e = i >> 6, refc = (i >> 4) & 3u, prevc = (i >> 2) & 3u, mutc = i & 3u;
@@ -84,11 +99,11 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     uint32_t* mring = reinterpret_cast<uint32_t*>(wbase + kOffMring);
     uint4* hring = reinterpret_cast<uint4*>(wbase + kOffHring);
     int* dnode = reinterpret_cast<int*>(wbase + kOffDnode);
-    int16_t* cval = reinterpret_cast<int16_t*>(wbase + kOffCval);
-    int16_t* stk = reinterpret_cast<int16_t*>(wbase + kOffStk);
+    int16_t* vals = reinterpret_cast<int16_t*>(wbase + kOffVals);
     uint2* hitbuf = reinterpret_cast<uint2*>(wbase + kOffHit);
     uint32_t* info = reinterpret_cast<uint32_t*>(wbase + kOffInfo);
     const uint32_t mring_a = smem_u32(mring), hring_a = smem_u32(hring), bars_a = smem_u32(wbase + kOffBars);
+    const uint32_t bm_a = smem_u32(bm_s);
 
     const uint32_t* bm_g = p.bitmap + (size_t)ggroup * p.bitmap_words;
     if (SMEM_BITMAP) {
@@ -97,8 +112,11 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
         for (uint32_t i = threadIdx.x; i < p.bitmap_words / 4; i += kThreads2) dst[i] = __ldg(src + i);
     }
     for (uint32_t i = threadIdx.x; i < 1024; i += kThreads2) lut[i] = lut_delta(i);
+    // the ring must only ever hold valid mutation words (lanes past a row's end still index the bitmap)
+    for (uint32_t i = lane; i < kMutRingWords; i += 32) mring[i] = 0u;
+    vals[kRowZero * 32u + lane] = 0;
     if (lane == 0) {
-        for (int i = 0; i < kMutStages + kHdrStages; i++) mbar_init(bars_a + 8 * i, 1);
+        for (int i = 0; i < kMutStages + kHdrStages2; i++) mbar_init(bars_a + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -110,17 +128,14 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     const uint32_t sample = ggroup * 32u + lane;
     const bool live = sample < p.n_samples;
 
-    auto stack_read = [&](uint32_t level, uint32_t s) -> int {
-        return level < (uint32_t)kStackDepth ? (int)stk[level * 32u + s] : gstk[(size_t)(level - kStackDepth) * 32u + s];
-    };
-    auto stack_write = [&](uint32_t level, uint32_t s, int v) {
-        if (level < (uint32_t)kStackDepth) stk[level * 32u + s] = (int16_t)v;
-        else gstk[(size_t)(level - kStackDepth) * 32u + s] = v;
-    };
     auto value_of = [&](uint32_t code, uint32_t s) -> int {
-        if (code & kSrcOut) return stack_read(code & 0x3ffffu, s);
-        if (code & kSrcZero) return 0;
-        return (int)cval[(code & 31u) * 32u + s];
+        if (code < kSrcSpill) return (int)vals[code * 32u + s];
+        return gstk[(size_t)(code - kSrcSpill) * 32u + s];
+    };
+    auto stack_read = [&](uint32_t level, uint32_t s) -> int { return value_of(src_level(level), s); };
+    auto stack_write = [&](uint32_t level, uint32_t s, int v) {
+        if (level < (uint32_t)kStackDepth) vals[(kRowStack + level) * 32u + s] = (int16_t)v;
+        else gstk[(size_t)(level - kStackDepth) * 32u + s] = v;
     };
 
     // per-lane (= sample) running best
@@ -183,15 +198,15 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                 mbar_expect_tx(bars_a + 8 * s, kMutChunk * 4);
                 bulk_g2s(mring_a + s * kMutChunk * 4, p.mutw + (size_t)c * kMutChunk, kMutChunk * 4, bars_a + 8 * s);
             }
-            for (int i = 0; i < kHdrStages && hc_issue + i < hc_end; i++) {
-                const uint32_t c = hc_issue + i, s = c % kHdrStages;
+            for (int i = 0; i < kHdrStages2 && hc_issue + i < hc_end; i++) {
+                const uint32_t c = hc_issue + i, s = c % kHdrStages2;
                 mbar_expect_tx(bars_a + 8 * (kMutStages + s), kHdrChunk * 16);
                 bulk_g2s(hring_a + s * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
                          bars_a + 8 * (kMutStages + s));
             }
         }
         mc_issue = min(mc_issue + kMutStages, mc_end);
-        hc_issue = min(hc_issue + kHdrStages, hc_end);
+        hc_issue = min(hc_issue + kHdrStages2, hc_end);
 
         // cross-warp bound of this lane's sample, and the tile-local floor of every value the tile can reference
         int gb = live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff;
@@ -239,13 +254,13 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
             const uint32_t b0 = max(blk, n0), b1 = min(blk + 32u, n1);
             // ================= A: headers (lane = node) =================
             {
-                const uint32_t hc = blk / kHdrChunk, s = hc % kHdrStages;
+                const uint32_t hc = blk / kHdrChunk, s = hc % kHdrStages2;
                 mbar_wait(bars_a + 8 * (kMutStages + s), (hphase >> s) & 1u);
                 hphase ^= 1u << s;
-                if (hc_issue < hc_end && hc_issue < hc + kHdrStages) {
+                if (hc_issue < hc_end && hc_issue < hc + kHdrStages2) {
                     // the previous block's header stage was consumed before its __syncwarp()s
                     if (lane == 0) {
-                        const uint32_t c = hc_issue, s2 = c % kHdrStages;
+                        const uint32_t c = hc_issue, s2 = c % kHdrStages2;
                         mbar_expect_tx(bars_a + 8 * (kMutStages + s2), kHdrChunk * 16);
                         bulk_g2s(hring_a + s2 * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
                                  bars_a + 8 * (kMutStages + s2));
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                     hc_issue++;
                 }
             }
-            const uint4 h = hring[(blk % kHdrRingNodes) + lane];
+            const uint4 h = hring[(blk % (kHdrChunk * kHdrStages2)) + lane];
             const uint32_t node = blk + lane;
             const bool act = node >= b0 && node < b1;
             const uint32_t level = hdr_level(h.z), plane = hdr_plane(h.z), flags = hdr_flags(h.z);
@@ -274,14 +289,17 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
             info[kInfoMisc + lane] = h.z;
             info[kInfoNc0 + lane] = h.w;
             info[kInfoHm + lane] = 0;
+            if (lane == 0) info[kInfoH] = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(dnode)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
             __syncwarp();
 
             // ================= B + C: scan the block's mutations, accumulate the hits =================
             {
-                uint32_t H = 0;
-                for (uint32_t i = rs_run; i < reb; i += 128) {
+                // 4 consecutive words per lane (one LDS.128); lanes outside [rs_run, reb) see other rows' (valid)
+                // words and are masked by the range test; hits are appended with a shared-memory atomic.
+                const uint32_t span = reb - rs_run;
+                for (uint32_t i = rs_run & ~3u; span != 0 && i < reb; i += 128) {
                     const uint32_t last = min(i + 128u, reb) - 1u;
                     while (mc_wait <= last / kMutChunk) {
                         const uint32_t s = mc_wait % kMutStages;
@@ -298,19 +316,30 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                         }
                         mc_issue++;
                     }
+                    const uint32_t base = i + 4u * lane;
+                    const uint4 q = lds128(mring_a + ((base % kMutRingWords) << 2));
+                    const uint32_t mw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint32_t idx = i + j * 32 + lane;
-                        const bool in = idx < reb;
-                        const uint32_t m = mring[idx % kMutRingWords];
-                        const bool hit = in && bitmap_test<SMEM_BITMAP>(bm_s, bm_g, m >> 6);
-                        const uint32_t bal = __ballot_sync(FULL, hit);
-                        if (hit) hitbuf[H + __popc(bal & lt_mask)] = make_uint2(m, idx);
-                        H += __popc(bal);
+                        const uint32_t m = mw[j];
+                        const uint32_t w = SMEM_BITMAP ? lds32(bm_a + ((m >> 11) << 2)) : __ldg(bm_g + (m >> 11));
+                        const bool hit = ((w >> ((m >> 6) & 31u)) & 1u) && (base + j - rs_run) < span;
+                        if (hit) {
+                            const uint32_t slot = atomicAdd(&info[kInfoH], 1u);
+                            hitbuf[slot] = make_uint2(m, base + j);
+                        }
                     }
-                    if (H > kHitCap - 128) { __syncwarp(); process_hits(H); H = 0; __syncwarp(); }
+                    __syncwarp();
+                    const uint32_t H = info[kInfoH];
+                    if (H > kHitCap - 128) {
+                        process_hits(H);
+                        __syncwarp();
+                        if (lane == 0) info[kInfoH] = 0;
+                        __syncwarp();
+                    }
                 }
                 __syncwarp();
+                const uint32_t H = info[kInfoH];
                 if (H) process_hits(H);
                 __syncwarp();
             }
@@ -323,18 +352,18 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
             const bool par_in = act && plane != 0 && (blk + plane - 1u) >= b0;
             const uint32_t pl = (plane - 1u) & 31u;
             uint32_t own;
-            if (!act) own = kSrcZero;
+            if (!act) own = kRowZero;
             else if (hitn && !leaf) own = lane;                          // own materialised row
-            else if (root) own = kSrcZero;
+            else if (root) own = kRowZero;
             else if (par_in) own = kSrcPtr | pl;
-            else own = kSrcOut | (level - 1u);
+            else own = src_level(level - 1u);
 #pragma unroll
             for (int r = 0; r < 5; r++) {
                 const uint32_t o2 = __shfl_sync(FULL, own, (own & kSrcPtr) ? (own & 31u) : lane);
                 if (own & kSrcPtr) own = o2;
             }
             const uint32_t own_pl = __shfl_sync(FULL, own, pl);
-            const uint32_t psrc = (root || !act) ? kSrcZero : (par_in ? own_pl : (kSrcOut | (level - 1u)));
+            const uint32_t psrc = (root || !act) ? kRowZero : (par_in ? own_pl : src_level(level - 1u));
             info[kInfoPsrc + lane] = psrc;
             {
                 uint32_t mm = __ballot_sync(FULL, act && hitn && !leaf);
@@ -344,7 +373,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                     const uint32_t ps = __shfl_sync(FULL, psrc, n);
                     const int v = dnode[n * 32u + lane];
                     const int c = value_of(ps, lane) + ((v + (1 << 19)) >> 20);
-                    cval[n * 32u + lane] = (int16_t)c;
+                    vals[n * 32u + lane] = (int16_t)c;
                     gmin = min(gmin, c);
                 }
             }

@@ -447,7 +447,7 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
     CU(cudaSetDevice(M->device));
     const bool smem_bitmap = S->bitmap_words * 4u <= ub200::kMaxSmemBitmapBytes;
     // the block-parallel kernel packs per-(node,sample) deltas in 10-bit fields and path corrections in int16
-    const bool smem_bitmap_v2 = S->bitmap_words * 4u <= 12u * 1024u;
+    const bool smem_bitmap_v2 = S->bitmap_words * 4u <= 5120u;   // what is left of 227 KB beside the 16 warps
     const char* force = getenv("UB200_KERNEL");
     const bool use_v2 = !(force && force[0] == '1') && M->d.max_row <= ub200::kMaxRowV2 &&
                         S->max_calls <= ub200::kMaxCallsV2;

@@ -26,19 +26,21 @@
 
 namespace ub200 {
 
-constexpr int kWarps2 = 13;
+constexpr int kWarps2 = 16;
 constexpr int kThreads2 = kWarps2 * 32;
-constexpr uint32_t kHitCap = 256;
+constexpr uint32_t kHitCap = 192;
+constexpr uint32_t kMutChunk2 = 128;                      // words per bulk copy in this kernel (512 B)
+constexpr uint32_t kMutRing2 = kMutChunk2 * kMutStages;   // 512 words = 2 KB
 // per-warp shared memory (bytes)
-constexpr uint32_t kOffMring = 0;       // u32[1024]
-constexpr uint32_t kOffHring = 4096;    // uint4[64]  (2 stages)
-constexpr uint32_t kOffDnode = 5120;    // i32[32][32] packed deltas
-constexpr uint32_t kOffVals = 9216;     // i16[66][32]: rows 0..31 materialised block rows, 32..63 stack levels
+constexpr uint32_t kOffMring = 0;       // u32[512]
+constexpr uint32_t kOffHring = 2048;    // uint4[64]  (2 stages)
+constexpr uint32_t kOffDnode = 3072;    // i32[32][32] packed deltas
+constexpr uint32_t kOffVals = 7168;     // i16[66][32]: rows 0..31 materialised block rows, 32..63 stack levels
                                         //              0..31, 64 = the all-zero row
-constexpr uint32_t kOffHit = 13440;     // uint2[256]
-constexpr uint32_t kOffInfo = 15488;    // per-block node info (see kInfo* below)
-constexpr uint32_t kOffBars = 16512;    // mbarriers
-constexpr uint32_t kWarpSmem2 = 16640;
+constexpr uint32_t kOffHit = 11392;     // uint2[192]
+constexpr uint32_t kOffInfo = 12928;    // per-block node info (see kInfo* below)
+constexpr uint32_t kOffBars = 13888;    // mbarriers
+constexpr uint32_t kWarpSmem2 = 13952;
 constexpr int kHdrStages2 = 2;
 constexpr uint32_t kInfoG = 0, kInfoTie = 32, kInfoMisc = 64, kInfoNc0 = 96, kInfoPsrc = 128, kInfoRs = 160,
                    kInfoHm = 200, kInfoH = 232;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     }
     for (uint32_t i = threadIdx.x; i < 1024; i += kThreads2) lut[i] = lut_delta(i);
     // the ring must only ever hold valid mutation words (lanes past a row's end still index the bitmap)
-    for (uint32_t i = lane; i < kMutRingWords; i += 32) mring[i] = 0u;
+    for (uint32_t i = lane; i < kMutRing2; i += 32) mring[i] = 0u;
     vals[kRowZero * 32u + lane] = 0;
     if (lane == 0) {
         for (int i = 0; i < kMutStages + kHdrStages2; i++) mbar_init(bars_a + 8 * i, 1);
@@ -187,16 +189,16 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     for (uint32_t t = wig; t < p.n_tiles; t += wpg) {
         const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
         const uint32_t ms = p.row32[n0], me = p.row32[n1];
-        uint32_t mc_issue = ms / kMutChunk;
-        const uint32_t mc_end = (me > ms) ? (me - 1) / kMutChunk + 1 : mc_issue;
+        uint32_t mc_issue = ms / kMutChunk2;
+        const uint32_t mc_end = (me > ms) ? (me - 1) / kMutChunk2 + 1 : mc_issue;
         uint32_t mc_wait = mc_issue;
         uint32_t hc_issue = n0 / kHdrChunk;
         const uint32_t hc_end = (n1 - 1) / kHdrChunk + 1;
         if (lane == 0) {
             for (int i = 0; i < kMutStages && mc_issue + i < mc_end; i++) {
                 const uint32_t c = mc_issue + i, s = c % kMutStages;
-                mbar_expect_tx(bars_a + 8 * s, kMutChunk * 4);
-                bulk_g2s(mring_a + s * kMutChunk * 4, p.mutw + (size_t)c * kMutChunk, kMutChunk * 4, bars_a + 8 * s);
+                mbar_expect_tx(bars_a + 8 * s, kMutChunk2 * 4);
+                bulk_g2s(mring_a + s * kMutChunk2 * 4, p.mutw + (size_t)c * kMutChunk2, kMutChunk2 * 4, bars_a + 8 * s);
             }
             for (int i = 0; i < kHdrStages2 && hc_issue + i < hc_end; i++) {
                 const uint32_t c = hc_issue + i, s = c % kHdrStages2;
@@ -301,23 +303,23 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                 const uint32_t span = reb - rs_run;
                 for (uint32_t i = rs_run & ~3u; span != 0 && i < reb; i += 128) {
                     const uint32_t last = min(i + 128u, reb) - 1u;
-                    while (mc_wait <= last / kMutChunk) {
+                    while (mc_wait <= last / kMutChunk2) {
                         const uint32_t s = mc_wait % kMutStages;
                         mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
                         mphase ^= 1u << s;
                         mc_wait++;
                     }
-                    while (mc_issue < mc_end && mc_issue < i / kMutChunk + kMutStages) {
+                    while (mc_issue < mc_end && mc_issue < i / kMutChunk2 + kMutStages) {
                         if (lane == 0) {
                             const uint32_t c = mc_issue, s = c % kMutStages;
-                            mbar_expect_tx(bars_a + 8 * s, kMutChunk * 4);
-                            bulk_g2s(mring_a + s * kMutChunk * 4, p.mutw + (size_t)c * kMutChunk, kMutChunk * 4,
+                            mbar_expect_tx(bars_a + 8 * s, kMutChunk2 * 4);
+                            bulk_g2s(mring_a + s * kMutChunk2 * 4, p.mutw + (size_t)c * kMutChunk2, kMutChunk2 * 4,
                                      bars_a + 8 * s);
                         }
                         mc_issue++;
                     }
                     const uint32_t base = i + 4u * lane;
-                    const uint4 q = lds128(mring_a + ((base % kMutRingWords) << 2));
+                    const uint4 q = lds128(mring_a + ((base % kMutRing2) << 2));
                     const uint32_t mw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                     for (int j = 0; j < 4; j++) {

@@ -397,6 +397,10 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
         if (!rc) rc = alloc((void**)&S->sample_ptr, ((size_t)g * 32 + 1) * 8);
         if (!rc) rc = alloc((void**)&S->set_ptr, ((size_t)g * 32 + 1) * 8);
         if (!rc) rc = alloc((void**)&S->set_fill, (size_t)g * 32 * 4);
+        // per-CTA partial bests of one pass: up to 8 groups x (CTAs per group) rows of 32 lanes
+        const size_t part_rows = (size_t)std::max<uint32_t>(M->grid, 8u) + 8u;
+        if (!rc) rc = alloc((void**)&S->part_key, part_rows * 32 * 8);
+        if (!rc) rc = alloc((void**)&S->part_cnt, part_rows * 32 * 4);
         if (rc) { S->cap_groups = 0; return rc; }
         S->cap_groups = g;
     }
@@ -452,14 +456,6 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
     const bool use_v2 = !(force && force[0] == '1') && M->d.max_row <= ub200::kMaxRowV2 &&
                         S->max_calls <= ub200::kMaxCallsV2;
     const uint32_t NG = M->pass_groups;
-    const uint32_t wpg_max = (std::max<uint32_t>(NG, (M->grid / 1))) * ub200::kWarpsPerCta;  // ngroups==1 bound
-    if (S->part_groups < NG || S->part_wpg < wpg_max) {
-        cudaFree(S->part_key); cudaFree(S->part_cnt);
-        S->part_key = nullptr; S->part_cnt = nullptr;
-        CU(cudaMalloc((void**)&S->part_key, (size_t)NG * wpg_max * 32 * 8));
-        CU(cudaMalloc((void**)&S->part_cnt, (size_t)NG * wpg_max * 32 * 4));
-        S->part_groups = NG; S->part_wpg = wpg_max;
-    }
     M->spans.clear(); M->ev_used = 0;
     M->last = {};
     { int rc = run_prep(M, S); if (rc) return rc; }

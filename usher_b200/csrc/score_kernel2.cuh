@@ -59,6 +59,15 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ int lds_s16(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// stack levels beyond the 32 kept in shared memory live in HBM; out of line so the hot path stays short
+__device__ __noinline__ int spill_read(const int32_t* gstk, uint32_t code, uint32_t s) {
+    return gstk[(size_t)(code - kSrcSpill) * 32u + s];
+}
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -130,9 +139,10 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     const uint32_t sample = ggroup * 32u + lane;
     const bool live = sample < p.n_samples;
 
+    const uint32_t vals_a = smem_u32(vals);
     auto value_of = [&](uint32_t code, uint32_t s) -> int {
-        if (code < kSrcSpill) return (int)vals[code * 32u + s];
-        return gstk[(size_t)(code - kSrcSpill) * 32u + s];
+        if (__builtin_expect(code >= kSrcSpill, 0)) return spill_read(gstk, code, s);
+        return lds_s16(vals_a + ((code * 32u + s) << 1));
     };
     auto stack_read = [&](uint32_t level, uint32_t s) -> int { return value_of(src_level(level), s); };
     auto stack_write = [&](uint32_t level, uint32_t s, int v) {
@@ -297,39 +307,48 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
             __syncwarp();
 
             // ================= B + C: scan the block's mutations, accumulate the hits =================
-            {
-                // 4 consecutive words per lane (one LDS.128); lanes outside [rs_run, reb) see other rows' (valid)
-                // words and are masked by the range test; hits are appended with a shared-memory atomic.
-                const uint32_t span = reb - rs_run;
-                for (uint32_t i = rs_run & ~3u; span != 0 && i < reb; i += 128) {
-                    const uint32_t last = min(i + 128u, reb) - 1u;
-                    while (mc_wait <= last / kMutChunk2) {
-                        const uint32_t s = mc_wait % kMutStages;
+            if (reb != rs_run) {
+                // One step = one aligned 128-word chunk of the stream = one ring stage (4 consecutive words per lane,
+                // one LDS.128).  Chunks cut by the block's ends are masked; a chunk shared by two blocks is scanned
+                // by both.  Hits are appended to the list with a shared-memory atomic.
+                const uint32_t c_first = rs_run / kMutChunk2, c_last = (reb - 1u) / kMutChunk2;
+                for (uint32_t c = c_first; c <= c_last; c++) {
+                    if (c >= mc_wait) {
+                        const uint32_t s = c % kMutStages;
                         mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
                         mphase ^= 1u << s;
-                        mc_wait++;
+                        mc_wait = c + 1;
                     }
-                    while (mc_issue < mc_end && mc_issue < i / kMutChunk2 + kMutStages) {
+                    // chunks below c are dead (only this block needed them): refill their stages
+                    while (mc_issue < mc_end && mc_issue < c + kMutStages) {
                         if (lane == 0) {
-                            const uint32_t c = mc_issue, s = c % kMutStages;
+                            const uint32_t cc = mc_issue, s = cc % kMutStages;
                             mbar_expect_tx(bars_a + 8 * s, kMutChunk2 * 4);
-                            bulk_g2s(mring_a + s * kMutChunk2 * 4, p.mutw + (size_t)c * kMutChunk2, kMutChunk2 * 4,
+                            bulk_g2s(mring_a + s * kMutChunk2 * 4, p.mutw + (size_t)cc * kMutChunk2, kMutChunk2 * 4,
                                      bars_a + 8 * s);
                         }
                         mc_issue++;
                     }
-                    const uint32_t base = i + 4u * lane;
-                    const uint4 q = lds128(mring_a + ((base % kMutRing2) << 2));
-                    const uint32_t mw[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t m = mw[j];
-                        const uint32_t w = SMEM_BITMAP ? lds32(bm_a + ((m >> 11) << 2)) : __ldg(bm_g + (m >> 11));
-                        const bool hit = ((w >> ((m >> 6) & 31u)) & 1u) && (base + j - rs_run) < span;
-                        if (hit) {
-                            const uint32_t slot = atomicAdd(&info[kInfoH], 1u);
-                            hitbuf[slot] = make_uint2(m, base + j);
-                        }
+                    const uint32_t base = c * kMutChunk2 + 4u * lane;
+                    const uint4 q = lds128(mring_a + (((c % kMutStages) * kMutChunk2 + 4u * lane) << 2));
+                    const uint32_t w0 = SMEM_BITMAP ? lds32(bm_a + ((q.x >> 11) << 2)) : __ldg(bm_g + (q.x >> 11));
+                    const uint32_t w1 = SMEM_BITMAP ? lds32(bm_a + ((q.y >> 11) << 2)) : __ldg(bm_g + (q.y >> 11));
+                    const uint32_t w2 = SMEM_BITMAP ? lds32(bm_a + ((q.z >> 11) << 2)) : __ldg(bm_g + (q.z >> 11));
+                    const uint32_t w3 = SMEM_BITMAP ? lds32(bm_a + ((q.w >> 11) << 2)) : __ldg(bm_g + (q.w >> 11));
+                    uint32_t hb = ((w0 >> ((q.x >> 6) & 31u)) & 1u) | (((w1 >> ((q.y >> 6) & 31u)) & 1u) << 1) |
+                                  (((w2 >> ((q.z >> 6) & 31u)) & 1u) << 2) | (((w3 >> ((q.w >> 6) & 31u)) & 1u) << 3);
+                    if (c == c_first || c == c_last) {   // warp-uniform: mask the words outside [rs_run, reb)
+                        const uint32_t span = reb - rs_run, o = base - rs_run;
+                        hb &= (o < span ? 1u : 0u) | (o + 1u < span ? 2u : 0u) | (o + 2u < span ? 4u : 0u) |
+                              (o + 3u < span ? 8u : 0u);
+                    }
+                    if (hb) {
+                        const uint32_t slot = atomicAdd(&info[kInfoH], (uint32_t)__popc(hb));
+                        uint32_t k = slot;
+                        if (hb & 1u) hitbuf[k++] = make_uint2(q.x, base);
+                        if (hb & 2u) hitbuf[k++] = make_uint2(q.y, base + 1u);
+                        if (hb & 4u) hitbuf[k++] = make_uint2(q.z, base + 2u);
+                        if (hb & 8u) hitbuf[k++] = make_uint2(q.w, base + 3u);
                     }
                     __syncwarp();
                     const uint32_t H = info[kInfoH];

@@ -48,6 +48,8 @@ def lib():
         L.usher_ref_usher_common.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
         L.usher_ref_search.restype = C.c_int
         L.usher_ref_search.argtypes = [vp, u32, vp, vp, C.c_int, C.c_int] + [vp] * 9 + [u64, vp]
+        L.usher_ref_condensed_export.restype = u64
+        L.usher_ref_condensed_export.argtypes = [vp, vp, u64]
         L.usher_ref_search_strided.restype = C.c_double
         L.usher_ref_search_strided.argtypes = [vp, u64, vp, u32, u32, C.c_int, vp]
         _lib = L
@@ -98,6 +100,16 @@ class RefTree:
             self.h, C.byref(n), C.byref(m), C.byref(nl), _p(parent), _p(row_ptr), _p(muts), _p(names)
         )
         return parent, row_ptr, muts, names.tobytes().decode().split("\n")[:-1]
+
+    def condensed(self):
+        n = lib().usher_ref_condensed_export(self.h, None, 0)
+        buf = C.create_string_buffer(int(n) + 1)
+        lib().usher_ref_condensed_export(self.h, buf, n)
+        out = {}
+        for line in buf.raw[: int(n)].decode().splitlines():
+            name, members = line.split("\t")
+            out[name] = members.split(",")
+        return out
 
     def read_samples(self, vcf):
         ns = lib().usher_ref_read_samples(self.h, vcf.encode())

@@ -406,4 +406,19 @@ double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, u
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// condensed_nodes of the tree as text: one line per node, "name\tmember1,member2,...\n"
+uint64_t usher_ref_condensed_export(void* hv, char* out, uint64_t cap) {
+    auto* h = (RefTree*)hv;
+    std::string s;
+    for (auto* n : h->T.depth_first_expansion()) {
+        auto it = h->T.condensed_nodes.find(n->identifier);
+        if (it == h->T.condensed_nodes.end()) continue;
+        s += n->identifier + "\t";
+        for (size_t i = 0; i < it->second.size(); i++) { if (i) s += ","; s += it->second[i]; }
+        s += "\n";
+    }
+    if (out && cap >= s.size()) memcpy(out, s.data(), s.size());
+    return s.size();
+}
+
 }  // extern "C"

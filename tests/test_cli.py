@@ -1,0 +1,106 @@
+"""The drop-in `usher` binary (usher_b200/csrc/host/*.cpp over the C ABI).
+CPU: the host data layer — parsimony.proto reader/writer (byte-identical round trip of a message serialised by the
+reference's own parsimony_pb2), newick parser naming/order, placement-mode VCF reader — against the config-1
+golden minted from the reference.  GPU: `usher -i tree.pb -v new.vcf -d out` reproduces the reference's
+placement_stats.tsv, mutation-paths.txt and final-tree.nh byte for byte (sequential graft = batch of 1 with a
+re-flatten per sample), plus the --no-add and --write-parsimony-scores-per-node runs."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import common
+from usher_b200 import build
+
+PB = os.path.join(common.GOLDEN, "config1.pb")
+VCF = os.path.join(common.GOLDEN, "config1_new_samples.vcf")
+
+
+@pytest.fixture(scope="module")
+def usher():
+    build.build()
+    assert os.path.exists(build.USHER)
+    return build.USHER
+
+
+def test_pb_newick_vcf_readers_match_reference(usher):
+    g = common.load(os.path.join(common.GOLDEN, "config1.npz"))
+    d = tempfile.mkdtemp()
+    subprocess.check_call([usher, "-i", PB, "-v", VCF, "--dump-flat", d + "/flat.txt"], stderr=subprocess.DEVNULL)
+    names = g["names"].tolist()
+    parent = g["parent"]
+    row_ptr = g["row_ptr"].astype(np.int64)
+    muts = g["muts"]
+    nodes = [l.rstrip("\n").split("\t") for l in open(d + "/flat.txt") if l.startswith("N\t")]
+    assert [n[1] for n in nodes] == names
+    assert [n[2] for n in nodes] == ["" if p < 0 else names[p] for p in parent]
+    for i, n in enumerate(nodes):
+        exp = "".join(f"{m['position']}:{m['ref_nuc']}:{m['par_nuc']}:{m['mut_nuc']}," for m in muts[row_ptr[i]:row_ptr[i + 1]])
+        assert n[3] == exp, (i, n[3], exp)
+    samples = [l.rstrip("\n").split("\t") for l in open(d + "/flat.txt") if l.startswith("S\t")]
+    assert [s[1] for s in samples] == g["snames"].tolist()
+    sp = g["s_ptr"].astype(np.int64)
+    for i, s in enumerate(samples):
+        exp = "".join(f"{c['position']}:{c['ref_nuc']}:{c['mut_nuc']}:{c['is_missing']}," for c in g["calls"][sp[i]:sp[i + 1]])
+        assert s[2] == exp
+    nwk = [l for l in open(d + "/flat.txt") if l.startswith("NEWICK\t")][0].split("\t")[1].strip()
+    assert nwk == str(g["current_tree"]).strip()   # the reference's -p run writes the labelled input tree
+
+
+def test_pb_round_trip_is_byte_identical(usher):
+    d = tempfile.mkdtemp()
+    subprocess.check_call([usher, "-i", PB, "--resave", d + "/re.pb"], stderr=subprocess.DEVNULL)
+    assert open(d + "/re.pb", "rb").read() == open(PB, "rb").read()
+    subprocess.check_call([usher, "-i", PB, "--resave", d + "/re.pb.gz"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([usher, "-i", d + "/re.pb.gz", "--resave", d + "/re2.pb"], stderr=subprocess.DEVNULL)
+    assert open(d + "/re2.pb", "rb").read() == open(PB, "rb").read()
+
+
+def test_cli_rejects_unsupported_and_missing_arguments(usher):
+    assert subprocess.run([usher], capture_output=True).returncode != 0
+    assert subprocess.run([usher, "-v", VCF], capture_output=True).returncode != 0
+    r = subprocess.run([usher, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--load-mutation-annotated-tree" in r.stderr
+
+
+@pytest.mark.gpu
+def test_config1_sequential_placement_matches_reference(usher):
+    g = common.load(os.path.join(common.GOLDEN, "config1.npz"))
+    d = tempfile.mkdtemp()
+    r = subprocess.run([usher, "-i", PB, "-v", VCF, "-d", d], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(d + "/placement_stats.tsv").read() == str(g["placement_stats"])
+    assert open(d + "/mutation-paths.txt").read() == str(g["mutation_paths"])
+    assert open(d + "/final-tree.nh").read() == str(g["final_tree"])
+    assert "The parsimony score for this tree is: 503" in r.stderr
+    assert "Sample1" in r.stderr.split("multiple possibilities of parsimony-optimal placements:")[1]
+
+
+@pytest.mark.gpu
+def test_config1_no_add_and_per_node_scores_match_reference(usher):
+    g = common.load(os.path.join(common.GOLDEN, "config1.npz"))
+    d = tempfile.mkdtemp()
+    r = subprocess.run([usher, "-i", PB, "-v", VCF, "-d", d, "-n"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(d + "/placement_stats.tsv").read() == str(g["noadd_placement_stats"])
+    assert open(d + "/final-tree.nh").read() == str(g["noadd_final_tree"])
+    d2 = tempfile.mkdtemp()
+    r = subprocess.run([usher, "-i", PB, "-v", VCF, "-d", d2, "-p"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(d2 + "/current-tree.nh").read() == str(g["current_tree"])
+    assert open(d2 + "/parsimony-scores.tsv").read() == str(g["parsimony_scores"])
+
+
+@pytest.mark.gpu
+def test_sorted_placement_and_saved_pb_reload(usher):
+    d = tempfile.mkdtemp()
+    r = subprocess.run([usher, "-i", PB, "-v", VCF, "-d", d, "-s", "-o", d + "/out.pb.gz"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # the saved tree contains the five new samples and reloads cleanly
+    d2 = tempfile.mkdtemp()
+    subprocess.check_call([usher, "-i", d + "/out.pb.gz", "-v", VCF, "--dump-flat", d2 + "/flat.txt"], stderr=subprocess.DEVNULL)
+    txt = open(d2 + "/flat.txt").read()
+    assert all(f"Sample{i}" in txt for i in range(1, 6))
+    assert not [l for l in txt.splitlines() if l.startswith("S\t")]   # all five are already in the tree now

@@ -14,6 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 INC = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "libusher_b200.so")
 SYNTH = os.path.join(PKG, "libub200_synth.so")
+USHER = os.path.join(PKG, "usher")   # the drop-in CLI (host C++ over the C ABI)
 # The image exports CXX=/opt/gcc/bin/g++, a wrapper that links libstdc++ statically; a second libstdc++ in a
 # python process that already loaded the shared one crashes.  Pin the system compiler.
 HOSTCXX = "/usr/bin/g++"
@@ -51,6 +52,12 @@ def build(force=False, verbose=False):
     ssrc = [os.path.join(CSRC, "synth.cpp")]
     if force or _stale(SYNTH, ssrc + hdrs):
         subprocess.check_call([HOSTCXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-I", INC, "-o", SYNTH] + ssrc)
+    hdir = os.path.join(CSRC, "host")
+    hsrc = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir)) if f.endswith(".cpp")]
+    hhdr = [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".hpp")]
+    if force or _stale(USHER, hsrc + hhdr + hdrs + [LIB]):
+        subprocess.check_call([HOSTCXX, "-std=c++17", "-O2", "-I", INC, "-I", hdir] + hsrc +
+                              ["-o", USHER, "-L", PKG, "-lusher_b200", "-Wl,-rpath,$ORIGIN", "-lz"])
     return LIB, SYNTH
 
 

@@ -1,0 +1,752 @@
+// See mutation_annotated_tree.hpp.  Behaviour follows reference src/mutation_annotated_tree.cpp (line ranges
+// cited per function); the code is an independent implementation.
+#include "mutation_annotated_tree.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <sstream>
+
+#include "usher_graph.hpp"
+
+namespace Mutation_Annotated_Tree {
+
+// ---------------------------------------------------------------- nucleotide codes (reference :17-208)
+int8_t get_nuc_id(char c) {
+    switch (c) {
+        case 'a': case 'A': return 1;
+        case 'c': case 'C': return 2;
+        case 'g': case 'G': return 4;
+        case 't': case 'T': return 8;
+        case 'R': return 5;
+        case 'Y': return 10;
+        case 'S': return 6;
+        case 'W': return 9;
+        case 'K': return 12;
+        case 'M': return 3;
+        case 'B': return 14;
+        case 'D': return 13;
+        case 'H': return 11;
+        // 'V' falls through to N in the reference (missing break, :65-71); kept for parity
+        default: return 15;
+    }
+}
+int8_t get_nuc_id(const std::vector<int8_t>& v) {
+    int8_t r = 0;
+    for (auto n : v) r = (int8_t)(r + (1 << n));
+    return r;
+}
+char get_nuc(int8_t id) {
+    static const char tab[16] = {'N', 'A', 'C', 'M', 'G', 'R', 'S', 'V', 'T', 'W', 'Y', 'H', 'K', 'D', 'B', 'N'};
+    return (id >= 1 && id <= 14) ? tab[id] : 'N';
+}
+int8_t get_nt(int8_t id) {
+    switch (id) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; default: return -1; }
+}
+std::vector<int8_t> get_nuc_vec_from_id(int8_t id) {
+    // goes through the IUPAC letter like the reference (get_nuc then get_nuc_vec): 7 -> 'V' -> {0,1,2}
+    const int8_t bits = (id >= 1 && id <= 14) ? id : 15;
+    std::vector<int8_t> v;
+    for (int8_t b = 0; b < 4; b++) if (bits & (1 << b)) v.push_back(b);
+    return v;
+}
+
+// ---------------------------------------------------------------- Node
+void Node::add_mutation(const Mutation& mut) {
+    auto it = std::lower_bound(mutations.begin(), mutations.end(), mut);
+    if (it != mutations.end() && it->position == mut.position) {
+        if (it->par_nuc != mut.mut_nuc) {
+            it->mut_nuc = mut.mut_nuc;
+        } else {
+            if (it->mut_nuc != mut.par_nuc) {
+                fprintf(stderr, "ERROR: add_mutation: consecutive mutations at same position disagree on nuc (%s > %s) "
+                        "-- called out of order?\n", it->get_string().c_str(), mut.get_string().c_str());
+                exit(1);
+            }
+            const int pos = it->position;
+            mutations.erase(std::remove_if(mutations.begin(), mutations.end(),
+                                           [pos](const Mutation& m) { return m.position == pos; }),
+                            mutations.end());
+        }
+    } else {
+        mutations.insert(it, mut);
+    }
+}
+
+// ---------------------------------------------------------------- Tree
+Tree& Tree::operator=(Tree&& o) noexcept {
+    if (this != &o) {
+        for (auto& kv : all_nodes) delete kv.second;
+        root = o.root; o.root = nullptr;
+        condensed_nodes = std::move(o.condensed_nodes);
+        condensed_order = std::move(o.condensed_order);
+        condensed_leaves = std::move(o.condensed_leaves);
+        curr_internal_node = o.curr_internal_node;
+        all_nodes = std::move(o.all_nodes);
+        o.all_nodes.clear();
+    }
+    return *this;
+}
+Tree::~Tree() { for (auto& kv : all_nodes) delete kv.second; }
+
+Node* Tree::create_node(const std::string& id, float len, size_t num_annotations) {
+    for (auto& kv : all_nodes) delete kv.second;
+    all_nodes.clear();
+    Node* n = new Node();
+    n->identifier = id;
+    n->level = 1;
+    n->branch_length = len;
+    n->clade_annotations.assign(num_annotations, "");
+    root = n;
+    all_nodes[id] = n;
+    return n;
+}
+Node* Tree::create_node(const std::string& id, Node* par, float len) {
+    if (all_nodes.count(id)) {
+        fprintf(stderr, "Error: %s already in the tree!\n", id.c_str());
+        exit(1);
+    }
+    Node* n = new Node();
+    n->identifier = id;
+    n->parent = par;
+    n->level = par->level + 1;
+    n->branch_length = len;
+    n->clade_annotations.assign(get_num_annotations(), "");
+    all_nodes[id] = n;
+    par->children.push_back(n);
+    return n;
+}
+Node* Tree::create_node(const std::string& id, const std::string& parent_id, float len) {
+    return create_node(id, all_nodes.at(parent_id), len);
+}
+Node* Tree::get_node(const std::string& id) const {
+    auto it = all_nodes.find(id);
+    return it == all_nodes.end() ? nullptr : it->second;
+}
+std::vector<Node*> Tree::rsearch(const std::string& nid, bool include_self) const {
+    std::vector<Node*> anc;
+    Node* n = get_node(nid);
+    if (!n) return anc;
+    if (include_self) anc.push_back(n);
+    for (n = n->parent; n; n = n->parent) anc.push_back(n);
+    return anc;
+}
+std::string Tree::get_clade_assignment(const Node* n, int clade_id, bool include_self) const {
+    for (auto a : rsearch(n->identifier, include_self))
+        if ((int)a->clade_annotations.size() > clade_id && a->clade_annotations[clade_id] != "")
+            return a->clade_annotations[clade_id];
+    return "UNDEFINED";
+}
+size_t Tree::get_num_leaves(Node* node) const {   // childless nodes below `node`; a condensed node counts 1 (:866-879)
+    if (!node) node = root;
+    size_t cnt = 0;
+    std::vector<Node*> st{node};
+    while (!st.empty()) {
+        Node* u = st.back();
+        st.pop_back();
+        if (u->children.empty()) cnt++;
+        for (auto c : u->children) st.push_back(c);
+    }
+    return cnt;
+}
+std::vector<Node*> Tree::get_leaves(const std::string& nid) const {
+    std::vector<Node*> out;
+    Node* start = nid.empty() ? root : get_node(nid);
+    if (!start) return out;
+    std::deque<Node*> q{start};
+    while (!q.empty()) {
+        Node* u = q.front();
+        q.pop_front();
+        if (u->children.empty()) out.push_back(u);
+        for (auto c : u->children) q.push_back(c);
+    }
+    return out;
+}
+std::vector<Node*> Tree::breadth_first_expansion(const std::string& nid) const {   // :1225-1251
+    std::vector<Node*> out;
+    Node* start = nid.empty() ? root : get_node(nid);
+    if (!start) return out;
+    out.push_back(start);
+    for (size_t h = 0; h < out.size(); h++)
+        for (auto c : out[h]->children) out.push_back(c);
+    return out;
+}
+std::vector<Node*> Tree::depth_first_expansion(Node* node) const {                 // :1253-1274, pre-order
+    std::vector<Node*> out;
+    if (!node) node = root;
+    if (!node) return out;
+    std::vector<Node*> st{node};
+    while (!st.empty()) {
+        Node* u = st.back();
+        st.pop_back();
+        out.push_back(u);
+        for (auto it = u->children.rbegin(); it != u->children.rend(); ++it) st.push_back(*it);
+    }
+    return out;
+}
+size_t Tree::get_parsimony_score() const {
+    size_t s = 0;
+    for (auto n : depth_first_expansion()) s += n->mutations.size();
+    return s;
+}
+
+static void relevel(Node* n) {
+    std::vector<Node*> st{n};
+    while (!st.empty()) {
+        Node* u = st.back();
+        st.pop_back();
+        u->level = u->parent ? u->parent->level + 1 : 1;
+        for (auto c : u->children) st.push_back(c);
+    }
+}
+
+// Reference :1135-1222.  The placement path only ever moves the chosen node under a brand-new internal node
+// whose single child (the new sample) has no mutations yet, i.e. the "simple re-link" case; the merge cases
+// of the reference (destination already has a child with the same non-empty mutation set) are reported.
+void Tree::move_node(const std::string& source_id, const std::string& dest_id) {
+    Node* src = all_nodes.at(source_id);
+    Node* dst = all_nodes.at(dest_id);
+    Node* old = src->parent;
+    if (old == dst) {
+        fprintf(stderr, "ERROR: move_node: dest_id=%s but that is already parent of source_id=%s\n", dest_id.c_str(),
+                source_id.c_str());
+        exit(1);
+    }
+    if (!src->mutations.empty()) {
+        for (auto c : dst->children) {
+            if (c == old || c->mutations.size() != src->mutations.size()) continue;
+            bool same = true;
+            for (size_t i = 0; i < c->mutations.size() && same; i++)
+                same = c->mutations[i].position == src->mutations[i].position &&
+                       c->mutations[i].mut_nuc == src->mutations[i].mut_nuc;
+            if (same) {
+                fprintf(stderr, "ERROR: move_node: merging with an identical sibling is not supported by this build\n");
+                exit(1);
+            }
+        }
+    }
+    src->parent = dst;
+    src->branch_length = -1.0f;
+    dst->children.push_back(src);
+    old->children.erase(std::find(old->children.begin(), old->children.end(), src));
+    if (old->children.empty()) remove_node(old->identifier, true);
+    relevel(src);
+}
+
+// Remove a childless node (and, like the reference :1002-1061, any ancestor left childless by it).
+void Tree::remove_node(const std::string& nid, bool move_level) {
+    (void)move_level;
+    Node* n = get_node(nid);
+    while (n) {
+        Node* par = n->parent;
+        if (par) par->children.erase(std::find(par->children.begin(), par->children.end(), n));
+        else root = nullptr;
+        all_nodes.erase(n->identifier);
+        delete n;
+        n = (par && par->children.empty()) ? par : nullptr;
+    }
+}
+
+// Sibling leaves without mutations collapse into node_<k>_condensed_<n>_leaves appended to the parent
+// (reference :1287-1332).
+void Tree::condense_leaves(const std::vector<std::string>& missing) {
+    if (!condensed_nodes.empty()) {
+        fprintf(stderr, "WARNING: tree contains condensed nodes. Uncondensing fist.\n");
+        uncondense_leaves();
+    }
+    auto is_missing = [&](const std::string& s) { return std::find(missing.begin(), missing.end(), s) != missing.end(); };
+    std::vector<std::string> leaf_ids;
+    for (auto l : get_leaves()) leaf_ids.push_back(l->identifier);
+    for (auto& id : leaf_ids) {
+        Node* l1 = get_node(id);
+        if (!l1 || is_missing(id) || !l1->mutations.empty() || !l1->parent) continue;
+        std::vector<Node*> poly;
+        for (auto l2 : l1->parent->children)
+            if (!is_missing(l2->identifier) && l2->is_leaf() && l2->mutations.empty()) poly.push_back(l2);
+        if (poly.size() > 1) {
+            const std::string name = "node_" + std::to_string(1 + condensed_nodes.size()) + "_condensed_" +
+                                     std::to_string(poly.size()) + "_leaves";
+            create_node(name, l1->parent, l1->branch_length);
+            std::vector<std::string> members;
+            for (auto p : poly) members.push_back(p->identifier);
+            for (auto& m : members) {
+                condensed_leaves.insert(m);
+                Node* p = get_node(m);
+                p->parent->children.erase(std::find(p->parent->children.begin(), p->parent->children.end(), p));
+                all_nodes.erase(m);
+                delete p;
+            }
+            condensed_nodes[name] = members;
+            condensed_order.push_back(name);
+        }
+    }
+}
+
+void Tree::uncondense_leaves() {   // reference :1334-1383
+    std::vector<std::string> order = condensed_order;
+    for (auto& kv : condensed_nodes)
+        if (std::find(order.begin(), order.end(), kv.first) == order.end()) order.push_back(kv.first);
+    for (auto& name : order) {
+        auto it = condensed_nodes.find(name);
+        if (it == condensed_nodes.end()) continue;
+        Node* n = get_node(name);
+        if (!n) continue;
+        Node* par = n->parent ? n->parent : n;
+        const auto& members = it->second;
+        const size_t k = members.size();
+        auto add = [&](const std::string& id, Node* p, float len) {
+            Node* nn = new Node();
+            nn->identifier = id; nn->parent = p; nn->level = p->level + 1; nn->branch_length = len;
+            nn->clade_annotations.assign(get_num_annotations(), "");
+            all_nodes[id] = nn;
+            p->children.push_back(nn);
+        };
+        if (k > 1 && !n->mutations.empty()) {
+            all_nodes.erase(n->identifier);
+            n->identifier = new_internal_node_id();
+            all_nodes[n->identifier] = n;
+            for (auto& m : members) add(m, n, -1.0f);
+        } else if (k > 1) {
+            all_nodes.erase(n->identifier);
+            n->identifier = members[0];
+            all_nodes[n->identifier] = n;
+            for (size_t s = 1; s < k; s++) add(members[s], par, n->branch_length);
+        } else if (k == 1) {
+            all_nodes.erase(n->identifier);
+            n->identifier = members[0];
+            all_nodes[n->identifier] = n;
+        }
+    }
+    condensed_nodes.clear();
+    condensed_order.clear();
+    condensed_leaves.clear();
+}
+
+// ---------------------------------------------------------------- newick
+// Writer: plain newick of the subtree, branch length = number of mutations on the branch (the reference forces
+// this, :228-230), internal names only when asked, a condensed leaf optionally expanded to its members.
+static void write_subtree(std::ostringstream& ss, const Tree& T, Node* top, bool names, bool lens, bool expand) {
+    struct Frame { Node* n; size_t next; };
+    std::vector<Frame> st{{top, 0}};
+    auto emit_len = [&](Node* n) { if (lens) { ss << ':' << static_cast<float>(n->mutations.size()); } };
+    while (!st.empty()) {
+        Frame& f = st.back();
+        Node* n = f.n;
+        if (n->children.empty()) {
+            auto cn = expand ? T.condensed_nodes.find(n->identifier) : T.condensed_nodes.end();
+            if (cn != T.condensed_nodes.end()) {
+                for (size_t i = 0; i < cn->second.size(); i++) { if (i) ss << ','; ss << cn->second[i]; }
+            } else {
+                ss << n->identifier;
+            }
+            emit_len(n);
+            st.pop_back();
+            continue;
+        }
+        if (f.next == 0) ss << '(';
+        if (f.next < n->children.size()) {
+            if (f.next) ss << ',';
+            Node* c = n->children[f.next++];
+            st.push_back({c, 0});
+            continue;
+        }
+        ss << ')';
+        if (names) ss << n->identifier;
+        emit_len(n);
+        st.pop_back();
+    }
+    ss << ';';
+}
+std::string get_newick_string(const Tree& T, Node* node, bool names, bool lens, bool, bool expand) {
+    std::ostringstream ss;
+    write_subtree(ss, T, node, names, lens, expand);
+    return ss.str();
+}
+std::string get_newick_string(const Tree& T, bool names, bool lens, bool keep, bool expand) {
+    return get_newick_string(T, T.root, names, lens, keep, expand);
+}
+
+void string_split(const std::string& s, char delim, std::vector<std::string>& words) {
+    size_t a = 0, b;
+    while ((b = s.find(delim, a)) != std::string::npos) {
+        words.emplace_back(s.substr(a, b - a));
+        a = b + 1;
+    }
+    if (a < s.size()) words.emplace_back(s.substr(a));
+}
+void string_split(const std::string& s, std::vector<std::string>& words) {
+    std::istringstream ss(s);
+    std::string w;
+    while (ss >> w) words.push_back(w);
+}
+
+// Parser with the reference's observable behaviour (:415-508): split on ',', leaf name = characters before the
+// first ':' or ')', internal nodes are (re)named node_1, node_2, ... in order of their '(' (names written after
+// ')' are ignored), branch lengths are parsed but never printed back.
+Tree create_tree_from_newick_string(const std::string& nwk) {
+    Tree T;
+    std::vector<std::string> toks;
+    string_split(nwk, ',', toks);
+    std::vector<Node*> stack;
+    long depth = 0;
+    for (auto& tok : toks) {
+        size_t opens = 0, closes = 0;
+        std::string leaf;
+        bool stop = false;
+        for (char c : tok) {
+            if (c == '(') opens++;
+            else if (c == ')') { closes++; stop = true; }
+            else if (c == ':') stop = true;
+            else if (!stop) leaf += c;
+        }
+        for (size_t j = 0; j < opens; j++) {
+            const std::string nid = T.new_internal_node_id();
+            Node* nn = stack.empty() ? T.create_node(nid, -1.0f) : T.create_node(nid, stack.back(), -1.0f);
+            stack.push_back(nn);
+            depth++;
+        }
+        if (stack.empty()) {
+            fprintf(stderr, "ERROR: incorrect Newick format!\n");
+            exit(1);
+        }
+        T.create_node(leaf, stack.back(), -1.0f);
+        for (size_t j = 0; j < closes; j++) {
+            if (stack.empty()) { fprintf(stderr, "ERROR: incorrect Newick format!\n"); exit(1); }
+            stack.pop_back();
+            depth--;
+        }
+    }
+    if (depth != 0) {
+        fprintf(stderr, "ERROR: incorrect Newick format!\n");
+        exit(1);
+    }
+    if (!T.root) fprintf(stderr, "WARNING: Tree found empty!\n");
+    return T;
+}
+Tree create_tree_from_newick(const std::string& filename) {
+    std::ifstream f(filename);
+    if (!f) {
+        fprintf(stderr, "ERROR: Could not open the tree file: %s!\n", filename.c_str());
+        exit(1);
+    }
+    std::string line;
+    std::getline(f, line);
+    return create_tree_from_newick_string(line);
+}
+
+// ---------------------------------------------------------------- file helpers (plain or gzip through zlib)
+static bool read_all(const std::string& filename, std::string& out) {
+    gzFile f = gzopen(filename.c_str(), "rb");   // transparently reads uncompressed files too
+    if (!f) return false;
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(f, buf, sizeof buf)) > 0) out.append(buf, (size_t)n);
+    gzclose(f);
+    return n == 0;
+}
+static bool write_all(const std::string& filename, const std::string& data) {
+    if (filename.find(".gz") != std::string::npos) {
+        gzFile f = gzopen(filename.c_str(), "wb");
+        if (!f) return false;
+        size_t off = 0;
+        while (off < data.size()) {
+            int n = gzwrite(f, data.data() + off, (unsigned)std::min<size_t>(data.size() - off, 1u << 30));
+            if (n <= 0) { gzclose(f); return false; }
+            off += (size_t)n;
+        }
+        return gzclose(f) == Z_OK;
+    }
+    std::ofstream o(filename, std::ios::binary);
+    if (!o) return false;
+    o.write(data.data(), (std::streamsize)data.size());
+    return (bool)o;
+}
+
+// ---------------------------------------------------------------- parsimony.proto wire codec
+namespace pb {
+struct Reader {
+    const uint8_t* p; const uint8_t* end; bool ok = true;
+    Reader(const void* d, size_t n) : p((const uint8_t*)d), end((const uint8_t*)d + n) {}
+    bool more() const { return ok && p < end; }
+    uint64_t varint() {
+        uint64_t v = 0; int sh = 0;
+        while (p < end) {
+            uint8_t b = *p++;
+            v |= (uint64_t)(b & 0x7f) << sh;
+            if (!(b & 0x80)) return v;
+            sh += 7;
+            if (sh > 63) break;
+        }
+        ok = false; return 0;
+    }
+    Reader sub() {
+        uint64_t n = varint();
+        if (!ok || n > (uint64_t)(end - p)) { ok = false; return Reader(p, 0); }
+        Reader r(p, (size_t)n); p += n; return r;
+    }
+    void skip(uint32_t wt) {
+        switch (wt) {
+            case 0: varint(); break;
+            case 1: if (end - p >= 8) p += 8; else ok = false; break;
+            case 2: sub(); break;
+            case 5: if (end - p >= 4) p += 4; else ok = false; break;
+            default: ok = false;
+        }
+    }
+};
+inline void put_varint(std::string& o, uint64_t v) {
+    while (v >= 0x80) { o.push_back((char)(v | 0x80)); v >>= 7; }
+    o.push_back((char)v);
+}
+inline void put_tag(std::string& o, uint32_t field, uint32_t wt) { put_varint(o, (field << 3) | wt); }
+inline void put_bytes(std::string& o, uint32_t field, const std::string& s) {
+    put_tag(o, field, 2); put_varint(o, s.size()); o += s;
+}
+inline void put_i32(std::string& o, uint32_t field, int32_t v) {   // proto3: default (0) is not written
+    if (v == 0) return;
+    put_tag(o, field, 0); put_varint(o, (uint64_t)(int64_t)v);
+}
+}  // namespace pb
+
+Tree load_mutation_annotated_tree(const std::string& filename) {   // reference :522-612
+    std::string raw;
+    if (!read_all(filename, raw)) {
+        fprintf(stderr, "ERROR: Could not load the mutation-annotated tree object from file: %s!\n", filename.c_str());
+        exit(1);
+    }
+    pb::Reader top(raw.data(), raw.size());
+    std::string newick;
+    std::vector<pb::Reader> lists, conds, metas;
+    while (top.more()) {
+        const uint64_t tag = top.varint();
+        const uint32_t field = (uint32_t)(tag >> 3), wt = (uint32_t)(tag & 7);
+        if (wt == 2 && field >= 1 && field <= 4) {
+            pb::Reader r = top.sub();
+            if (field == 1) newick.assign((const char*)r.p, (size_t)(r.end - r.p));
+            else if (field == 2) lists.push_back(r);
+            else if (field == 3) conds.push_back(r);
+            else metas.push_back(r);
+        } else {
+            top.skip(wt);
+        }
+    }
+    if (!top.ok) {
+        fprintf(stderr, "ERROR: %s is not a valid parsimony.proto message\n", filename.c_str());
+        exit(1);
+    }
+    if (metas.empty()) fprintf(stderr, "WARNING: This pb does not include any metadata. Filling in default values\n");
+    Tree tree = create_tree_from_newick_string(newick);
+    auto dfs = tree.depth_first_expansion();
+    if (lists.size() < dfs.size()) {
+        fprintf(stderr, "ERROR: protobuf holds %zu mutation lists for %zu nodes\n", lists.size(), dfs.size());
+        exit(1);
+    }
+    for (size_t i = 0; i < dfs.size(); i++) {
+        Node* node = dfs[i];
+        if (i < metas.size()) {
+            pb::Reader m = metas[i];
+            while (m.more()) {
+                const uint64_t tag = m.varint();
+                if ((tag >> 3) == 1 && (tag & 7) == 2) {
+                    pb::Reader s = m.sub();
+                    node->clade_annotations.emplace_back((const char*)s.p, (size_t)(s.end - s.p));
+                } else m.skip((uint32_t)(tag & 7));
+            }
+        }
+        pb::Reader l = lists[i];
+        while (l.more()) {
+            const uint64_t tag = l.varint();
+            if (!((tag >> 3) == 1 && (tag & 7) == 2)) { l.skip((uint32_t)(tag & 7)); continue; }
+            pb::Reader mr = l.sub();
+            int32_t pos = 0, refn = 0, parn = 0;
+            std::vector<int8_t> mutv;
+            Mutation m;
+            while (mr.more()) {
+                const uint64_t t2 = mr.varint();
+                const uint32_t f2 = (uint32_t)(t2 >> 3), w2 = (uint32_t)(t2 & 7);
+                if (f2 == 1 && w2 == 0) pos = (int32_t)mr.varint();
+                else if (f2 == 2 && w2 == 0) refn = (int32_t)mr.varint();
+                else if (f2 == 3 && w2 == 0) parn = (int32_t)mr.varint();
+                else if (f2 == 4 && w2 == 0) mutv.push_back((int8_t)mr.varint());
+                else if (f2 == 4 && w2 == 2) { pb::Reader pk = mr.sub(); while (pk.more()) mutv.push_back((int8_t)pk.varint()); }
+                else if (f2 == 5 && w2 == 2) { pb::Reader s = mr.sub(); m.chrom.assign((const char*)s.p, (size_t)(s.end - s.p)); }
+                else mr.skip(w2);
+            }
+            m.position = pos;
+            if (!m.is_masked()) {
+                m.ref_nuc = (int8_t)(1 << refn);
+                m.par_nuc = (int8_t)(1 << parn);
+                m.mut_nuc = get_nuc_id(mutv);
+                if (m.mut_nuc != m.par_nuc) node->add_mutation(m);   // :580
+            } else {
+                m.ref_nuc = m.par_nuc = m.mut_nuc = 0;
+                node->add_mutation(m);
+            }
+        }
+        if (!std::is_sorted(node->mutations.begin(), node->mutations.end())) {
+            fprintf(stderr, "WARNING: Mutations not sorted!\n");
+            std::sort(node->mutations.begin(), node->mutations.end());
+        }
+    }
+    for (auto c : conds) {
+        std::string name;
+        std::vector<std::string> members;
+        while (c.more()) {
+            const uint64_t tag = c.varint();
+            if ((tag & 7) != 2) { c.skip((uint32_t)(tag & 7)); continue; }
+            pb::Reader s = c.sub();
+            if ((tag >> 3) == 1) name.assign((const char*)s.p, (size_t)(s.end - s.p));
+            else if ((tag >> 3) == 2) members.emplace_back((const char*)s.p, (size_t)(s.end - s.p));
+        }
+        for (auto& m : members) tree.condensed_leaves.insert(m);
+        tree.condensed_nodes[name] = members;
+        tree.condensed_order.push_back(name);
+    }
+    return tree;
+}
+
+void save_mutation_annotated_tree(const Tree& tree, const std::string& filename) {   // reference :614-681
+    std::string out;
+    pb::put_bytes(out, 1, get_newick_string(tree, false, true, true));
+    auto dfs = tree.depth_first_expansion();
+    for (auto n : dfs) {
+        std::string list;
+        for (auto& m : n->mutations) {
+            std::string mm;
+            pb::put_i32(mm, 1, m.position);
+            if (m.is_masked()) {
+                pb::put_i32(mm, 2, -1);
+                pb::put_i32(mm, 3, -1);
+            } else {
+                pb::put_i32(mm, 2, get_nt(m.ref_nuc));
+                pb::put_i32(mm, 3, get_nt(m.par_nuc));
+                std::string packed;
+                for (auto b : get_nuc_vec_from_id(m.mut_nuc)) pb::put_varint(packed, (uint64_t)b);
+                if (!packed.empty()) pb::put_bytes(mm, 4, packed);
+            }
+            if (!m.chrom.empty()) pb::put_bytes(mm, 5, m.chrom);
+            pb::put_bytes(list, 1, mm);
+        }
+        pb::put_bytes(out, 2, list);
+    }
+    std::vector<std::string> order = tree.condensed_order;
+    for (auto& kv : tree.condensed_nodes)
+        if (std::find(order.begin(), order.end(), kv.first) == order.end()) order.push_back(kv.first);
+    for (auto& name : order) {
+        auto it = tree.condensed_nodes.find(name);
+        if (it == tree.condensed_nodes.end()) continue;
+        std::string c;
+        pb::put_bytes(c, 1, name);
+        for (auto& l : it->second) pb::put_bytes(c, 2, l);
+        pb::put_bytes(out, 3, c);
+    }
+    for (auto n : dfs) {
+        std::string meta;
+        for (auto& a : n->clade_annotations) pb::put_bytes(meta, 1, a);
+        pb::put_bytes(out, 4, meta);
+    }
+    if (!write_all(filename, out)) {
+        fprintf(stderr, "ERROR: Could not write %s\n", filename.c_str());
+        exit(1);
+    }
+}
+
+// ---------------------------------------------------------------- outputs / inputs around the placement
+void get_sample_mutation_paths(Tree* T, const std::vector<std::string>& samples, const std::string& filename) {
+    FILE* f = fopen(filename.c_str(), "w");   // reference :1991-2050
+    if (!f) { fprintf(stderr, "ERROR: cannot write %s\n", filename.c_str()); exit(1); }
+    for (auto& sample : samples) {
+        Node* sn = T->get_node(sample);
+        if (!sn) continue;   // not placed (thresholds)
+        std::vector<std::string> segs;
+        auto seg = [&](Node* n) {
+            if (n->mutations.empty()) return;
+            std::string s = n->identifier + ":";
+            for (size_t k = 0; k < n->mutations.size(); k++)
+                s += n->mutations[k].get_string() + (k + 1 < n->mutations.size() ? "," : " ");
+            segs.push_back(s);
+        };
+        seg(sn);
+        for (auto a : T->rsearch(sample)) seg(a);
+        fprintf(f, "%s\t", sample.c_str());
+        for (auto it = segs.rbegin(); it != segs.rend(); ++it) fputs(it->c_str(), f);
+        fputc('\n', f);
+    }
+    fclose(f);
+}
+
+void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Sample>& missing_samples,
+              bool create_new_mat) {
+    if (create_new_mat) {
+        fprintf(stderr, "ERROR: building a MAT from newick+VCF (Fitch-Sankoff, reference usher_mapper.cpp:6-161) is "
+                        "outside this build's scope; load a protobuf with -i.\n");
+        exit(1);
+    }
+    fprintf(stderr, "Loading VCF file\n");   // reference :2180-2278
+    std::string raw;
+    if (!read_all(vcf_filename, raw)) {
+        fprintf(stderr, "ERROR: Could not open the VCF file: %s!\n", vcf_filename.c_str());
+        exit(1);
+    }
+    std::istringstream in(raw);
+    bool header = false;
+    std::vector<std::string> ids;
+    std::vector<size_t> cols;
+    std::string line;
+    while (std::getline(in, line)) {
+        std::vector<std::string> w;
+        string_split(line, w);
+        if (!header && w.size() > 1) {
+            if (w[1] == "POS") {
+                for (size_t j = 9; j < w.size(); j++) {
+                    ids.push_back(w[j]);
+                    if (!T->get_node(w[j]) && !T->condensed_leaves.count(w[j])) {
+                        missing_samples.emplace_back(Missing_Sample(w[j]));
+                        cols.push_back(j);
+                    } else {
+                        fprintf(stderr, "WARNING: Ignoring sample %s as it is already in the tree.\n", w[j].c_str());
+                    }
+                }
+                header = true;
+            }
+        } else if (header) {
+            if (w.size() != 9 + ids.size()) {
+                fprintf(stderr, "ERROR! Incorrect VCF format. Expected %zu columns but got %zu.\n", 9 + ids.size(), w.size());
+                exit(1);
+            }
+            std::vector<std::string> alleles;
+            string_split(w[4], ',', alleles);
+            for (size_t k = 0; k < cols.size(); k++) {
+                const std::string& gt = w[cols[k]];
+                Mutation m;
+                m.chrom = w[0];
+                m.position = std::stoi(w[1]);
+                m.ref_nuc = get_nuc_id(w[3][0]);
+                m.par_nuc = m.ref_nuc;
+                bool add = false;
+                if (isdigit((unsigned char)gt[0])) {
+                    const int a = std::stoi(gt);
+                    if (a > 0) {
+                        const std::string& al = alleles.at((size_t)a - 1);   // first character only, like the reference
+                        m.mut_nuc = get_nuc_id(al[0]);
+                        m.is_missing = (al[0] == 'N') || m.mut_nuc == 15;
+                        add = true;
+                    }
+                } else {
+                    m.is_missing = true;
+                    m.mut_nuc = 15;
+                    add = true;
+                }
+                if (add) missing_samples[k].mutations.push_back(m);
+                if (m.mut_nuc & (m.mut_nuc - 1)) missing_samples[k].num_ambiguous++;
+            }
+        }
+    }
+}
+
+}  // namespace Mutation_Annotated_Tree

@@ -125,6 +125,11 @@ int main(int argc, char** argv) {
             for (auto& m : s.mutations) fprintf(f, "%d:%d:%d:%d,", m.position, m.ref_nuc, m.mut_nuc, (int)m.is_missing);
             fprintf(f, "\n");
         }
+        for (auto& name : T.condensed_order) {
+            fprintf(f, "C\t%s\t", name.c_str());
+            for (auto& m : T.condensed_nodes.at(name)) fprintf(f, "%s,", m.c_str());
+            fprintf(f, "\n");
+        }
         fprintf(f, "NEWICK\t%s\n", MAT::get_newick_string(T, true, true).c_str());
         fclose(f);
         return 0;

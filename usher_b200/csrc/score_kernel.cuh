@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
                 }
                 // chunks below i/kMutChunk are dead: refill their stages
                 while (mc_issue < mc_end && mc_issue < i / kMutChunk + kMutStages) {
+                    __syncwarp();   // every lane's reads of the dead stage are ordered before its refill
                     if (lane == 0) {
                         const uint32_t c = mc_issue, s = c % kMutStages;
                         mbar_expect_tx(bars_a + 8 * s, kMutChunk * 4);
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
                     mc_issue++;
                 }
                 const bool in = (i + lane) < re;
-                const uint32_t m = mring[(i + lane) % kMutRingWords];
+                const uint32_t m = in ? mring[(i + lane) % kMutRingWords] : 0u;   // lanes past the row may fall in a chunk still in flight
                 uint32_t hm = __ballot_sync(FULL, in && bitmap_test<SMEM_BITMAP>(bm_s, bm_g, m >> 6));
                 while (hm) {
                     const int j = __ffs(hm) - 1;

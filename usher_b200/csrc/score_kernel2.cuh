@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
             }
 
             // ================= G: stack levels later blocks can inherit from (last internal node per level) ======
+            __syncwarp();   // E/F read rows of `vals` with lane = node / per-lane loops; G overwrites stack rows
             {
                 const bool isint = act && !leaf;
                 const uint32_t peers = __match_any_sync(FULL, isint ? level : (0xffff0000u | lane));

@@ -104,3 +104,31 @@ def test_sorted_placement_and_saved_pb_reload(usher):
     txt = open(d2 + "/flat.txt").read()
     assert all(f"Sample{i}" in txt for i in range(1, 6))   # as a node or as a member of a condensed node
     assert not [l for l in txt.splitlines() if l.startswith("S\t")]   # all five are already in the tree now
+
+
+REF_TEST = "/root/reference/test"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TEST), reason="reference test inputs are only mounted in the build container")
+def test_build_mat_from_newick_and_vcf_matches_reference(usher):
+    """`usher -t global_phylo.nh -v global_samples.vcf -o tree.pb` (Fitch-Sankoff per site + condense + save):
+    same nodes, names, mutations, newick and condensed sets as the MAT the reference builds (config 1)."""
+    d = tempfile.mkdtemp()
+    r = subprocess.run([usher, "-t", REF_TEST + "/global_phylo.nh", "-v", REF_TEST + "/global_samples.vcf", "-o",
+                        d + "/tree.pb", "-d", d], capture_output=True, text=True)
+    assert r.returncode == 0 and "The parsimony score for this tree is: 500" in r.stderr
+    subprocess.check_call([usher, "-i", d + "/tree.pb", "-v", VCF, "--dump-flat", d + "/a.txt"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([usher, "-i", PB, "-v", VCF, "--dump-flat", d + "/b.txt"], stderr=subprocess.DEVNULL)
+    a, b = open(d + "/a.txt").read().splitlines(), open(d + "/b.txt").read().splitlines()
+    assert [l for l in a if not l.startswith("C\t")] == [l for l in b if not l.startswith("C\t")]
+    assert sorted(l for l in a if l.startswith("C\t")) == sorted(l for l in b if l.startswith("C\t"))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/scripts/testBranchLen2.nwk"), reason="reference not mounted")
+def test_fitch_sankoff_known_answer(usher):
+    """scripts/testBranchLen2.*: the input branch lengths are the expected per-branch mutation counts."""
+    d = tempfile.mkdtemp()
+    subprocess.check_call([usher, "-t", "/root/reference/scripts/testBranchLen2.nwk", "-v",
+                           "/root/reference/scripts/testBranchLen2.vcf", "--dump-flat", d + "/f.txt"], stderr=subprocess.DEVNULL)
+    nwk = [l for l in open(d + "/f.txt") if l.startswith("NEWICK\t")][0].split("\t")[1].strip()
+    assert nwk == "((a:0,(b:0,(c:0,d:1)node_4:1)node_3:2,((e:0,f:1)node_6:3,g:0)node_5:4)node_2:5,h:0)node_1:0;"

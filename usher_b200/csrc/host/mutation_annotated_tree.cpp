@@ -5,6 +5,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -680,12 +681,125 @@ void get_sample_mutation_paths(Tree* T, const std::vector<std::string>& samples,
     fclose(f);
 }
 
+// MAT construction: one Fitch-Sankoff pass per VCF row over the BFS vector (reference mapper_body,
+// src/usher_mapper.cpp:6-161, driven row by row from read_vcf :2099-2179).  Serial host code: this is the
+// pre-processing stage of `usher -t tree.nh -v samples.vcf -o tree.pb`, not the placement hot path.
+static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Sample>& missing_samples) {
+    std::vector<Node*> bfs = T->breadth_first_expansion();
+    std::unordered_map<std::string, size_t> bfs_idx;
+    for (size_t i = 0; i < bfs.size(); i++) bfs_idx[bfs[i]->identifier] = i;
+    const int big = (int)bfs.size();
+    std::vector<size_t> parent_idx(bfs.size(), (size_t)-1);
+    std::vector<uint8_t> is_leaf(bfs.size());
+    for (size_t i = 0; i < bfs.size(); i++) {
+        if (bfs[i]->parent) parent_idx[i] = bfs_idx[bfs[i]->parent->identifier];
+        is_leaf[i] = bfs[i]->is_leaf();
+    }
+    fprintf(stderr, "Loading VCF file.\n");
+    std::string raw;
+    if (!read_all(vcf_filename, raw)) {
+        fprintf(stderr, "ERROR: Could not open the VCF file: %s!\n", vcf_filename.c_str());
+        exit(1);
+    }
+    fprintf(stderr, "Computing parsimonious assignments for input variants.\n");
+    std::istringstream in(raw);
+    std::string line;
+    bool header = false;
+    std::vector<std::string> ids;
+    std::vector<long> col_node;      // BFS index of the column's sample, or -(1+k) for missing sample k
+    std::vector<std::array<int, 4>> score(bfs.size());
+    std::vector<int8_t> state(bfs.size());
+    while (std::getline(in, line)) {
+        std::vector<std::string> w;
+        string_split(line, w);
+        if (!header) {
+            if (w.size() > 1 && w[1] == "POS") {
+                for (size_t j = 9; j < w.size(); j++) {
+                    ids.push_back(w[j]);
+                    auto it = bfs_idx.find(w[j]);
+                    if (it == bfs_idx.end()) {
+                        missing_samples.emplace_back(Missing_Sample(w[j]));
+                        col_node.push_back(-(long)missing_samples.size());
+                    } else {
+                        col_node.push_back((long)it->second);
+                    }
+                }
+                header = true;
+            }
+            continue;
+        }
+        if (w.size() != 9 + ids.size()) {
+            fprintf(stderr, "ERROR! Incorrect VCF format.\n");
+            exit(1);
+        }
+        const int pos = std::stoi(w[1]);
+        const int8_t ref = get_nuc_id(w[3][0]);
+        const int ref_nt = get_nt(ref);
+        std::vector<std::string> alleles;
+        string_split(w[4], ',', alleles);
+        fprintf(stderr, "At variant site %i\n", pos);
+        // leaves: reference allele free, everything else "impossible" (:33-44); internal nodes start at 0
+        for (size_t i = 0; i < bfs.size(); i++) {
+            for (int j = 0; j < 4; j++) score[i][j] = (is_leaf[i] && j != ref_nt) ? big : 0;
+            state[i] = 0;
+        }
+        for (size_t c = 0; c < ids.size(); c++) {
+            const std::string& gt = w[9 + c];
+            int8_t nuc;
+            if (isdigit((unsigned char)gt[0])) {
+                const int a = std::stoi(gt);
+                if (a <= 0) continue;
+                nuc = get_nuc_id(alleles.at((size_t)a - 1)[0]);
+            } else {
+                nuc = 15;
+            }
+            if (col_node[c] >= 0) {
+                for (int j = 0; j < 4; j++) score[(size_t)col_node[c]][j] = (nuc & (1 << j)) ? 0 : big;
+            } else {
+                Mutation m;
+                m.chrom = w[0];
+                m.position = pos;
+                m.ref_nuc = ref;
+                m.par_nuc = ref;   // the reference leaves par_nuc unset here (:65-82); scoring never reads it
+                m.is_missing = (nuc == 15);
+                m.mut_nuc = nuc;
+                missing_samples[(size_t)(-col_node[c] - 1)].mutations.push_back(m);
+            }
+        }
+        // Sankoff forward pass: children before parents = reverse BFS (:86-111)
+        for (size_t i = bfs.size(); i-- > 1;) {
+            const size_t p = parent_idx[i];
+            for (int j = 0; j < 4; j++) {
+                int best = big + 1;
+                for (int k = 0; k < 4; k++) best = std::min(best, score[i][k] + (k != j));
+                score[p][j] += best;
+            }
+        }
+        // backward pass: keep the parent's state unless another base is strictly cheaper (:114-156)
+        for (size_t i = 0; i < bfs.size(); i++) {
+            const int8_t par_state = parent_idx[i] == (size_t)-1 ? (int8_t)ref_nt : state[parent_idx[i]];
+            int8_t st = par_state;
+            int best = score[i][par_state];
+            for (int j = 0; j < 4; j++) if (score[i][j] < best) { best = score[i][j]; st = (int8_t)j; }
+            state[i] = st;
+            if (st != par_state) {
+                Mutation m;
+                m.chrom = w[0];
+                m.position = pos;
+                m.ref_nuc = ref;
+                m.par_nuc = (int8_t)(1 << par_state);
+                m.mut_nuc = (int8_t)(1 << st);
+                bfs[i]->add_mutation(m);
+            }
+        }
+    }
+}
+
 void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Sample>& missing_samples,
               bool create_new_mat) {
     if (create_new_mat) {
-        fprintf(stderr, "ERROR: building a MAT from newick+VCF (Fitch-Sankoff, reference usher_mapper.cpp:6-161) is "
-                        "outside this build's scope; load a protobuf with -i.\n");
-        exit(1);
+        build_mat_from_vcf(T, vcf_filename, missing_samples);
+        return;
     }
     fprintf(stderr, "Loading VCF file\n");   // reference :2180-2278
     std::string raw;

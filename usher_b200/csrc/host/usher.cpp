@@ -11,7 +11,7 @@ namespace {
 struct Opt { const char* lng; char sht; bool arg; const char* help; };
 const Opt kOpts[] = {
     {"vcf", 'v', true, "Input VCF file (in uncompressed or gzip-compressed .gz format) [REQUIRED]"},
-    {"tree", 't', true, "Input tree file (newick; building a MAT from it is outside this build's scope)"},
+    {"tree", 't', true, "Input tree file"},
     {"outdir", 'd', true, "Output directory to dump output and log files [DEFAULT uses current directory]"},
     {"load-mutation-annotated-tree", 'i', true, "Load mutation-annotated tree object"},
     {"save-mutation-annotated-tree", 'o', true, "Save output mutation-annotated tree object to the specified filename"},
@@ -97,22 +97,26 @@ int main(int argc, char** argv) {
     if (vcf.empty() && resave.empty()) { fprintf(stderr, "the option '--vcf' is required but missing\n"); usage(); return 1; }
     MAT::Tree T;
     Timer timer;
+    bool from_newick = false;
     if (!din.empty()) {
         timer.Start();
         fprintf(stderr, "Loading existing mutation-annotated tree object from file %s\n", din.c_str());
         T = MAT::load_mutation_annotated_tree(din);
         fprintf(stderr, "Completed in %ld msec \n\n", timer.Stop());
     } else if (!tree_fn.empty()) {
-        fprintf(stderr, "ERROR: building a mutation-annotated tree from --tree + --vcf is outside this build's scope; "
-                        "use --load-mutation-annotated-tree.\n");
-        return 1;
+        fprintf(stderr, "Loading input tree.\n");
+        timer.Start();
+        T = MAT::create_tree_from_newick(tree_fn);
+        if (!T.root) { fprintf(stderr, "ERROR: Empty tree.\n"); return 1; }
+        fprintf(stderr, "Completed in %ld msec \n\n", timer.Stop());
+        from_newick = true;
     } else {
-        fprintf(stderr, "ERROR: must provide --load-mutation-annotated-tree\n");
+        fprintf(stderr, "Error! No input tree or assignment file provided!\n");
         return 1;
     }
     if (!resave.empty()) { MAT::save_mutation_annotated_tree(T, resave); return 0; }
     std::vector<Missing_Sample> missing;
-    MAT::read_vcf(&T, vcf, missing, false);
+    MAT::read_vcf(&T, vcf, missing, from_newick);
     if (!dump_flat.empty()) {
         FILE* f = fopen(dump_flat.c_str(), "w");
         for (auto n : T.depth_first_expansion()) {

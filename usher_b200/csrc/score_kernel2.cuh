@@ -29,8 +29,9 @@ namespace ub200 {
 constexpr int kWarps2 = 16;
 constexpr int kThreads2 = kWarps2 * 32;
 constexpr uint32_t kHitCap = 192;
-constexpr uint32_t kMutChunk2 = 128;                      // words per bulk copy in this kernel (512 B)
-constexpr uint32_t kMutRing2 = kMutChunk2 * kMutStages;   // 512 words = 2 KB
+constexpr uint32_t kMutChunk2 = 256;                      // words per bulk copy in this kernel (1 KB)
+constexpr int kMutStages2 = 2;
+constexpr uint32_t kMutRing2 = kMutChunk2 * kMutStages2;  // 512 words = 2 KB
 // per-warp shared memory (bytes)
 constexpr uint32_t kOffMring = 0;       // u32[512]
 constexpr uint32_t kOffHring = 2048;    // uint4[64]  (2 stages)
@@ -67,6 +68,9 @@ __device__ __forceinline__ int lds_s16(uint32_t a) {
 // stack levels beyond the 32 kept in shared memory live in HBM; out of line so the hot path stays short
 __device__ __noinline__ int spill_read(const int32_t* gstk, uint32_t code, uint32_t s) {
     return gstk[(size_t)(code - kSrcSpill) * 32u + s];
+}
+__device__ __noinline__ void spill_write(int32_t* gstk, uint32_t level, uint32_t s, int v) {
+    gstk[(size_t)(level - kStackDepth) * 32u + s] = v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     for (uint32_t i = lane; i < kMutRing2; i += 32) mring[i] = 0u;
     vals[kRowZero * 32u + lane] = 0;
     if (lane == 0) {
-        for (int i = 0; i < kMutStages + kHdrStages2; i++) mbar_init(bars_a + 8 * i, 1);
+        for (int i = 0; i < kMutStages2 + kHdrStages2; i++) mbar_init(bars_a + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -146,8 +150,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     };
     auto stack_read = [&](uint32_t level, uint32_t s) -> int { return value_of(src_level(level), s); };
     auto stack_write = [&](uint32_t level, uint32_t s, int v) {
-        if (level < (uint32_t)kStackDepth) vals[(kRowStack + level) * 32u + s] = (int16_t)v;
-        else gstk[(size_t)(level - kStackDepth) * 32u + s] = v;
+        if (__builtin_expect(level >= (uint32_t)kStackDepth, 0)) spill_write(gstk, level, s, v);
+        else vals[(kRowStack + level) * 32u + s] = (int16_t)v;
     };
 
     // per-lane (= sample) running best
@@ -205,19 +209,19 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
         uint32_t hc_issue = n0 / kHdrChunk;
         const uint32_t hc_end = (n1 - 1) / kHdrChunk + 1;
         if (lane == 0) {
-            for (int i = 0; i < kMutStages && mc_issue + i < mc_end; i++) {
-                const uint32_t c = mc_issue + i, s = c % kMutStages;
+            for (int i = 0; i < kMutStages2 && mc_issue + i < mc_end; i++) {
+                const uint32_t c = mc_issue + i, s = c % kMutStages2;
                 mbar_expect_tx(bars_a + 8 * s, kMutChunk2 * 4);
                 bulk_g2s(mring_a + s * kMutChunk2 * 4, p.mutw + (size_t)c * kMutChunk2, kMutChunk2 * 4, bars_a + 8 * s);
             }
             for (int i = 0; i < kHdrStages2 && hc_issue + i < hc_end; i++) {
                 const uint32_t c = hc_issue + i, s = c % kHdrStages2;
-                mbar_expect_tx(bars_a + 8 * (kMutStages + s), kHdrChunk * 16);
+                mbar_expect_tx(bars_a + 8 * (kMutStages2 + s), kHdrChunk * 16);
                 bulk_g2s(hring_a + s * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
-                         bars_a + 8 * (kMutStages + s));
+                         bars_a + 8 * (kMutStages2 + s));
             }
         }
-        mc_issue = min(mc_issue + kMutStages, mc_end);
+        mc_issue = min(mc_issue + kMutStages2, mc_end);
         hc_issue = min(hc_issue + kHdrStages2, hc_end);
 
         // cross-warp bound of this lane's sample, and the tile-local floor of every value the tile can reference
@@ -267,15 +271,15 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
             // ================= A: headers (lane = node) =================
             {
                 const uint32_t hc = blk / kHdrChunk, s = hc % kHdrStages2;
-                mbar_wait(bars_a + 8 * (kMutStages + s), (hphase >> s) & 1u);
+                mbar_wait(bars_a + 8 * (kMutStages2 + s), (hphase >> s) & 1u);
                 hphase ^= 1u << s;
                 if (hc_issue < hc_end && hc_issue < hc + kHdrStages2) {
                     // the previous block's header stage was consumed before its __syncwarp()s
                     if (lane == 0) {
                         const uint32_t c = hc_issue, s2 = c % kHdrStages2;
-                        mbar_expect_tx(bars_a + 8 * (kMutStages + s2), kHdrChunk * 16);
+                        mbar_expect_tx(bars_a + 8 * (kMutStages2 + s2), kHdrChunk * 16);
                         bulk_g2s(hring_a + s2 * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
-                                 bars_a + 8 * (kMutStages + s2));
+                                 bars_a + 8 * (kMutStages2 + s2));
                     }
                     hc_issue++;
                 }
@@ -314,41 +318,54 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                 const uint32_t c_first = rs_run / kMutChunk2, c_last = (reb - 1u) / kMutChunk2;
                 for (uint32_t c = c_first; c <= c_last; c++) {
                     if (c >= mc_wait) {
-                        const uint32_t s = c % kMutStages;
+                        const uint32_t s = c % kMutStages2;
                         mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
                         mphase ^= 1u << s;
                         mc_wait = c + 1;
                     }
                     // chunks below c are dead (only this block needed them): refill their stages
-                    while (mc_issue < mc_end && mc_issue < c + kMutStages) {
+                    while (mc_issue < mc_end && mc_issue < c + kMutStages2) {
                         if (lane == 0) {
-                            const uint32_t cc = mc_issue, s = cc % kMutStages;
+                            const uint32_t cc = mc_issue, s = cc % kMutStages2;
                             mbar_expect_tx(bars_a + 8 * s, kMutChunk2 * 4);
                             bulk_g2s(mring_a + s * kMutChunk2 * 4, p.mutw + (size_t)cc * kMutChunk2, kMutChunk2 * 4,
                                      bars_a + 8 * s);
                         }
                         mc_issue++;
                     }
-                    const uint32_t base = c * kMutChunk2 + 4u * lane;
-                    const uint4 q = lds128(mring_a + (((c % kMutStages) * kMutChunk2 + 4u * lane) << 2));
-                    const uint32_t w0 = SMEM_BITMAP ? lds32(bm_a + ((q.x >> 11) << 2)) : __ldg(bm_g + (q.x >> 11));
-                    const uint32_t w1 = SMEM_BITMAP ? lds32(bm_a + ((q.y >> 11) << 2)) : __ldg(bm_g + (q.y >> 11));
-                    const uint32_t w2 = SMEM_BITMAP ? lds32(bm_a + ((q.z >> 11) << 2)) : __ldg(bm_g + (q.z >> 11));
-                    const uint32_t w3 = SMEM_BITMAP ? lds32(bm_a + ((q.w >> 11) << 2)) : __ldg(bm_g + (q.w >> 11));
-                    uint32_t hb = ((w0 >> ((q.x >> 6) & 31u)) & 1u) | (((w1 >> ((q.y >> 6) & 31u)) & 1u) << 1) |
-                                  (((w2 >> ((q.z >> 6) & 31u)) & 1u) << 2) | (((w3 >> ((q.w >> 6) & 31u)) & 1u) << 3);
-                    if (c == c_first || c == c_last) {   // warp-uniform: mask the words outside [rs_run, reb)
-                        const uint32_t span = reb - rs_run, o = base - rs_run;
-                        hb &= (o < span ? 1u : 0u) | (o + 1u < span ? 2u : 0u) | (o + 2u < span ? 4u : 0u) |
-                              (o + 3u < span ? 8u : 0u);
-                    }
-                    if (hb) {
-                        const uint32_t slot = atomicAdd(&info[kInfoH], (uint32_t)__popc(hb));
-                        uint32_t k = slot;
-                        if (hb & 1u) hitbuf[k++] = make_uint2(q.x, base);
-                        if (hb & 2u) hitbuf[k++] = make_uint2(q.y, base + 1u);
-                        if (hb & 4u) hitbuf[k++] = make_uint2(q.z, base + 2u);
-                        if (hb & 8u) hitbuf[k++] = make_uint2(q.w, base + 3u);
+                    const bool edge = (c == c_first || c == c_last);   // warp-uniform
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        const uint32_t base = c * kMutChunk2 + half * 128u + 4u * lane;
+                        const uint4 q = lds128(mring_a + (((c % kMutStages2) * kMutChunk2 + half * 128u + 4u * lane) << 2));
+                        const uint32_t w0 = SMEM_BITMAP ? lds32(bm_a + ((q.x >> 11) << 2)) : __ldg(bm_g + (q.x >> 11));
+                        const uint32_t w1 = SMEM_BITMAP ? lds32(bm_a + ((q.y >> 11) << 2)) : __ldg(bm_g + (q.y >> 11));
+                        const uint32_t w2 = SMEM_BITMAP ? lds32(bm_a + ((q.z >> 11) << 2)) : __ldg(bm_g + (q.z >> 11));
+                        const uint32_t w3 = SMEM_BITMAP ? lds32(bm_a + ((q.w >> 11) << 2)) : __ldg(bm_g + (q.w >> 11));
+                        uint32_t hb = ((w0 >> ((q.x >> 6) & 31u)) & 1u) | (((w1 >> ((q.y >> 6) & 31u)) & 1u) << 1) |
+                                      (((w2 >> ((q.z >> 6) & 31u)) & 1u) << 2) | (((w3 >> ((q.w >> 6) & 31u)) & 1u) << 3);
+                        if (edge) {   // mask the words outside [rs_run, reb)
+                            const uint32_t span = reb - rs_run, o = base - rs_run;
+                            hb &= (o < span ? 1u : 0u) | (o + 1u < span ? 2u : 0u) | (o + 2u < span ? 4u : 0u) |
+                                  (o + 3u < span ? 8u : 0u);
+                        }
+                        if (hb) {
+                            const uint32_t slot = atomicAdd(&info[kInfoH], (uint32_t)__popc(hb));
+                            uint32_t k = slot;
+                            if (hb & 1u) hitbuf[k++] = make_uint2(q.x, base);
+                            if (hb & 2u) hitbuf[k++] = make_uint2(q.y, base + 1u);
+                            if (hb & 4u) hitbuf[k++] = make_uint2(q.z, base + 2u);
+                            if (hb & 8u) hitbuf[k++] = make_uint2(q.w, base + 3u);
+                        }
+                        if (half == 0) {
+                            __syncwarp();
+                            if (info[kInfoH] > kHitCap - 128) {
+                                process_hits(info[kInfoH]);
+                                __syncwarp();
+                                if (lane == 0) info[kInfoH] = 0;
+                                __syncwarp();
+                            }
+                        }
                     }
                     __syncwarp();
                     const uint32_t H = info[kInfoH];

@@ -252,7 +252,8 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     M->device = device;
     M->num_sms = prop.multiProcessorCount;
     M->grid = (uint32_t)M->num_sms * 2u;
-    const uint32_t total_warps = M->grid * ub200::kWarpsPerCta;
+    // workers of either kernel (k_score: 2 CTAs x 8 warps per SM, k_score2: 1 CTA x kWarps2)
+    const uint32_t total_warps = std::max<uint32_t>(M->grid * ub200::kWarpsPerCta, (uint32_t)M->num_sms * ub200::kWarps2);
     std::string err;
     int rc = ub200::derive(*flat, total_warps * 8u, M->d, err);
     if (rc != UB200_OK) { delete M; return fail(rc, err); }

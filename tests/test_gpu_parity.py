@@ -130,3 +130,21 @@ def test_bad_samples_are_rejected():
         m.place_batch(np.array([0, 2], np.uint64), calls)
     assert e.value.code == -5
     m.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_config5_ambiguity_and_n_runs_vs_reference():
+    """BASELINE config 5 at reduced size: IUPAC-widened calls and N runs (mean length 200) over mutated path
+    positions; score, best node, tie index, num_best and sibling/child flag bit-exact against the reference's own
+    mapper2_body (many-way ties included)."""
+    s = capi.Synth(30_000, 8.0, 30_000, capi.Synth.SC2, 20260929)
+    p, r, mu = s.arrays()
+    sp, sc, _ = s.samples(96, capi.Synth.AMBIG, 55)
+    m = capi.Mat.from_flat_struct(s.flat)
+    got = common.placements_to_dict(m.place_batch(sp, sc, best_set=True))
+    rt = ref.RefTree.from_flat(p, r, mu)
+    o = rt.search(sp, sc, len(p), threads=os.cpu_count() or 1)
+    for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
+        assert np.array_equal(np.asarray(got[k]).astype(np.int64), o[k].astype(np.int64)), k
+    assert (o["num_best"] > 1).any()
+    rt.close(); m.close(); s.close()

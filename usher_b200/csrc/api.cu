@@ -81,6 +81,7 @@ struct ub200_samples {
     uint32_t* tab = nullptr;
     int32_t* base = nullptr;
     int32_t* gbest = nullptr;
+    uint32_t* tile_counter = nullptr;
     ub200_placement* results = nullptr;
     int32_t* best_rel = nullptr;
     unsigned long long* part_key = nullptr;
@@ -144,7 +145,7 @@ int launch_score(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngrou
     p.part_key = S->part_key; p.part_cnt = S->part_cnt;
     p.gstack = M->gstack; p.gstack_levels = M->gstack_levels;
     p.node_scores = S->node_scores; p.target_rel = S->best_rel;
-    p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
+    p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill; p.tile_counter = nullptr;
     const uint32_t grid = std::max<uint32_t>(ngroups, (M->grid / ngroups) * ngroups);
     const uint32_t bm_bytes = smem_bitmap ? ((S->bitmap_words * 4u + 127u) & ~127u) : 0u;
     const size_t smem = bm_bytes + (size_t)kWarpsPerCta * kWarpSmemBytes;
@@ -162,7 +163,8 @@ int launch_score(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngrou
 }
 
 // Block-parallel best-placement kernel (score_kernel2.cuh); same parameters, one 12-warp CTA per SM.
-int launch_score2(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, bool smem_bitmap, uint32_t* grid_out) {
+int launch_score2(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, bool smem_bitmap, uint32_t* grid_out,
+                  bool collect = false) {
     using namespace ub200;
     ScoreParams p;
     p.mutw = M->mutw; p.hdr = M->hdr; p.row32 = M->row32;
@@ -172,20 +174,22 @@ int launch_score2(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngro
     p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups;
     p.part_key = S->part_key; p.part_cnt = S->part_cnt;
     p.gstack = M->gstack; p.gstack_levels = M->gstack_levels;
-    p.node_scores = nullptr; p.target_rel = nullptr; p.set_out = nullptr; p.set_ptr = nullptr; p.set_fill = nullptr;
+    p.node_scores = nullptr; p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
+    p.tile_counter = S->tile_counter;
+    CU(cudaMemsetAsync(S->tile_counter, 0, 64, M->stream));
     const uint32_t grid = std::max<uint32_t>(ngroups, ((uint32_t)M->num_sms / ngroups) * ngroups);
     *grid_out = grid;
     const uint32_t bm_bytes = smem_bitmap ? ((S->bitmap_words * 4u + 127u) & ~127u) : 0u;
     const size_t smem = bm_bytes + kLutBytes + (size_t)kWarps2 * kWarpSmem2;
-    if (smem_bitmap) {
-        auto k = k_score2<true>;
+    auto go = [&](auto k) -> int {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, kThreads2, smem, M->stream>>>(p);
-    } else {
-        auto k = k_score2<false>;
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kThreads2, smem, M->stream>>>(p);
-    }
+        return 0;
+    };
+    int rc;
+    if (smem_bitmap) rc = collect ? go(k_score2<true, true>) : go(k_score2<true, false>);
+    else rc = collect ? go(k_score2<false, true>) : go(k_score2<false, false>);
+    if (rc) return rc;
     CU(cudaGetLastError());
     return 0;
 }
@@ -340,7 +344,7 @@ void ub200_samples_free(ub200_samples* S) {
     if (!S) return;
     cudaSetDevice(S->mat->device);
     cudaFree(S->calls); cudaFree(S->sample_ptr); cudaFree(S->call_sample); cudaFree(S->bitmap); cudaFree(S->tab);
-    cudaFree(S->base); cudaFree(S->gbest); cudaFree(S->results); cudaFree(S->best_rel); cudaFree(S->part_key); cudaFree(S->part_cnt);
+    cudaFree(S->base); cudaFree(S->gbest); cudaFree(S->tile_counter); cudaFree(S->results); cudaFree(S->best_rel); cudaFree(S->part_key); cudaFree(S->part_cnt);
     cudaFree(S->node_scores); cudaFree(S->set_out); cudaFree(S->set_ptr); cudaFree(S->set_fill);
     delete S;
 }
@@ -393,6 +397,7 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
         if (!rc) rc = alloc((void**)&S->tab, (size_t)g * M->L * 32);
         if (!rc) rc = alloc((void**)&S->base, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->gbest, (size_t)g * 32 * 4);
+        if (!rc && !S->tile_counter) rc = alloc((void**)&S->tile_counter, 64);
         if (!rc) rc = alloc((void**)&S->results, (size_t)g * 32 * sizeof(ub200_placement));
         if (!rc) rc = alloc((void**)&S->best_rel, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->sample_ptr, ((size_t)g * 32 + 1) * 8);
@@ -508,7 +513,10 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
         CU(cudaMemsetAsync(S->set_fill, 0, (size_t)S->n_groups * 32 * 4, M->stream));
         for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
             const uint32_t ng = std::min(NG, S->n_groups - g0);
-            int rc = launch_score<ub200::kModeCollect>(M, S, g0, ng, smem_bitmap); if (rc) return rc;
+            uint32_t grid_unused = 0;
+            int rc = use_v2 ? launch_score2(M, S, g0, ng, smem_bitmap_v2, &grid_unused, true)
+                            : launch_score<ub200::kModeCollect>(M, S, g0, ng, smem_bitmap);
+            if (rc) return rc;
             M->last.total_launches++;
         }
         M->last.total_launches++;

@@ -63,6 +63,7 @@ struct ScoreParams {
     uint32_t* set_out;            // MODE 2
     const unsigned long long* set_ptr;
     uint32_t* set_fill;
+    uint32_t* tile_counter;       // k_score2: [ngroups] next tile to hand out (zeroed before each launch)
 };
 
 // ---------------------------------------------------------------- PTX helpers

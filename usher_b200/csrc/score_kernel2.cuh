@@ -95,7 +95,9 @@ __device__ __forceinline__ void unpack_delta(int v, int& dcorr, int& da, int& dc
     dcorr = (v1 - da) >> 10;
 }
 
-template <bool SMEM_BITMAP>
+// COLLECT = false: best placement per sample.  COLLECT = true: second pass that lists every optimal node of each
+// sample (best_j_vec + node_has_unique); the final best score is the bound, so almost every block is pruned.
+template <bool SMEM_BITMAP, bool COLLECT>
 __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -154,11 +156,18 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
         else vals[(kRowStack + level) * 32u + s] = (int16_t)v;
     };
 
-    // per-lane (= sample) running best
-    int bsc = 0x7fffffff;
+    // per-lane (= sample) running best (COLLECT: the known final best, fixed)
+    int bsc = COLLECT ? (live ? p.target_rel[sample] : (int)0x80000000) : 0x7fffffff;
     unsigned long long bkey = ~0ull;
     uint32_t cnt = 0;
-    auto merge = [&](int sc, uint32_t tiekey, uint32_t hu) {
+    auto merge = [&](int sc, uint32_t tiekey, uint32_t hu, uint32_t node) {
+        if (COLLECT) {
+            if (sc == bsc) {
+                const uint32_t k = atomicAdd(p.set_fill + sample, 1u);
+                p.set_out[p.set_ptr[sample] + k] = node | (hu ? 0x80000000u : 0u);
+            }
+            return;
+        }
         const unsigned long long key =
             ((unsigned long long)(uint32_t)(sc + kScoreBias) << 33) | ((unsigned long long)tiekey << 1) | hu;
         if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
@@ -200,7 +209,14 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
 
     uint32_t mphase = 0, hphase = 0;
 
-    for (uint32_t t = wig; t < p.n_tiles; t += wpg) {
+    (void)wig; (void)wpg;
+    for (;;) {
+        // tiles are handed out in DFS order by a per-group counter: balances uneven tiles, and the CTAs of
+        // different groups still walk the tree in the same order (one HBM read, the rest from L2)
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(p.tile_counter + group, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= p.n_tiles) break;
         const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
         const uint32_t ms = p.row32[n0], me = p.row32[n1];
         uint32_t mc_issue = ms / kMutChunk2;
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
         hc_issue = min(hc_issue + kHdrStages2, hc_end);
 
         // cross-warp bound of this lane's sample, and the tile-local floor of every value the tile can reference
-        int gb = live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff;
+        int gb = COLLECT ? bsc : (live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff);
         int gmin = 0;
 
         // ================= seed: running corrections of the tile's root path (levels 0 .. depth-1) =================
@@ -437,7 +453,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                         const int scj = __shfl_sync(FULL, sc, j);
                         const uint32_t tkj = __shfl_sync(FULL, h.y, j);
                         const uint32_t huj = __shfl_sync(FULL, (flags & kFlagHu0) ? 1u : 0u, j);
-                        if (lane == s) merge(scj, tkj, huj);
+                        if (lane == s) merge(scj, tkj, huj, blk + j);
                     }
                 }
             }
@@ -466,7 +482,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
                         hu = (masked || (int)(w >> 16) > common) ? 1u : 0u;
                         valid = (fl & kFlagLeaf) ? common > 0 : (!hu || common > 0);
                     }
-                    if (valid && sc <= bsc) merge(sc, info[kInfoTie + n], hu);
+                    if (valid && sc <= bsc) merge(sc, info[kInfoTie + n], hu, blk + n);
                 }
             }
 
@@ -489,10 +505,11 @@ __global__ void __launch_bounds__(kThreads2, 1) k_score2(const ScoreParams p) {
             __syncwarp();
         }
         // publish an improved bound for the other warps working on this sample group
-        if (live && bsc < gb) atomicMin(p.gbest + sample, bsc);
+        if (!COLLECT && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
         __syncwarp();
     }
 
+    if (COLLECT) return;
     // fold the CTA's warps in shared memory (the rings are dead now), one partial row per CTA
     __syncthreads();
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);

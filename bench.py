@@ -120,7 +120,9 @@ def cpu_reference_rate(synth, calls_list, threads, target_seconds, log_prefix):
     rt = ref.RefTree.from_flat(p, r, m)
     log(f"{log_prefix} reference MAT::Tree built in {time.time() - t:.1f}s")
     n = len(p)
-    # calibrate: a thin slice first, then pick the stride that fits the budget
+    # calibrate: a thin slice first (after one throw-away call that pays the one-time BFS expansion), then pick
+    # the stride that fits the budget
+    rt.search_strided(calls_list[0], 4096, 0, threads)
     sec, _ = rt.search_strided(calls_list[0], 256, 0, threads)
     est_full = sec * 256
     stride = 1

@@ -358,8 +358,9 @@ double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, u
     const size_t total_nodes = bfs.size();
     const size_t visits = (total_nodes > offset) ? (total_nodes - offset + stride - 1) / stride : 0;
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::vector<MAT::Mutation>> node_excess_mutations(visits);
-    std::vector<std::vector<MAT::Mutation>> node_imputed_mutations(visits);
+    // one extra slot: pass 2 may revisit BFS node 0 (the initial best_j_vec entry) which is not on the stride
+    std::vector<std::vector<MAT::Mutation>> node_excess_mutations(visits + 1);
+    std::vector<std::vector<MAT::Mutation>> node_imputed_mutations(visits + 1);
     size_t best_node_num_leaves = 0;
     int best_set_difference = (int)(sample.size() + T->root->mutations.size() + 1);
     size_t best_j = 0;
@@ -374,7 +375,7 @@ double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, u
         tbb::parallel_for(tbb::blocked_range<size_t>(0, cnt), [&](tbb::blocked_range<size_t> r) {
             for (size_t q = r.begin(); q < r.end(); ++q) {
                 const size_t k = only ? (*only)[q] : offset + q * stride;
-                const size_t slot = only ? (k - offset) / stride : q;
+                const size_t slot = !only ? q : ((k >= offset && (k - offset) % stride == 0) ? (k - offset) / stride : visits);
                 mapper2_input inp;
                 inp.T = T;
                 inp.node = bfs[k];

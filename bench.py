@@ -143,7 +143,7 @@ def run_reference(args, wl, rank, world):
     log(f"[ref] synthetic MAT: {nodes} nodes, {synth.m} mutations in {time.time() - t:.1f}s")
     sp, sc, _ = synth.samples(args.steps + args.warmup, fam, 777)
     calls = [sc[int(sp[i]):int(sp[i + 1])] for i in range(args.steps + args.warmup)]
-    rt, stride, est_full, n = cpu_reference_rate(synth, calls, threads, 3.0, "[ref]")
+    rt, stride, est_full, n = cpu_reference_rate(synth, calls, threads, 10.0, "[ref]")
     log(f"[ref] one full search ~{est_full:.1f}s on {threads} threads -> stride {stride}")
     for i in range(args.warmup):
         rt.search_strided(calls[i], stride, 0, threads)

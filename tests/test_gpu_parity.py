@@ -29,6 +29,18 @@ def test_golden_vectors(path):
     m.close()
 
 
+@pytest.mark.parametrize("path", common.golden_cases()[::3], ids=lambda p: p.split("/")[-1])
+def test_golden_vectors_many_tiles(path, monkeypatch):
+    """Same vectors with the tree cut into many small tiles: every tile re-seeds its root path from seed segments."""
+    monkeypatch.setenv("UB200_MIN_TILE", "96")
+    g = common.load(path)
+    m = capi.Mat(g["parent"], g["row_ptr"], g["muts"])
+    assert m.info.n_tiles > 1 or len(g["parent"]) < 64
+    res = m.place_batch(g["s_ptr"], g["calls"], best_set=True)
+    common.assert_matches_expected(g, common.placements_to_dict(res), path)
+    m.close()
+
+
 @pytest.mark.parametrize("pass_samples", [32, 64, 256])
 def test_pass_width_does_not_change_results(pass_samples):
     g = common.load(common.GOLDEN + "/random_07.npz")

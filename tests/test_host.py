@@ -19,7 +19,7 @@ from usher_b200 import capi
 @pytest.mark.parametrize("path", common.golden_cases(), ids=lambda p: p.split("/")[-1])
 def test_derivation_and_closed_form_match_golden(path):
     g = common.load(path)
-    d = capi.debug_derive(g["parent"], g["row_ptr"], g["muts"], target_tiles=7)
+    d = capi.debug_derive(g["parent"], g["row_ptr"], g["muts"], target_tiles=7, min_tile_cost=96)
     n = len(g["parent"])
     if n > 600:  # keep the pure-Python model quick
         sel = np.arange(0, len(g["s_ptr"]) - 1)[:12]
@@ -38,6 +38,16 @@ def test_derivation_and_closed_form_match_golden(path):
         assert [x for x, _ in r["optimal"]] == g["exp_best_set"][a:b].tolist()
         assert [h for _, h in r["optimal"]] == g["exp_best_set_unique"][a:b].tolist()
         assert np.array_equal(ns[i], g["exp_node_scores"][s])
+    # the segment layout of k_score3, interpreted the way that kernel does
+    res3 = kernel_model.place3(d, sub_ptr, sub_calls)
+    assert len(d["tile3_start"]) > 2 or n < 64
+    for i, s in enumerate(sel):
+        r = res3[i]
+        assert (r["score"], r["best_node"], r["best_j"], r["num_best"], r["has_unique"]) == (
+            int(g["exp_score"][s]), int(g["exp_best_dfs"][s]), int(g["exp_best_j"][s]), int(g["exp_num_best"][s]),
+            int(g["exp_has_unique"][s])), (path, s, "k_score3 layout")
+        a, b = int(g["exp_best_set_ptr"][s]), int(g["exp_best_set_ptr"][s + 1])
+        assert [x for x, _ in r["optimal"]] == g["exp_best_set"][a:b].tolist()
 
 
 def test_derive_structure():

@@ -45,7 +45,9 @@ class DerivedView(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("genome_len", C.c_uint32), ("max_level", C.c_uint32),
                 ("n_tiles", C.c_uint32), ("n_mutations", C.c_uint64)] + [
         (k, C.c_void_p) for k in ("level", "tie_index", "num_leaves", "tiekey", "key_to_node", "row32", "mutw",
-                                  "hdr", "ref_of", "tile_start", "anc_ptr", "anc")]
+                                  "hdr", "ref_of", "tile_start", "anc_ptr", "anc")] + [
+        ("n_tiles3", C.c_uint32), ("n_seed_segs", C.c_uint32), ("stream_words", C.c_uint64)] + [
+        (k, C.c_void_p) for k in ("stream", "hdr3", "tile3_start", "tile3_w0", "tile3_lvl", "tile3_sseg", "seed_end")]
 
 
 class UB200Error(RuntimeError):
@@ -93,7 +95,7 @@ def lib():
         L.ub200_mat_set_stream.argtypes = [vp, vp]
         L.ub200_mat_synchronize.argtypes = [vp]
         L.ub200_last_timing.argtypes = [vp, C.POINTER(Timing)]
-        L.ub200_debug_derive.argtypes = [C.POINTER(FlatMat), u32, C.POINTER(vp), C.POINTER(DerivedView),
+        L.ub200_debug_derive.argtypes = [C.POINTER(FlatMat), u32, u32, C.POINTER(vp), C.POINTER(DerivedView),
                                          C.c_char_p, C.c_size_t]
         L.ub200_debug_derive_free.argtypes = [vp]
         L.ub200_debug_derive_free.restype = None
@@ -145,13 +147,13 @@ def _view(ptr, dtype, count):
     return np.frombuffer(buf, dtype=dtype, count=count)
 
 
-def debug_derive(parent, row_ptr, muts, tie_index=None, target_tiles=64):
+def debug_derive(parent, row_ptr, muts, tie_index=None, target_tiles=64, min_tile_cost=0):
     """Host-only: run the derivation and return copies of the derived arrays (no GPU needed)."""
     f = make_flat(parent, row_ptr, muts, tie_index)
     h = C.c_void_p()
     v = DerivedView()
     err = C.create_string_buffer(512)
-    rc = lib().ub200_debug_derive(C.byref(f), target_tiles, C.byref(h), C.byref(v), err, 512)
+    rc = lib().ub200_debug_derive(C.byref(f), target_tiles, min_tile_cost, C.byref(h), C.byref(v), err, 512)
     if rc != 0:
         raise UB200Error(rc, err.value.decode())
     n, T = v.n_nodes, v.n_tiles
@@ -166,6 +168,17 @@ def debug_derive(parent, row_ptr, muts, tie_index=None, target_tiles=64):
         "anc_ptr": _view(v.anc_ptr, np.uint32, T + 1).copy(),
     }
     out["anc"] = _view(v.anc, np.uint32, int(out["anc_ptr"][-1])).copy()
+    T3 = v.n_tiles3
+    if T3:   # k_score3 layout
+        out.update({
+            "stream": _view(v.stream, np.uint32, int(v.stream_words)).copy(),
+            "hdr3": _view(v.hdr3, HDR_DTYPE, n).copy(),
+            "tile3_start": _view(v.tile3_start, np.uint32, T3 + 1).copy(),
+            "tile3_w0": _view(v.tile3_w0, np.uint32, T3 + 1).copy(),
+            "tile3_lvl": _view(v.tile3_lvl, np.uint32, T3).copy(),
+            "tile3_sseg": _view(v.tile3_sseg, np.uint32, T3 + 1).copy(),
+            "seed_end": _view(v.seed_end, np.uint32, v.n_seed_segs).copy(),
+        })
     lib().ub200_debug_derive_free(h)
     return out
 

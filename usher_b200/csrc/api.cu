@@ -11,7 +11,7 @@
 #include <cstdlib>
 
 #include "score_kernel.cuh"
-#include "score_kernel2.cuh"
+#include "score_kernel3.cuh"
 #include "ub200_internal.h"
 #include "usher_b200.h"
 
@@ -48,7 +48,15 @@ struct ub200_mat {
     ub200::Derived d;           // host copies of the small derived arrays (big ones are freed after upload)
     uint32_t n = 0, n_tiles = 0, L = 0;
     uint64_t m = 0;
-    // device
+    // device: k_score3 layout (always resident when the genome fits its 23-bit position field)
+    uint32_t* mstream = nullptr;
+    ub200::NodeHdr* hdr3 = nullptr;
+    uint32_t *tiekey = nullptr, *tile3_start = nullptr, *tile3_w0 = nullptr, *tile3_lvl = nullptr, *tile3_sseg = nullptr,
+             *seed_end = nullptr;
+    int32_t* gstack3 = nullptr;
+    uint32_t gstack3_levels = 0, n_tiles3 = 0;
+    // device: k_score layout, uploaded on first use (per-node scores, oversized rows / call lists)
+    bool v1_resident = false;
     uint32_t* mutw = nullptr;
     ub200::NodeHdr* hdr = nullptr;
     uint32_t *row32 = nullptr, *tile_start = nullptr, *anc_ptr = nullptr, *anc = nullptr;
@@ -145,7 +153,7 @@ int launch_score(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngrou
     p.part_key = S->part_key; p.part_cnt = S->part_cnt;
     p.gstack = M->gstack; p.gstack_levels = M->gstack_levels;
     p.node_scores = S->node_scores; p.target_rel = S->best_rel;
-    p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill; p.tile_counter = nullptr;
+    p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
     const uint32_t grid = std::max<uint32_t>(ngroups, (M->grid / ngroups) * ngroups);
     const uint32_t bm_bytes = smem_bitmap ? ((S->bitmap_words * 4u + 127u) & ~127u) : 0u;
     const size_t smem = bm_bytes + (size_t)kWarpsPerCta * kWarpSmemBytes;
@@ -162,33 +170,62 @@ int launch_score(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngrou
     return 0;
 }
 
-// Block-parallel best-placement kernel (score_kernel2.cuh); same parameters, one 12-warp CTA per SM.
-int launch_score2(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, bool smem_bitmap, uint32_t* grid_out,
+// Upload the k_score layout the first time a launch needs it.
+int ensure_v1(ub200_mat* M) {
+    if (M->v1_resident) return 0;
+    auto& d = M->d;
+    int rc = 0;
+    auto guard = [&](int r) { if (r && !rc) rc = r; };
+    guard(dev_upload(&M->mutw, d.mutw.data(), d.mutw.size(), M->stream));
+    guard(dev_upload(&M->hdr, d.hdr.data(), d.hdr.size(), M->stream));
+    guard(dev_upload(&M->row32, d.row32.data(), d.row32.size(), M->stream));
+    guard(dev_upload(&M->tile_start, d.tile_start.data(), d.tile_start.size(), M->stream));
+    guard(dev_upload(&M->anc_ptr, d.anc_ptr.data(), d.anc_ptr.size(), M->stream));
+    guard(dev_upload(&M->anc, d.anc.data(), d.anc.size(), M->stream));
+    if (rc) return rc;
+    M->device_bytes += d.mutw.size() * 4 + d.hdr.size() * 16 + d.row32.size() * 4 + d.tile_start.size() * 4 +
+                       d.anc_ptr.size() * 4 + d.anc.size() * 4;
+    if (d.max_level + 1 > (uint32_t)ub200::kStackDepth) {
+        M->gstack_levels = d.max_level + 1 - ub200::kStackDepth;
+        const size_t bytes = (size_t)M->grid * ub200::kWarpsPerCta * M->gstack_levels * 32 * sizeof(int32_t);
+        CU(cudaMalloc((void**)&M->gstack, bytes));
+        M->device_bytes += bytes;
+    }
+    CU(cudaStreamSynchronize(M->stream));
+    M->v1_resident = true;
+    return 0;
+}
+
+// Streaming best-placement kernel (score_kernel3.cuh): one 16-warp CTA per SM.
+int launch_score3(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, uint32_t* grid_out,
                   bool collect = false) {
     using namespace ub200;
-    ScoreParams p;
-    p.mutw = M->mutw; p.hdr = M->hdr; p.row32 = M->row32;
-    p.tile_start = M->tile_start; p.anc_ptr = M->anc_ptr; p.anc = M->anc;
-    p.n_nodes = M->n; p.n_tiles = M->n_tiles; p.L = M->L;
-    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.base = S->base; p.gbest = S->gbest;
+    Score3Params p;
+    p.stream = M->mstream; p.hdr = M->hdr3; p.tiekey = M->tiekey;
+    p.tile_start = M->tile3_start; p.tile_w0 = M->tile3_w0; p.tile_lvl = M->tile3_lvl; p.tile_sseg = M->tile3_sseg;
+    p.seed_end = M->seed_end;
+    p.n_nodes = M->n; p.n_tiles = M->n_tiles3; p.L = M->L;
+    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.gbest = S->gbest;
     p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups;
     p.part_key = S->part_key; p.part_cnt = S->part_cnt;
-    p.gstack = M->gstack; p.gstack_levels = M->gstack_levels;
-    p.node_scores = nullptr; p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
+    p.gstack = M->gstack3; p.gstack_levels = M->gstack3_levels;
+    p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
     p.tile_counter = S->tile_counter;
     CU(cudaMemsetAsync(S->tile_counter, 0, 64, M->stream));
     const uint32_t grid = std::max<uint32_t>(ngroups, ((uint32_t)M->num_sms / ngroups) * ngroups);
     *grid_out = grid;
-    const uint32_t bm_bytes = smem_bitmap ? ((S->bitmap_words * 4u + 127u) & ~127u) : 0u;
-    const size_t smem = bm_bytes + kLutBytes + (size_t)kWarps2 * kWarpSmem2;
+    const uint32_t fixed = kLut3Bytes + (uint32_t)kWarps3 * kWarpSmem3;
+    const uint32_t bm_need = (S->bitmap_words * 4u + 127u) & ~127u;
+    const bool smem_bitmap = fixed + bm_need <= kSmemLimit3;
+    const size_t smem = fixed + (smem_bitmap ? bm_need : 0u);
     auto go = [&](auto k) -> int {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kThreads2, smem, M->stream>>>(p);
+        k<<<grid, kThreads3, smem, M->stream>>>(p);
         return 0;
     };
     int rc;
-    if (smem_bitmap) rc = collect ? go(k_score2<true, true>) : go(k_score2<true, false>);
-    else rc = collect ? go(k_score2<false, true>) : go(k_score2<false, false>);
+    if (smem_bitmap) rc = collect ? go(k_score3<true, true>) : go(k_score3<true, false>);
+    else rc = collect ? go(k_score3<false, true>) : go(k_score3<false, false>);
     if (rc) return rc;
     CU(cudaGetLastError());
     return 0;
@@ -237,6 +274,8 @@ void ub200_mat_destroy(ub200_mat* M) {
     cudaFree(M->mutw); cudaFree(M->hdr); cudaFree(M->row32); cudaFree(M->tile_start); cudaFree(M->anc_ptr);
     cudaFree(M->anc); cudaFree(M->key_to_node); cudaFree(M->tie_index); cudaFree(M->num_leaves);
     cudaFree(M->gstack);
+    cudaFree(M->mstream); cudaFree(M->hdr3); cudaFree(M->tiekey); cudaFree(M->tile3_start); cudaFree(M->tile3_w0);
+    cudaFree(M->tile3_lvl); cudaFree(M->tile3_sseg); cudaFree(M->seed_end); cudaFree(M->gstack3);
     if (M->scratch) ub200_samples_free(M->scratch);
     for (auto e : M->ev) cudaEventDestroy(e);
     if (M->own_stream) cudaStreamDestroy(M->own_stream);
@@ -256,10 +295,12 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     M->device = device;
     M->num_sms = prop.multiProcessorCount;
     M->grid = (uint32_t)M->num_sms * 2u;
-    // workers of either kernel (k_score: 2 CTAs x 8 warps per SM, k_score2: 1 CTA x kWarps2)
-    const uint32_t total_warps = std::max<uint32_t>(M->grid * ub200::kWarpsPerCta, (uint32_t)M->num_sms * ub200::kWarps2);
+    // workers of either kernel (k_score: 2 CTAs x 8 warps per SM, k_score3: 1 CTA x kWarps3)
+    const uint32_t warps3 = (uint32_t)std::max(M->num_sms, 8) * ub200::kWarps3;
+    const uint32_t total_warps = std::max<uint32_t>(M->grid * ub200::kWarpsPerCta, warps3);
     std::string err;
-    int rc = ub200::derive(*flat, total_warps * 8u, M->d, err);
+    const char* mt = getenv("UB200_MIN_TILE");   // test hook: cut small trees into many tiles
+    int rc = ub200::derive(*flat, total_warps * 8u, M->d, err, mt ? (uint32_t)atoi(mt) : 0u);
     if (rc != UB200_OK) { delete M; return fail(rc, err); }
     auto& d = M->d;
     M->n = d.n; M->m = d.m; M->L = d.L; M->n_tiles = (uint32_t)d.tile_start.size() - 1;
@@ -267,26 +308,32 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     auto guard = [&](int r) { if (r && !rc) rc = r; };
     CU(cudaStreamCreateWithFlags(&M->own_stream, cudaStreamNonBlocking));
     M->stream = M->own_stream;
-    guard(dev_upload(&M->mutw, d.mutw.data(), d.mutw.size(), M->stream));
-    guard(dev_upload(&M->hdr, d.hdr.data(), d.hdr.size(), M->stream));
-    guard(dev_upload(&M->row32, d.row32.data(), d.row32.size(), M->stream));
-    guard(dev_upload(&M->tile_start, d.tile_start.data(), d.tile_start.size(), M->stream));
-    guard(dev_upload(&M->anc_ptr, d.anc_ptr.data(), d.anc_ptr.size(), M->stream));
-    guard(dev_upload(&M->anc, d.anc.data(), d.anc.size(), M->stream));
     guard(dev_upload(&M->key_to_node, d.key_to_node.data(), d.key_to_node.size(), M->stream));
     guard(dev_upload(&M->tie_index, d.tie_index.data(), d.tie_index.size(), M->stream));
     guard(dev_upload(&M->num_leaves, d.num_leaves.data(), d.num_leaves.size(), M->stream));
-    M->device_bytes = d.mutw.size() * 4 + d.hdr.size() * 16 + d.row32.size() * 4 + d.tile_start.size() * 4 +
-                      d.anc_ptr.size() * 4 + d.anc.size() * 4 + (uint64_t)d.n * 12;
-    if (!rc && d.max_level + 1 > (uint32_t)ub200::kStackDepth) {
-        M->gstack_levels = d.max_level + 1 - ub200::kStackDepth;
-        const size_t bytes = (size_t)total_warps * M->gstack_levels * 32 * sizeof(int32_t);
-        if (bytes > (size_t)16 << 30) {
-            rc = fail(UB200_E_LIMIT, "tree too deep for the spill stack (" + std::to_string(d.max_level) + " levels)");
-        } else {
-            cudaError_t e = cudaMalloc((void**)&M->gstack, bytes);
-            if (e != cudaSuccess) rc = fail((int)e, std::string("cudaMalloc spill stack: ") + cudaGetErrorString(e));
-            M->device_bytes += bytes;
+    M->device_bytes = (uint64_t)d.n * 12;
+    if (d.have3) {
+        M->n_tiles3 = (uint32_t)d.tile3_start.size() - 1;
+        guard(dev_upload(&M->mstream, d.stream.data(), d.stream.size(), M->stream));
+        guard(dev_upload(&M->hdr3, d.hdr3.data(), d.hdr3.size(), M->stream));
+        guard(dev_upload(&M->tiekey, d.tiekey.data(), d.tiekey.size(), M->stream));
+        guard(dev_upload(&M->tile3_start, d.tile3_start.data(), d.tile3_start.size(), M->stream));
+        guard(dev_upload(&M->tile3_w0, d.tile3_w0.data(), d.tile3_w0.size(), M->stream));
+        guard(dev_upload(&M->tile3_lvl, d.tile3_lvl.data(), d.tile3_lvl.size(), M->stream));
+        guard(dev_upload(&M->tile3_sseg, d.tile3_sseg.data(), d.tile3_sseg.size(), M->stream));
+        guard(dev_upload(&M->seed_end, d.seed_end.data(), d.seed_end.size(), M->stream));
+        M->device_bytes += d.stream.size() * 4 + d.hdr3.size() * 16 + d.tiekey.size() * 4 +
+                           (d.tile3_start.size() * 4 + d.seed_end.size()) * 4;
+        if (!rc && d.max_level + 1 > (uint32_t)ub200::kStack3) {
+            M->gstack3_levels = d.max_level + 1 - ub200::kStack3;
+            const size_t bytes = (size_t)warps3 * M->gstack3_levels * 32 * sizeof(int32_t);
+            if (bytes > (size_t)16 << 30) {
+                rc = fail(UB200_E_LIMIT, "tree too deep for the spill stack (" + std::to_string(d.max_level) + " levels)");
+            } else {
+                cudaError_t e = cudaMalloc((void**)&M->gstack3, bytes);
+                if (e != cudaSuccess) rc = fail((int)e, std::string("cudaMalloc spill stack: ") + cudaGetErrorString(e));
+                M->device_bytes += bytes;
+            }
         }
     }
     if (!rc) {
@@ -294,10 +341,9 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
         if (e != cudaSuccess) rc = fail((int)e, std::string("upload: ") + cudaGetErrorString(e));
     }
     if (rc) { ub200_mat_destroy(M); return rc; }
-    // the big host arrays are no longer needed
-    std::vector<uint32_t>().swap(d.mutw);
-    std::vector<ub200::NodeHdr>().swap(d.hdr);
-    std::vector<uint32_t>().swap(d.anc);
+    // host copies of the streamed arrays are no longer needed (the k_score layout stays for ensure_v1)
+    std::vector<uint32_t>().swap(d.stream);
+    std::vector<ub200::NodeHdr>().swap(d.hdr3);
     *out = M;
     return UB200_OK;
 }
@@ -305,7 +351,7 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
 int ub200_mat_info_get(const ub200_mat* M, ub200_mat_info* o) {
     if (!M || !o) return fail(UB200_E_ARG, "ub200_mat_info_get: NULL argument");
     o->n_nodes = M->n; o->max_level = M->d.max_level; o->n_mutations = M->m; o->genome_len = M->L;
-    o->n_tiles = M->n_tiles; o->device_bytes = M->device_bytes;
+    o->n_tiles = M->d.have3 ? M->n_tiles3 : M->n_tiles; o->device_bytes = M->device_bytes;
     o->algorithmic_bytes = 4ull * M->m + 16ull * M->n;
     o->device = M->device; o->reserved = 0;
     return UB200_OK;
@@ -380,7 +426,7 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
     }
     CU(cudaSetDevice(M->device));
     const uint32_t n_groups = (n_samples + 31) / 32;
-    S->bitmap_words = ((M->L + 31) / 32 + 3) & ~3u;
+    S->bitmap_words = ((M->L + 1 + 31) / 32 + 3) & ~3u;   // bit L exists and stays clear (stream pad words)
     if ((size_t)n_groups * M->L * 32 > ((size_t)24 << 30))
         return fail(UB200_E_LIMIT, "sample batch too large for one resident table; split the batch");
     auto alloc = [&](void** p, size_t bytes) -> int {
@@ -456,11 +502,11 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
     if (!M || !S || S->mat != M) return fail(UB200_E_ARG, "ub200_place_resident: bad handles");
     CU(cudaSetDevice(M->device));
     const bool smem_bitmap = S->bitmap_words * 4u <= ub200::kMaxSmemBitmapBytes;
-    // the block-parallel kernel packs per-(node,sample) deltas in 10-bit fields and path corrections in int16
-    const bool smem_bitmap_v2 = S->bitmap_words * 4u <= 5120u;   // what is left of 227 KB beside the 16 warps
+    // the streaming kernel packs per-(node,sample) deltas in 10-bit fields and path corrections in int16
     const char* force = getenv("UB200_KERNEL");
-    const bool use_v2 = !(force && force[0] == '1') && M->d.max_row <= ub200::kMaxRowV2 &&
-                        S->max_calls <= ub200::kMaxCallsV2;
+    const bool use_v3 = !(force && force[0] == '1') && M->d.have3 && M->d.max_row <= ub200::kMaxRowV3 &&
+                        S->max_calls <= ub200::kMaxCallsV3;
+    if (!use_v3 || (flags & UB200_WANT_NODE_SCORES)) { int rc = ensure_v1(M); if (rc) return rc; }
     const uint32_t NG = M->pass_groups;
     M->spans.clear(); M->ev_used = 0;
     M->last = {};
@@ -470,7 +516,7 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
         const uint32_t ng = std::min(NG, S->n_groups - g0);
         int rc = span_begin(M, 1); if (rc) return rc;
         uint32_t grid = std::max<uint32_t>(ng, (M->grid / ng) * ng);
-        if (use_v2) rc = launch_score2(M, S, g0, ng, smem_bitmap_v2, &grid);
+        if (use_v3) rc = launch_score3(M, S, g0, ng, &grid);
         else rc = launch_score<ub200::kModeBest>(M, S, g0, ng, smem_bitmap);
         if (rc) return rc;
         rc = span_end(M); if (rc) return rc;
@@ -514,7 +560,7 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
         for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
             const uint32_t ng = std::min(NG, S->n_groups - g0);
             uint32_t grid_unused = 0;
-            int rc = use_v2 ? launch_score2(M, S, g0, ng, smem_bitmap_v2, &grid_unused, true)
+            int rc = use_v3 ? launch_score3(M, S, g0, ng, &grid_unused, true)
                             : launch_score<ub200::kModeCollect>(M, S, g0, ng, smem_bitmap);
             if (rc) return rc;
             M->last.total_launches++;

@@ -21,7 +21,98 @@
 
 namespace ub200 {
 
-int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::string& err) {
+// The k_score3 layout (ub200_internal.h), built from the arrays derive() has already filled.
+static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min_tile_cost, Derived& d) {
+    const uint32_t n = d.n;
+    d.have3 = d.L <= kMaxPos3;
+    if (!d.have3) return;
+    const uint32_t nblk = (n + 31) / 32;
+    // subtree ends (DFS pre-order: subtree of i = [i, send[i])), words on the root path above each node
+    std::vector<uint32_t> send(n);
+    for (uint32_t i = 0; i < n; i++) send[i] = i + 1;
+    for (uint32_t i = n; i-- > 1;) send[f.parent[i]] = std::max(send[f.parent[i]], send[i]);
+    std::vector<uint64_t> pathw(n, 0);
+    for (uint32_t i = 1; i < n; i++) {
+        const uint32_t p = (uint32_t)f.parent[i];
+        pathw[i] = pathw[p] + (d.row32[p + 1] - d.row32[p]);
+    }
+    // headers: y = in-block ancestor mask, flags + open
+    d.hdr3 = d.hdr;
+    {
+        std::vector<uint32_t> am(n, 0);
+        for (uint32_t i = 0; i < n; i++) {
+            if (i && (uint32_t)f.parent[i] >= (i & ~31u)) am[i] = am[f.parent[i]] | (1u << (f.parent[i] & 31));
+            NodeHdr& h = d.hdr3[i];
+            const uint32_t flags = hdr_flags(h.level_flags);
+            const bool leaf = flags & kFlagLeaf;
+            const bool open = !leaf && send[i] > (i | 31u) + 1u;
+            h.tiekey = am[i];
+            h.level_flags = (d.level[i] << kLevelShift) | flags | (open ? kFlagOpen : 0u);
+        }
+    }
+    // tiles: whole blocks, roughly equal cost; the seed stream must stay a small fraction of the tree
+    const uint64_t node_cost = 4;
+    const uint64_t total = d.m + node_cost * n;
+    uint64_t per = total / (target_tiles ? target_tiles : 1);
+    per = std::min<uint64_t>(std::max<uint64_t>(per, min_tile_cost ? min_tile_cost : 6144), 1u << 16);
+    for (;;) {
+        d.tile3_start.assign(1, 0);
+        uint64_t acc = 0, seed = 0;
+        for (uint32_t b = 0; b < nblk; b++) {
+            const uint32_t e = std::min(n, b * 32 + 32);
+            acc += (d.row32[e] - d.row32[b * 32]) + node_cost * (e - b * 32);
+            if (acc >= per && e < n) {
+                d.tile3_start.push_back(e);
+                seed += pathw[e];
+                acc = 0;
+            }
+        }
+        d.tile3_start.push_back(n);
+        if (seed <= std::max<uint64_t>(d.m / 8, 1u << 16) || d.tile3_start.size() <= 2) break;
+        per += per / 2;
+    }
+    const size_t T = d.tile3_start.size() - 1;
+    d.tile3_w0.assign(T + 1, 0);
+    d.tile3_lvl.assign(T, 0);
+    d.tile3_sseg.assign(T + 1, 0);
+    d.seed_end.clear();
+    d.stream.clear();
+    d.stream.reserve(d.m + d.m / 6 + 4 * kChunk3);
+    const uint32_t pad = pack_mut3(d.L, 0, 0, 0);
+    auto conv = [&](uint32_t w, uint32_t lane) { return pack_mut3(w >> 6, lane, (w >> 2) & 3u, w & 3u); };
+    auto align_to = [&](size_t a) { while (d.stream.size() % a) d.stream.push_back(pad); };
+    std::vector<uint32_t> chain;
+    d.seed_words = 0;
+    for (size_t t = 0; t < T; t++) {
+        align_to(kChunk3);
+        d.tile3_w0[t] = (uint32_t)(d.stream.size() / kChunk3);
+        const uint32_t n0 = d.tile3_start[t], n1 = d.tile3_start[t + 1];
+        const uint32_t lvl0 = d.level[n0];
+        d.tile3_lvl[t] = lvl0;
+        chain.assign(lvl0, 0);
+        for (int32_t a = f.parent[n0]; a >= 0; a = f.parent[a]) chain[d.level[a]] = (uint32_t)a;
+        const size_t before = d.stream.size();
+        for (uint32_t l0 = 0; l0 < lvl0; l0 += 32) {
+            for (uint32_t l = l0; l < std::min(lvl0, l0 + 32); l++)
+                for (uint32_t k = d.row32[chain[l]]; k < d.row32[chain[l] + 1]; k++)
+                    d.stream.push_back(conv(d.mutw[k], l & 31u));
+            align_to(4);
+            d.seed_end.push_back((uint32_t)(d.stream.size() / 4));
+        }
+        d.seed_words += d.stream.size() - before;
+        d.tile3_sseg[t + 1] = (uint32_t)d.seed_end.size();
+        for (uint32_t b = n0; b < n1; b += 32) {
+            for (uint32_t i = b; i < std::min(n1, b + 32); i++)
+                for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) d.stream.push_back(conv(d.mutw[k], i & 31u));
+            align_to(4);
+        }
+    }
+    align_to(kChunk3);
+    d.tile3_w0[T] = (uint32_t)(d.stream.size() / kChunk3);
+    d.seed_end.push_back(0);   // never empty
+}
+
+int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::string& err, uint32_t min_tile_cost) {
     const uint32_t n = f.n_nodes;
     if (n == 0 || !f.parent || !f.row_ptr || (f.n_mutations && !f.mutations)) {
         err = "flat MAT: empty tree or NULL array";
@@ -198,7 +289,7 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
         const uint64_t node_cost = 4;
         const uint64_t total = kept + node_cost * n;
         uint64_t per = total / (target_tiles ? target_tiles : 1);
-        per = std::min<uint64_t>(std::max<uint64_t>(per, 6144), 1u << 16);   // >= ~180 nodes: keeps root-path seeding < 10%
+        per = std::min<uint64_t>(std::max<uint64_t>(per, min_tile_cost ? min_tile_cost : 6144), 1u << 16);   // >= ~180 nodes: keeps root-path seeding < 10%
         d.tile_start.clear();
         d.tile_start.push_back(0);
         uint64_t acc = 0;
@@ -221,6 +312,8 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
             d.anc_ptr[t + 1] = (uint32_t)d.anc.size();
         }
     }
+    derive3(f, target_tiles, min_tile_cost, d);
+    if (d.have3 && d.stream.size() / 4 >= (1ull << 32)) { err = "flat MAT: stream longer than 2^34 words"; return UB200_E_LIMIT; }
     return UB200_OK;
 }
 
@@ -235,13 +328,18 @@ struct ub200_derived_view {
     const uint32_t* level; const uint32_t* tie_index; const uint32_t* num_leaves; const uint32_t* tiekey;
     const uint32_t* key_to_node; const uint32_t* row32; const uint32_t* mutw; const void* hdr;
     const uint8_t* ref_of; const uint32_t* tile_start; const uint32_t* anc_ptr; const uint32_t* anc;
+    // k_score3 layout
+    uint32_t n_tiles3, n_seed_segs;
+    uint64_t stream_words;
+    const uint32_t* stream; const void* hdr3; const uint32_t* tile3_start; const uint32_t* tile3_w0;
+    const uint32_t* tile3_lvl; const uint32_t* tile3_sseg; const uint32_t* seed_end;
 };
 
-int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, void** handle, ub200_derived_view* view,
-                       char* errbuf, size_t errlen) {
+int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32_t min_tile_cost, void** handle,
+                       ub200_derived_view* view, char* errbuf, size_t errlen) {
     auto* d = new ub200::Derived();
     std::string err;
-    int rc = ub200::derive(*flat, target_tiles, *d, err);
+    int rc = ub200::derive(*flat, target_tiles, *d, err, min_tile_cost);
     if (rc != UB200_OK) {
         if (errbuf && errlen) { std::strncpy(errbuf, err.c_str(), errlen - 1); errbuf[errlen - 1] = 0; }
         delete d;
@@ -253,6 +351,12 @@ int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, void**
     view->tiekey = d->tiekey.data(); view->key_to_node = d->key_to_node.data(); view->row32 = d->row32.data();
     view->mutw = d->mutw.data(); view->hdr = d->hdr.data(); view->ref_of = d->ref_of.data();
     view->tile_start = d->tile_start.data(); view->anc_ptr = d->anc_ptr.data(); view->anc = d->anc.data();
+    view->n_tiles3 = d->have3 ? (uint32_t)d->tile3_start.size() - 1 : 0;
+    view->n_seed_segs = (uint32_t)d->seed_end.size();
+    view->stream_words = d->stream.size();
+    view->stream = d->stream.data(); view->hdr3 = d->hdr3.data(); view->tile3_start = d->tile3_start.data();
+    view->tile3_w0 = d->tile3_w0.data(); view->tile3_lvl = d->tile3_lvl.data();
+    view->tile3_sseg = d->tile3_sseg.data(); view->seed_end = d->seed_end.data();
     *handle = d;
     return UB200_OK;
 }

@@ -48,7 +48,8 @@ struct ScoreParams {
     uint32_t L;
     uint32_t bitmap_words;        // per group (multiple of 4)
     const uint32_t* bitmap;       // [all groups][bitmap_words]
-    const uint32_t* tab;          // [all groups][L][8]: w0 = lanes that call the position, w1..w4 = cost nibbles
+    const uint32_t* tab;          // [all groups][L][8]: w0 = lanes that call the position, w1 = ref code << 4,
+                                  // w2..w5 = cost nibbles
     int32_t* gbest;               // [samples] running upper bound of the best relative score (pruning only)
     const int32_t* base;          // [samples] LOOP-2 count against the pure reference genome
     uint32_t n_samples;
@@ -63,7 +64,6 @@ struct ScoreParams {
     uint32_t* set_out;            // MODE 2
     const unsigned long long* set_ptr;
     uint32_t* set_fill;
-    uint32_t* tile_counter;       // k_score2: [ngroups] next tile to hand out (zeroed before each launch)
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -122,7 +122,7 @@ __device__ __forceinline__ void apply_hit(uint32_t m, uint32_t e, int& dcorr, in
 __device__ __forceinline__ uint32_t tab_entry(const uint32_t* tabg, uint32_t pos, uint32_t lane) {
     const uint32_t* row = tabg + (size_t)pos * 8u;
     const uint32_t pm = __ldg(row);
-    const uint32_t nw = __ldg(row + 1 + (lane >> 3));
+    const uint32_t nw = __ldg(row + 2 + (lane >> 3));
     return (((pm >> lane) & 1u) << 4) | ((nw >> ((lane & 7u) * 4u)) & 15u);
 }
 
@@ -450,7 +450,8 @@ __global__ void k_prep_scatter(const PrepParams p) {
         const uint32_t cost = c.is_missing ? 0u : (~set & 15u);
         uint32_t* row = p.tab + ((size_t)g * p.L + pos) * 8u;
         atomicOr(row, 1u << lane);
-        if (cost) atomicOr(row + 1 + (lane >> 3), cost << ((lane & 7u) * 4u));
+        row[1] = (uint32_t)(31 - __clz((int)c.ref_nuc)) << 4;   // same value from every caller (checked on upload)
+        if (cost) atomicOr(row + 2 + (lane >> 3), cost << ((lane & 7u) * 4u));
     }
 }
 

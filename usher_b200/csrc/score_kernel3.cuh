@@ -1,0 +1,471 @@
+// k_score3 — streaming best-placement kernel on the segment layout (ub200_internal.h, DESIGN.md "Kernels").
+//
+// One persistent launch scores every node of the tree against NG groups of 32 samples.  A warp is an independent
+// worker on tiles (contiguous DFS ranges of whole 32-node blocks).  A tile is ONE contiguous piece of the
+// mutation stream — [seed segments][block segments] — that the warp pulls through its own shared-memory ring
+// with 1 KB bulk async copies (cp.async.bulk -> UBLKCP) completing on per-stage mbarriers; headers come through a
+// second ring, 512 B (one block) per copy.  Per segment the lane role switches by phase:
+//   A  lane = node      header decode; the segment length is the warp sum of the rows (no offsets are read)
+//   B  lane = 4 words   one LDS.128 per lane per step (128 words), every word's position tested against the
+//                       group's bitmap; lanes that saw a hit append (their 4 words, 4-bit hit mask) to a
+//                       64-entry ring with one ballot
+//   C  lane = entry     hit word -> node lane (stored in the word), table row of the position (32 B, L2) ->
+//                       for every sample calling the position: packed (dcorr, da, dcommon) from a 1024-entry
+//                       LUT, shared-memory atomics into dnode[node][sample], hm[sample] |= node,
+//                       neg[sample] += min(dcorr, 0)
+//   bound               exact lower bound of every pair of the block:  min(G - nmut) + gmin + neg  against the
+//                       running best; blocks that cannot hold an optimum skip E and F entirely
+//   E  lane = node      non-hit pairs of a sample that can still improve or tie
+//   F  lane = sample    hit pairs, exactly (score, validity, tie key)
+//   G  lane = sample    path corrections of the block's OPEN chain (nodes with descendants in later blocks) ->
+//                       stack rows the following blocks read
+// The correction of the path above a node inside its own block is never materialised: it is
+// stack[level above the block] + sum of dnode over (in-block ancestors & hit nodes of the sample), with the
+// in-block ancestor mask precomputed in the header.  All pruning is exact, so results are schedule-independent.
+#pragma once
+#include "score_kernel.cuh"
+
+namespace ub200 {
+
+constexpr int kWarps3 = 16;
+constexpr int kThreads3 = kWarps3 * 32;
+constexpr int kMutStages3 = 4;
+constexpr uint32_t kRingWords3 = kChunk3 * kMutStages3;   // 1024 words = 4 KB
+constexpr int kHdrStages3 = 2;
+constexpr uint32_t kEntRing = 64;
+constexpr int kStack3 = 40;                                // levels kept in shared memory (deeper: HBM spill)
+// per-warp shared memory (bytes)
+constexpr uint32_t kO3Mring = 0;                           // u32[1024]
+constexpr uint32_t kO3Hring = 4096;                        // uint4[64]
+constexpr uint32_t kO3Dnode = 5120;                        // i32[32][32] packed deltas
+constexpr uint32_t kO3Stack = 9216;                        // i16[40][32]
+constexpr uint32_t kO3Ent = kO3Stack + kStack3 * 64;       // uint4[64]
+constexpr uint32_t kO3Ehb = kO3Ent + kEntRing * 16;        // u8[64]
+constexpr uint32_t kO3Info = kO3Ehb + kEntRing;            // u32[6][32]: G, z, w, am, hm, neg
+constexpr uint32_t kO3Bars = kO3Info + 6 * 128;            // mbarriers
+constexpr uint32_t kWarpSmem3 = (kO3Bars + 64 + 127) & ~127u;
+constexpr uint32_t kI3G = 0, kI3Z = 32, kI3W = 64, kI3Am = 96, kI3Hm = 128, kI3Neg = 160;
+constexpr uint32_t kLut3Bytes = 4096;
+constexpr uint32_t kMaxRowV3 = 500;      // packed 10-bit delta fields
+constexpr uint32_t kMaxCallsV3 = 32000;  // path corrections are int16
+constexpr uint32_t kSmemLimit3 = 232448; // 227 KB
+
+struct Score3Params {
+    const uint32_t* stream;
+    const NodeHdr* hdr;           // hdr3
+    const uint32_t* tiekey;
+    const uint32_t* tile_start;   // [T+1]
+    const uint32_t* tile_w0;      // [T+1]
+    const uint32_t* tile_lvl;     // [T]
+    const uint32_t* tile_sseg;    // [T+1]
+    const uint32_t* seed_end;
+    uint32_t n_nodes, n_tiles, L, bitmap_words;
+    const uint32_t* bitmap;
+    const uint32_t* tab;          // [groups][L][8]: mask, ref<<4, nibbles[4], -, -
+    int32_t* gbest;
+    uint32_t n_samples, group0, ngroups;
+    unsigned long long* part_key;
+    uint32_t* part_cnt;
+    int32_t* gstack;
+    uint32_t gstack_levels;
+    const int32_t* target_rel;
+    uint32_t* set_out;
+    const unsigned long long* set_ptr;
+    uint32_t* set_fill;
+    uint32_t* tile_counter;
+};
+
+__device__ __forceinline__ uint32_t lds32_3(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128_3(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __noinline__ int spill_read3(const int32_t* gstk, uint32_t level, uint32_t s) {
+    return gstk[(size_t)(level - kStack3) * 32u + s];
+}
+__device__ __noinline__ void spill_write3(int32_t* gstk, uint32_t level, uint32_t s, int v) {
+    gstk[(size_t)(level - kStack3) * 32u + s] = v;
+}
+__device__ __forceinline__ int lut_delta3(uint32_t i) {
+    const uint32_t e = i >> 6, refc = (i >> 4) & 3u, prevc = (i >> 2) & 3u, mutc = i & 3u;
+    const int rm = (mutc != refc), rp = (prevc != refc);
+    const int wm = (e >> mutc) & 1u, wp = (e >> prevc) & 1u;
+    const int dcorr = (wm - wp) - (rm - rp);
+    const int tk = wm ^ 1, t0 = rm ^ 1;
+    const int da = (tk & wp) - (t0 & rp);
+    const int dcom = tk - t0;
+    return dcorr * (1 << 20) + da * (1 << 10) + dcom;
+}
+__device__ __forceinline__ int dc_of(int v) { return (v + (1 << 19)) >> 20; }
+__device__ __forceinline__ void unpack_delta3(int v, int& dcorr, int& da, int& dcom) {
+    dcom = (int)((uint32_t)v << 22) >> 22;
+    const int v1 = (v - dcom) >> 10;
+    da = (int)((uint32_t)v1 << 22) >> 22;
+    dcorr = (v1 - da) >> 10;
+}
+
+template <bool SMEM_BITMAP, bool COLLECT>
+__global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t group = blockIdx.x % p.ngroups;
+    const uint32_t cta_in_group = blockIdx.x / p.ngroups;
+    const uint32_t ctas_per_group = gridDim.x / p.ngroups;
+    const uint32_t ggroup = p.group0 + group;
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    constexpr int BIG = 0x3fffffff;
+
+    // ---- shared memory: [bitmap][lut][warp 0 .. warp 15]
+    uint32_t* bm_s = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t bm_bytes = SMEM_BITMAP ? ((p.bitmap_words * 4u + 127u) & ~127u) : 0u;
+    int* lut = reinterpret_cast<int*>(smem + bm_bytes);
+    uint8_t* wbase = smem + bm_bytes + kLut3Bytes + warp * kWarpSmem3;
+    uint32_t* mring = reinterpret_cast<uint32_t*>(wbase + kO3Mring);
+    uint4* hring = reinterpret_cast<uint4*>(wbase + kO3Hring);
+    int* dnode = reinterpret_cast<int*>(wbase + kO3Dnode);
+    int16_t* stk = reinterpret_cast<int16_t*>(wbase + kO3Stack);
+    uint4* ent = reinterpret_cast<uint4*>(wbase + kO3Ent);
+    uint8_t* ehb = wbase + kO3Ehb;
+    uint32_t* info = reinterpret_cast<uint32_t*>(wbase + kO3Info);
+    const uint32_t mring_a = smem_u32(mring), hring_a = smem_u32(hring), bars_a = smem_u32(wbase + kO3Bars);
+    const uint32_t bm_a = smem_u32(bm_s);
+
+    const uint32_t* bm_g = p.bitmap + (size_t)ggroup * p.bitmap_words;
+    if (SMEM_BITMAP) {
+        const uint4* src = reinterpret_cast<const uint4*>(bm_g);
+        uint4* dst = reinterpret_cast<uint4*>(bm_s);
+        for (uint32_t i = threadIdx.x; i < p.bitmap_words / 4; i += kThreads3) dst[i] = __ldg(src + i);
+    }
+    for (uint32_t i = threadIdx.x; i < 1024; i += kThreads3) lut[i] = lut_delta3(i);
+    // lanes past a segment's end still index the bitmap with what the ring holds: only ever valid words
+    for (uint32_t i = lane; i < kRingWords3; i += 32) mring[i] = 0u;
+    if (lane == 0) {
+        for (int i = 0; i < kMutStages3 + kHdrStages3; i++) mbar_init(bars_a + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t* tabg = p.tab + (size_t)ggroup * p.L * 8u;
+    int32_t* gstk = p.gstack ? p.gstack + ((size_t)(blockIdx.x * kWarps3 + warp) * p.gstack_levels) * 32u : nullptr;
+    const uint32_t sample = ggroup * 32u + lane;
+    const bool live = sample < p.n_samples;
+
+    auto stack_read = [&](uint32_t level, uint32_t s) -> int {
+        if (__builtin_expect(level >= (uint32_t)kStack3, 0)) return spill_read3(gstk, level, s);
+        return stk[level * 32u + s];
+    };
+    auto stack_write = [&](uint32_t level, uint32_t s, int v) {
+        if (__builtin_expect(level >= (uint32_t)kStack3, 0)) spill_write3(gstk, level, s, v);
+        else stk[level * 32u + s] = (int16_t)v;
+    };
+
+    // per-lane (= sample) running best (COLLECT: the known final best, fixed)
+    int bsc = COLLECT ? (live ? p.target_rel[sample] : (int)0x80000000) : 0x7fffffff;
+    unsigned long long bkey = ~0ull;
+    uint32_t cnt = 0;
+    auto merge = [&](int sc, uint32_t hu, uint32_t node) {
+        if (COLLECT) {
+            if (sc == bsc) {
+                const uint32_t k = atomicAdd(p.set_fill + sample, 1u);
+                p.set_out[p.set_ptr[sample] + k] = node | (hu ? 0x80000000u : 0u);
+            }
+            return;
+        }
+        const uint32_t tiekey = __ldg(p.tiekey + node);
+        const unsigned long long key =
+            ((unsigned long long)(uint32_t)(sc + kScoreBias) << 33) | ((unsigned long long)tiekey << 1) | hu;
+        if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
+        else if (sc == bsc) { cnt++; if (key < bkey) bkey = key; }
+    };
+
+    uint32_t mphase = 0, hphase = 0;
+    uint32_t head = 0, tail = 0;     // entry ring (warp-uniform)
+    uint32_t mc_issue = 0, mc_end = 0, mc_wait = 0;
+
+    // C: the oldest `n` entries (lane = entry)
+    auto process = [&](uint32_t n) {
+        if (lane < n) {
+            const uint32_t e = (head + lane) & (kEntRing - 1u);
+            const uint4 q = ent[e];
+            uint32_t hb = ehb[e];
+            do {
+                const uint32_t j = __ffs(hb) - 1;
+                hb &= hb - 1;
+                const uint32_t w = j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w;
+                const uint32_t* row = tabg + (size_t)(w >> 9) * 8u;
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row));
+                const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+                const uint32_t nl = (w >> 4) & 31u;
+                const uint32_t lo = r0.y | (w & 15u);
+                uint32_t pm = r0.x;
+                while (pm) {
+                    const uint32_t s = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
+                    const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
+                    const int d = lut[(e4 << 6) | lo];
+                    atomicAdd(&dnode[nl * 32u + s], d);
+                    atomicOr(&info[kI3Hm + s], 1u << nl);
+                    const int dc = dc_of(d);
+                    if (dc < 0) atomicAdd(reinterpret_cast<int*>(&info[kI3Neg + s]), dc);
+                }
+            } while (hb);
+        }
+        head += n;
+    };
+
+    // B: scan stream words [o0, o1) (both multiples of 4) of the current tile
+    auto scan = [&](uint32_t o0, uint32_t o1) {
+        for (uint32_t off = o0; off < o1; off += 128u) {
+            const uint32_t c_hi = (min(off + 128u, o1) - 1u) / kChunk3;
+            while (mc_wait <= c_hi) {
+                const uint32_t s = mc_wait % kMutStages3;
+                mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
+                mphase ^= 1u << s;
+                mc_wait++;
+            }
+            // chunks below off / kChunk3 are dead: refill their stages
+            while (mc_issue < mc_end && mc_issue < off / kChunk3 + kMutStages3) {
+                if (lane == 0) {
+                    const uint32_t s = mc_issue % kMutStages3;
+                    mbar_expect_tx(bars_a + 8 * s, kChunk3 * 4);
+                    bulk_g2s(mring_a + s * kChunk3 * 4, p.stream + (size_t)mc_issue * kChunk3, kChunk3 * 4, bars_a + 8 * s);
+                }
+                mc_issue++;
+            }
+            const uint32_t idx = off + 4u * lane;
+            const uint4 q = lds128_3(mring_a + ((idx & (kRingWords3 - 1u)) << 2));
+            const uint32_t w0 = SMEM_BITMAP ? lds32_3(bm_a + ((q.x >> 14) << 2)) : __ldg(bm_g + (q.x >> 14));
+            const uint32_t w1 = SMEM_BITMAP ? lds32_3(bm_a + ((q.y >> 14) << 2)) : __ldg(bm_g + (q.y >> 14));
+            const uint32_t w2 = SMEM_BITMAP ? lds32_3(bm_a + ((q.z >> 14) << 2)) : __ldg(bm_g + (q.z >> 14));
+            const uint32_t w3 = SMEM_BITMAP ? lds32_3(bm_a + ((q.w >> 14) << 2)) : __ldg(bm_g + (q.w >> 14));
+            uint32_t hb = (__funnelshift_r(w0, 0u, q.x >> 9) & 1u) | ((__funnelshift_r(w1, 0u, q.y >> 9) & 1u) << 1) |
+                          ((__funnelshift_r(w2, 0u, q.z >> 9) & 1u) << 2) | ((__funnelshift_r(w3, 0u, q.w >> 9) & 1u) << 3);
+            if (idx >= o1) hb = 0u;   // lanes past the segment read whatever the ring holds
+            const uint32_t any = __ballot_sync(FULL, hb != 0u);
+            if (hb) {
+                const uint32_t slot = (tail + __popc(any & lt_mask)) & (kEntRing - 1u);
+                ent[slot] = q;
+                ehb[slot] = (uint8_t)hb;
+            }
+            tail += __popc(any);
+            if (tail - head >= 32u) {
+                __syncwarp();
+                process(32u);
+                __syncwarp();
+            }
+        }
+    };
+    auto drain = [&]() {
+        __syncwarp();
+        if (tail != head) process(tail - head);
+        __syncwarp();
+    };
+    auto zero_dnode = [&]() {
+#pragma unroll
+        for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(dnode)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
+        info[kI3Hm + lane] = 0;
+        info[kI3Neg + lane] = 0;
+    };
+
+    for (;;) {
+        // tiles are handed out in DFS order by a per-group counter: balances uneven tiles, and the CTAs of
+        // different groups still walk the tree in the same order (one HBM read, the rest from L2)
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(p.tile_counter + group, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= p.n_tiles) break;
+        const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
+        const uint32_t lvl0 = p.tile_lvl[t];
+        const uint32_t sseg = p.tile_sseg[t];
+        mc_issue = p.tile_w0[t];
+        mc_end = p.tile_w0[t + 1];
+        mc_wait = mc_issue;
+        uint32_t o0 = mc_issue * kChunk3;
+        uint32_t hc_issue = n0 / kHdrChunk;
+        const uint32_t hc_end = (n1 - 1) / kHdrChunk + 1;
+        if (lane == 0) {
+            for (int i = 0; i < kMutStages3 && mc_issue + i < mc_end; i++) {
+                const uint32_t c = mc_issue + i, s = c % kMutStages3;
+                mbar_expect_tx(bars_a + 8 * s, kChunk3 * 4);
+                bulk_g2s(mring_a + s * kChunk3 * 4, p.stream + (size_t)c * kChunk3, kChunk3 * 4, bars_a + 8 * s);
+            }
+            for (int i = 0; i < kHdrStages3 && hc_issue + i < hc_end; i++) {
+                const uint32_t c = hc_issue + i, s = c % kHdrStages3;
+                mbar_expect_tx(bars_a + 8 * (kMutStages3 + s), kHdrChunk * 16);
+                bulk_g2s(hring_a + s * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
+                         bars_a + 8 * (kMutStages3 + s));
+            }
+        }
+        mc_issue = min(mc_issue + kMutStages3, mc_end);
+        hc_issue = min(hc_issue + kHdrStages3, hc_end);
+
+        // cross-warp bound of this lane's sample, and the tile-local floor of every stack value
+        const int gb = COLLECT ? bsc : (live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff);
+        int gmin = 0;
+
+        // ================= seed: path corrections of levels 0 .. lvl0-1, 32 levels per segment =================
+        for (uint32_t l0 = 0; l0 < lvl0; l0 += 32u) {
+            zero_dnode();
+            __syncwarp();
+            const uint32_t o1 = p.seed_end[sseg + (l0 >> 5)] * 4u;
+            scan(o0, o1);
+            o0 = o1;
+            drain();
+            const uint32_t cn = min(32u, lvl0 - l0);
+            int v = l0 ? stack_read(l0 - 1u, lane) : 0;
+            for (uint32_t j = 0; j < cn; j++) {
+                v += dc_of(dnode[j * 32u + lane]);
+                stack_write(l0 + j, lane, v);
+                gmin = min(gmin, v);
+            }
+            __syncwarp();
+        }
+
+        for (uint32_t blk = n0; blk < n1; blk += 32u) {
+            // ================= A: headers (lane = node) =================
+            const uint32_t hc = blk / kHdrChunk, hs = hc % kHdrStages3;
+            mbar_wait(bars_a + 8 * (kMutStages3 + hs), (hphase >> hs) & 1u);
+            hphase ^= 1u << hs;
+            const uint4 h = hring[hs * kHdrChunk + lane];
+            const bool act = blk + lane < n1;
+            const uint32_t level = h.z >> kLevelShift, flags = h.z & 0x3fffu;
+            const uint32_t nmut = act ? (h.w >> 16) : 0u;
+            const uint32_t o1 = o0 + ((__reduce_add_sync(FULL, nmut) + 3u) & ~3u);
+            const bool dense_ok = act && (flags & kFlagValid0);
+            const int min_g = __reduce_min_sync(FULL, dense_ok ? h.x : BIG);
+            const int min_gn = __reduce_min_sync(FULL, act ? h.x - (int)nmut : BIG);
+            info[kI3G + lane] = (uint32_t)h.x;
+            info[kI3Z + lane] = h.z;
+            info[kI3W + lane] = h.w;
+            info[kI3Am + lane] = h.y;
+            zero_dnode();
+            __syncwarp();
+            if (hc_issue < hc_end) {   // this block's header stage is free again
+                if (lane == 0) {
+                    const uint32_t c = hc_issue, s2 = c % kHdrStages3;
+                    mbar_expect_tx(bars_a + 8 * (kMutStages3 + s2), kHdrChunk * 16);
+                    bulk_g2s(hring_a + s2 * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
+                             bars_a + 8 * (kMutStages3 + s2));
+                }
+                hc_issue++;
+            }
+
+            // ================= B + C =================
+            scan(o0, o1);
+            o0 = o1;
+            drain();
+
+            // ================= bound: can any pair of this block still be optimal? =================
+            const uint32_t hmv = info[kI3Hm + lane];             // lane = sample: its hit nodes
+            const int lbase = gmin + (int)info[kI3Neg + lane];
+            const int bound = min(bsc, gb);
+            const uint32_t needs = __ballot_sync(FULL, live && min_gn + lbase <= bound);
+            if (needs) {
+                // correction of the path above node (level, am) for sample s
+                auto above = [&](uint32_t lvl, uint32_t am, uint32_t hmask, uint32_t s) -> int {
+                    const uint32_t top = lvl - __popc(am);
+                    int v = top ? stack_read(top - 1u, s) : 0;
+                    uint32_t m = am & hmask;
+                    while (m) {
+                        const uint32_t a = __ffs(m) - 1;
+                        m &= m - 1;
+                        v += dc_of(dnode[a * 32u + s]);
+                    }
+                    return v;
+                };
+                // ---- E: non-hit pairs (lane = node), one sample at a time
+                uint32_t need_e = __ballot_sync(FULL, live && min_g < BIG && min_g + lbase <= bound);
+                while (need_e) {
+                    const uint32_t s = __ffs(need_e) - 1;
+                    need_e &= need_e - 1;
+                    const uint32_t hm_s = info[kI3Hm + s];
+                    const int sc = h.x + above(level, h.y, hm_s, s);
+                    const int bs = __shfl_sync(FULL, bsc, s);
+                    uint32_t cm = __ballot_sync(FULL, dense_ok && !((hm_s >> lane) & 1u) && sc <= bs);
+                    while (cm) {
+                        const uint32_t j = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        const int scj = __shfl_sync(FULL, sc, j);
+                        const uint32_t huj = __shfl_sync(FULL, (flags & kFlagHu0) ? 1u : 0u, j);
+                        if (lane == s) merge(scj, huj, blk + j);
+                    }
+                }
+                // ---- F: hit pairs, exact (lane = sample)
+                if ((needs >> lane) & 1u) {
+                    uint32_t hmw = hmv;
+                    while (hmw) {
+                        const uint32_t n = __ffs(hmw) - 1;
+                        hmw &= hmw - 1;
+                        int dcorr, da, dcom;
+                        unpack_delta3(dnode[n * 32u + lane], dcorr, da, dcom);
+                        const uint32_t z = info[kI3Z + n], w = info[kI3W + n];
+                        const uint32_t fl = z & 0x3fffu;
+                        const int g = (int)info[kI3G + n];
+                        int sc;
+                        bool valid;
+                        uint32_t hu;
+                        if (fl & kFlagRoot) {
+                            sc = g + dcorr; valid = true; hu = 0;
+                        } else {
+                            const bool masked = fl & kFlagMasked;
+                            if (masked) { da = 0; dcom = 0; }
+                            sc = g + above(z >> kLevelShift, info[kI3Am + n], hmv, lane) - da;
+                            const int common = (int)(w & 0xffffu) + dcom;
+                            hu = (masked || (int)(w >> 16) > common) ? 1u : 0u;
+                            valid = (fl & kFlagLeaf) ? common > 0 : (!hu || common > 0);
+                        }
+                        if (valid && sc <= bsc) merge(sc, hu, blk + n);
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ================= G: stack rows of the open chain (lane = sample) =================
+            uint32_t chain = __ballot_sync(FULL, act && (flags & kFlagOpen));
+            if (chain) {
+                uint32_t lv = __shfl_sync(FULL, level, __ffs(chain) - 1);
+                int v = lv ? stack_read(lv - 1u, lane) : 0;
+                while (chain) {
+                    const uint32_t n = __ffs(chain) - 1;
+                    chain &= chain - 1;
+                    v += dc_of(dnode[n * 32u + lane]);
+                    stack_write(lv, lane, v);
+                    gmin = min(gmin, v);
+                    lv++;
+                }
+            }
+            __syncwarp();
+        }
+        // publish an improved bound for the other warps working on this sample group
+        if (!COLLECT && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
+        __syncwarp();
+    }
+
+    if (COLLECT) return;
+    // fold the CTA's warps in shared memory (the rings are dead now), one partial row per CTA
+    __syncthreads();
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
+    uint32_t* scnt = reinterpret_cast<uint32_t*>(smem + kWarps3 * 32 * 8);
+    skey[warp * 32 + lane] = bkey;
+    scnt[warp * 32 + lane] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long best = ~0ull;
+        for (int w = 0; w < kWarps3; w++) best = min(best, skey[w * 32 + lane]);
+        uint32_t c = 0;
+        for (int w = 0; w < kWarps3; w++)
+            if ((skey[w * 32 + lane] >> 33) == (best >> 33)) c += scnt[w * 32 + lane];
+        const size_t o = ((size_t)group * ctas_per_group + cta_in_group) * 32u + lane;
+        p.part_key[o] = best;
+        p.part_cnt[o] = c;
+    }
+}
+
+}  // namespace ub200

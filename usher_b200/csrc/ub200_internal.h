@@ -53,6 +53,19 @@ static_assert(sizeof(NodeHdr) == 16, "header must be 16 bytes");
 constexpr uint32_t kMutChunk = 256;   // mutation words per bulk copy (1 KB)
 constexpr uint32_t kHdrChunk = 32;    // headers per bulk copy (512 B)
 
+// ---- k_score3 layout (score_kernel3.cuh, DESIGN.md "Data layout") ----
+// stream word: pos:23 | lane:5 | prev:2 | mut:2   (lane = node & 31 in a block segment, level & 31 in a seed
+// segment; the reference allele comes from the sample table row).  Pad words carry pos = L (never called).
+constexpr uint32_t kPosBits3 = 23;
+constexpr uint32_t kMaxPos3 = (1u << kPosBits3) - 2;
+UB200_HD inline uint32_t pack_mut3(uint32_t pos, uint32_t lane, uint32_t prevc, uint32_t mutc) {
+    return (pos << 9) | (lane << 4) | (prevc << 2) | mutc;
+}
+// header of the k_score3 layout: x = G, y = bitmask of the node's ancestors inside its own aligned 32-node
+// block, z = level:18 | flags:14, w = nmut<<16 | c0
+constexpr uint32_t kFlagOpen = 32u;    // internal node with a descendant beyond its 32-node block
+constexpr uint32_t kChunk3 = 256;      // stream words per bulk copy (1 KB); tiles start on chunk boundaries
+
 struct Derived {
     uint32_t n = 0;
     uint64_t m = 0;          // unmasked mutations kept on the device
@@ -69,11 +82,26 @@ struct Derived {
     std::vector<uint32_t> anc_ptr;    // [T+1]
     std::vector<uint32_t> anc;        // node ids, root first
     int32_t root_init_extra = 0;      // |root row| (incl. masked) for the reference's initial bound
+    // ---- k_score3 layout: per tile one contiguous piece of `stream` = [seed segments][block segments];
+    // a seed segment holds the rows of up to 32 consecutive levels of the root path of the tile's first node,
+    // a block segment the rows of one aligned 32-node block; every segment starts on a 4-word boundary.
+    bool have3 = false;               // false: genome too long for the 23-bit position field
+    std::vector<uint32_t> stream;     // padded to kChunk3
+    std::vector<NodeHdr> hdr3;        // padded like hdr
+    std::vector<uint32_t> tile3_start;// [T3+1] first node of each tile (multiple of 32)
+    std::vector<uint32_t> tile3_w0;   // [T3+1] first stream chunk of each tile (tile t ends where t+1 starts)
+    std::vector<uint32_t> tile3_lvl;  // [T3]   level of the tile's first node = number of seeded levels
+    std::vector<uint32_t> tile3_sseg; // [T3+1] offsets into seed_end
+    std::vector<uint32_t> seed_end;   // end of each seed segment, in 4-word units
+    uint64_t seed_words = 0;          // stream words spent on seed segments
 };
 
 // Validate the caller's flat tree and derive everything the kernels need.  Returns UB200_* status and
 // fills err on failure.
-int derive(const ub200_flat_mat& flat, uint32_t target_tiles, Derived& out, std::string& err);
+// min_tile_cost: floor of a tile's cost (mutations + 4 per node); 0 = default (tests pass small values to
+// cut small trees into many tiles).
+int derive(const ub200_flat_mat& flat, uint32_t target_tiles, Derived& out, std::string& err,
+           uint32_t min_tile_cost = 0);
 
 inline int nuc_code(uint8_t one_hot) {
     switch (one_hot) {

@@ -98,11 +98,11 @@ def place3(d, s_ptr, calls):
             out = {}
             for k in range(o0, o1):
                 w = int(stream[k])
-                e = tab.get(w >> 9)
+                e = tab.get(((w >> 14) << 5) | (w & 31))
                 if e is None:
                     continue
                 e, refc = e
-                nl, prevc, mutc = (w >> 4) & 31, (w >> 2) & 3, w & 3
+                nl, prevc, mutc = (w >> 9) & 31, (w >> 7) & 3, (w >> 5) & 3
                 rm, rp = int(mutc != refc), int(prevc != refc)
                 wm, wp = (e >> mutc) & 1, (e >> prevc) & 1
                 tk, t0 = wm ^ 1, rm ^ 1

@@ -6,10 +6,10 @@
 // with 1 KB bulk async copies (cp.async.bulk -> UBLKCP) completing on per-stage mbarriers; headers come through a
 // second ring, 512 B (one block) per copy.  Per segment the lane role switches by phase:
 //   A  lane = node      header decode; the segment length is the warp sum of the rows (no offsets are read)
-//   B  lane = 4 words   one LDS.128 per lane per step (128 words), every word's position tested against the
-//                       group's bitmap; lanes that saw a hit append (their 4 words, 4-bit hit mask) to a
-//                       64-entry ring with one ballot
-//   C  lane = entry     hit word -> node lane (stored in the word), table row of the position (32 B, L2) ->
+//   B  lane = 16 words  up to four LDS.128 per lane per step (512 words); every word's position is tested against
+//                       the group's bitmap (3 instructions + 1 funnel shift that collects the hit bits); the
+//                       hit words are compacted into a 256-word list (one warp prefix sum per step)
+//   C  lane = hit       hit word -> node lane (stored in the word), table row of the position (32 B, L2) ->
 //                       for every sample calling the position: packed (dcorr, da, dcommon) from a 1024-entry
 //                       LUT, shared-memory atomics into dnode[node][sample], hm[sample] |= node,
 //                       neg[sample] += min(dcorr, 0)
@@ -32,16 +32,15 @@ constexpr int kThreads3 = kWarps3 * 32;
 constexpr int kMutStages3 = 4;
 constexpr uint32_t kRingWords3 = kChunk3 * kMutStages3;   // 1024 words = 4 KB
 constexpr int kHdrStages3 = 2;
-constexpr uint32_t kEntRing = 64;
+constexpr uint32_t kListCap = 256;                         // hit words waiting for phase C
 constexpr int kStack3 = 40;                                // levels kept in shared memory (deeper: HBM spill)
 // per-warp shared memory (bytes)
 constexpr uint32_t kO3Mring = 0;                           // u32[1024]
 constexpr uint32_t kO3Hring = 4096;                        // uint4[64]
 constexpr uint32_t kO3Dnode = 5120;                        // i32[32][32] packed deltas
 constexpr uint32_t kO3Stack = 9216;                        // i16[40][32]
-constexpr uint32_t kO3Ent = kO3Stack + kStack3 * 64;       // uint4[64]
-constexpr uint32_t kO3Ehb = kO3Ent + kEntRing * 16;        // u8[64]
-constexpr uint32_t kO3Info = kO3Ehb + kEntRing;            // u32[6][32]: G, z, w, am, hm, neg
+constexpr uint32_t kO3List = kO3Stack + kStack3 * 64;      // u32[256]
+constexpr uint32_t kO3Info = kO3List + kListCap * 4;       // u32[6][32]: G, z, w, am, hm, neg
 constexpr uint32_t kO3Bars = kO3Info + 6 * 128;            // mbarriers
 constexpr uint32_t kWarpSmem3 = (kO3Bars + 64 + 127) & ~127u;
 constexpr uint32_t kI3G = 0, kI3Z = 32, kI3W = 64, kI3Am = 96, kI3Hm = 128, kI3Neg = 160;
@@ -101,6 +100,10 @@ __device__ __forceinline__ int lut_delta3(uint32_t i) {
     const int dcom = tk - t0;
     return dcorr * (1 << 20) + da * (1 << 10) + dcom;
 }
+template <bool SMEM_BITMAP>
+__device__ __forceinline__ uint32_t bitmap_word(const uint32_t* bm_s, const uint32_t* bm_g, uint32_t i) {
+    return SMEM_BITMAP ? bm_s[i] : __ldg(bm_g + i);
+}
 __device__ __forceinline__ int dc_of(int v) { return (v + (1 << 19)) >> 20; }
 __device__ __forceinline__ void unpack_delta3(int v, int& dcorr, int& da, int& dcom) {
     dcom = (int)((uint32_t)v << 22) >> 22;
@@ -118,7 +121,6 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     const uint32_t ctas_per_group = gridDim.x / p.ngroups;
     const uint32_t ggroup = p.group0 + group;
     const uint32_t FULL = 0xffffffffu;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     constexpr int BIG = 0x3fffffff;
 
     // ---- shared memory: [bitmap][lut][warp 0 .. warp 15]
@@ -130,8 +132,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     uint4* hring = reinterpret_cast<uint4*>(wbase + kO3Hring);
     int* dnode = reinterpret_cast<int*>(wbase + kO3Dnode);
     int16_t* stk = reinterpret_cast<int16_t*>(wbase + kO3Stack);
-    uint4* ent = reinterpret_cast<uint4*>(wbase + kO3Ent);
-    uint8_t* ehb = wbase + kO3Ehb;
+    uint32_t* list = reinterpret_cast<uint32_t*>(wbase + kO3List);
     uint32_t* info = reinterpret_cast<uint32_t*>(wbase + kO3Info);
     const uint32_t mring_a = smem_u32(mring), hring_a = smem_u32(hring), bars_a = smem_u32(wbase + kO3Bars);
     const uint32_t bm_a = smem_u32(bm_s);
@@ -185,52 +186,39 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     };
 
     uint32_t mphase = 0, hphase = 0;
-    uint32_t head = 0, tail = 0;     // entry ring (warp-uniform)
+    uint32_t head = 0, tail = 0;     // hit list (warp-uniform counters, slots mod kListCap)
     uint32_t mc_issue = 0, mc_end = 0, mc_wait = 0;
 
-    // C: the oldest `n` entries (lane = entry)
+    // C: the oldest `n` hit words (lane = hit)
     auto process = [&](uint32_t n) {
         if (lane < n) {
-            const uint32_t e = (head + lane) & (kEntRing - 1u);
-            const uint4 q = ent[e];
-            uint32_t hb = ehb[e];
-            do {
-                const uint32_t j = __ffs(hb) - 1;
-                hb &= hb - 1;
-                const uint32_t w = j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w;
-                const uint32_t* row = tabg + (size_t)(w >> 9) * 8u;
-                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row));
-                const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
-                const uint32_t nl = (w >> 4) & 31u;
-                const uint32_t lo = r0.y | (w & 15u);
-                uint32_t pm = r0.x;
-                while (pm) {
-                    const uint32_t s = __ffs(pm) - 1;
-                    pm &= pm - 1;
-                    const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
-                    const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
-                    const int d = lut[(e4 << 6) | lo];
-                    atomicAdd(&dnode[nl * 32u + s], d);
-                    atomicOr(&info[kI3Hm + s], 1u << nl);
-                    const int dc = dc_of(d);
-                    if (dc < 0) atomicAdd(reinterpret_cast<int*>(&info[kI3Neg + s]), dc);
-                }
-            } while (hb);
+            const uint32_t w = list[(head + lane) & (kListCap - 1u)];
+            const uint32_t* row = tabg + (size_t)mut3_pos(w) * 8u;
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row));
+            const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+            const uint32_t nl = (w >> 9) & 31u;
+            const uint32_t lo = r0.y | ((w >> 5) & 15u);
+            uint32_t pm = r0.x;
+            while (pm) {
+                const uint32_t s = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
+                const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
+                const int d = lut[(e4 << 6) | lo];
+                atomicAdd(&dnode[nl * 32u + s], d);
+                atomicOr(&info[kI3Hm + s], 1u << nl);
+                const int dc = dc_of(d);
+                if (dc < 0) atomicAdd(reinterpret_cast<int*>(&info[kI3Neg + s]), dc);
+            }
         }
         head += n;
     };
 
-    // B: scan stream words [o0, o1) (both multiples of 4) of the current tile
+    // B: scan stream words [o0, o1) (both multiples of 4) of the current tile, 512 words per step
     auto scan = [&](uint32_t o0, uint32_t o1) {
-        for (uint32_t off = o0; off < o1; off += 128u) {
-            const uint32_t c_hi = (min(off + 128u, o1) - 1u) / kChunk3;
-            while (mc_wait <= c_hi) {
-                const uint32_t s = mc_wait % kMutStages3;
-                mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
-                mphase ^= 1u << s;
-                mc_wait++;
-            }
-            // chunks below off / kChunk3 are dead: refill their stages
+        for (uint32_t off = o0; off < o1; off += 512u) {
+            const uint32_t lim = min(off + 512u, o1);
+            // chunks below off / kChunk3 are dead: refill their stages; then wait for the step's words
             while (mc_issue < mc_end && mc_issue < off / kChunk3 + kMutStages3) {
                 if (lane == 0) {
                     const uint32_t s = mc_issue % kMutStages3;
@@ -239,25 +227,69 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 }
                 mc_issue++;
             }
-            const uint32_t idx = off + 4u * lane;
-            const uint4 q = lds128_3(mring_a + ((idx & (kRingWords3 - 1u)) << 2));
-            const uint32_t w0 = SMEM_BITMAP ? lds32_3(bm_a + ((q.x >> 14) << 2)) : __ldg(bm_g + (q.x >> 14));
-            const uint32_t w1 = SMEM_BITMAP ? lds32_3(bm_a + ((q.y >> 14) << 2)) : __ldg(bm_g + (q.y >> 14));
-            const uint32_t w2 = SMEM_BITMAP ? lds32_3(bm_a + ((q.z >> 14) << 2)) : __ldg(bm_g + (q.z >> 14));
-            const uint32_t w3 = SMEM_BITMAP ? lds32_3(bm_a + ((q.w >> 14) << 2)) : __ldg(bm_g + (q.w >> 14));
-            uint32_t hb = (__funnelshift_r(w0, 0u, q.x >> 9) & 1u) | ((__funnelshift_r(w1, 0u, q.y >> 9) & 1u) << 1) |
-                          ((__funnelshift_r(w2, 0u, q.z >> 9) & 1u) << 2) | ((__funnelshift_r(w3, 0u, q.w >> 9) & 1u) << 3);
-            if (idx >= o1) hb = 0u;   // lanes past the segment read whatever the ring holds
-            const uint32_t any = __ballot_sync(FULL, hb != 0u);
-            if (hb) {
-                const uint32_t slot = (tail + __popc(any & lt_mask)) & (kEntRing - 1u);
-                ent[slot] = q;
-                ehb[slot] = (uint8_t)hb;
+            while (mc_wait <= (lim - 1u) / kChunk3) {
+                const uint32_t s = mc_wait % kMutStages3;
+                mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
+                mphase ^= 1u << s;
+                mc_wait++;
             }
-            tail += __popc(any);
-            if (tail - head >= 32u) {
+            const uint32_t nq = (lim - off + 127u) >> 7;      // quads (LDS.128) per lane in this step, 1..4
+            const uint32_t idx = off + 4u * lane;
+            uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                if (k < nq) {
+                    const uint4 q = lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2));
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.x >> 14), 0u, q.x), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.y >> 14), 0u, q.y), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.z >> 14), 0u, q.z), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.w >> 14), 0u, q.w), 1u);
+                } else {
+                    acc >>= 4;
+                }
+            }
+            uint32_t hb = acc >> 16;                           // bit 4k+j = word j of quad k
+            if (lim - off < 512u) {                            // lanes past the segment read whatever the ring holds
+                const int dwords = (int)(lim - idx);
+                const uint32_t nv = dwords > 0 ? min((uint32_t)(dwords + 127) >> 7, 4u) : 0u;
+                hb &= (1u << (4u * nv)) - 1u;
+            }
+            // compact the hit words into the list: lane l gets the slots after those of lanes < l
+            const uint32_t c = __popc(hb);
+            uint32_t incl = c;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
+                if (lane >= (uint32_t)dlt) incl += v;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (total == 0) continue;
+            // more hits than the list can take at once (dense call sets): one quad at a time
+            const bool split = total + 32u > kListCap;
+            for (uint32_t part = 0; part < (split ? 4u : 1u); part++) {
+                uint32_t hbp = hb, slot = tail + incl - c, tot = total;
+                if (split) {
+                    hbp = hb & (15u << (4u * part));
+                    const uint32_t cp = __popc(hbp);
+                    uint32_t ip = cp;
+#pragma unroll
+                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                        const uint32_t v = __shfl_up_sync(FULL, ip, dlt);
+                        if (lane >= (uint32_t)dlt) ip += v;
+                    }
+                    tot = __shfl_sync(FULL, ip, 31);
+                    slot = tail + ip - cp;
+                }
+                while (hbp) {
+                    const uint32_t bit = __ffs(hbp) - 1;
+                    hbp &= hbp - 1;
+                    const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
+                    list[slot & (kListCap - 1u)] = lds32_3(mring_a + ((wi & (kRingWords3 - 1u)) << 2));
+                    slot++;
+                }
+                tail += tot;
                 __syncwarp();
-                process(32u);
+                while (tail - head >= 32u) process(32u);
                 __syncwarp();
             }
         }

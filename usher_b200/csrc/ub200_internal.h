@@ -54,13 +54,16 @@ constexpr uint32_t kMutChunk = 256;   // mutation words per bulk copy (1 KB)
 constexpr uint32_t kHdrChunk = 32;    // headers per bulk copy (512 B)
 
 // ---- k_score3 layout (score_kernel3.cuh, DESIGN.md "Data layout") ----
-// stream word: pos:23 | lane:5 | prev:2 | mut:2   (lane = node & 31 in a block segment, level & 31 in a seed
-// segment; the reference allele comes from the sample table row).  Pad words carry pos = L (never called).
+// stream word: pos>>5 :18 | lane:5 | prev:2 | mut:2 | pos&31 :5   (lane = node & 31 in a block segment,
+// level & 31 in a seed segment; the reference allele comes from the sample table row).  The split position
+// gives the bitmap word index with one shift and the bit index with none (funnel shifts wrap at 32).
+// Pad words carry pos = L (never called).
 constexpr uint32_t kPosBits3 = 23;
 constexpr uint32_t kMaxPos3 = (1u << kPosBits3) - 2;
 UB200_HD inline uint32_t pack_mut3(uint32_t pos, uint32_t lane, uint32_t prevc, uint32_t mutc) {
-    return (pos << 9) | (lane << 4) | (prevc << 2) | mutc;
+    return ((pos >> 5) << 14) | (lane << 9) | (prevc << 7) | (mutc << 5) | (pos & 31u);
 }
+UB200_HD inline uint32_t mut3_pos(uint32_t w) { return ((w >> 14) << 5) | (w & 31u); }
 // header of the k_score3 layout: x = G, y = bitmask of the node's ancestors inside its own aligned 32-node
 // block, z = level:18 | flags:14, w = nmut<<16 | c0
 constexpr uint32_t kFlagOpen = 32u;    // internal node with a descendant beyond its 32-node block

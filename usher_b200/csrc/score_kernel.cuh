@@ -102,6 +102,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
+// one lane of the (converged) warp: lets ptxas feed UBLKCP from uniform registers without a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- per-hit correction
 // e: table byte of this lane's sample at the mutation's position: bit4 = sample calls this position,
 //    bits0-3 = cost of each path state there (0 for an N call).  m: packed tree mutation (warp-uniform).

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             const uint32_t lim = min(off + 512u, o1);
             // chunks below off / kChunk3 are dead: refill their stages; then wait for the step's words
             while (mc_issue < mc_end && mc_issue < off / kChunk3 + kMutStages3) {
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t s = mc_issue % kMutStages3;
                     mbar_expect_tx(bars_a + 8 * s, kChunk3 * 4);
                     bulk_g2s(mring_a + s * kChunk3 * 4, p.stream + (size_t)mc_issue * kChunk3, kChunk3 * 4, bars_a + 8 * s);

@@ -132,6 +132,7 @@ def place3(d, s_ptr, calls):
                 nodes = range(blk, min(blk + 32, n1))
                 seglen = sum(int(hdr[i]["nmut_c0"]) >> 16 for i in nodes)
                 o1 = o0 + ((seglen + 3) & ~3)
+                assert int(d["blk_words"][blk >> 5]) == o1 - o0   # what the scanner warp reads instead of headers
                 dl = seg_deltas(o0, o1)
                 o0 = o1
 

@@ -51,6 +51,7 @@ struct ub200_mat {
     // device: k_score3 layout (always resident when the genome fits its 23-bit position field)
     uint32_t* mstream = nullptr;
     ub200::NodeHdr* hdr3 = nullptr;
+    uint32_t *blk_words = nullptr;
     uint32_t *tiekey = nullptr, *tile3_start = nullptr, *tile3_w0 = nullptr, *tile3_lvl = nullptr, *tile3_sseg = nullptr,
              *seed_end = nullptr;
     int32_t* gstack3 = nullptr;
@@ -196,14 +197,14 @@ int ensure_v1(ub200_mat* M) {
     return 0;
 }
 
-// Streaming best-placement kernel (score_kernel3.cuh): one 16-warp CTA per SM.
+// Streaming best-placement kernel (score_kernel3.cuh): one CTA of 16 scanner/consumer warp pairs per SM.
 int launch_score3(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, uint32_t* grid_out,
                   bool collect = false) {
     using namespace ub200;
     Score3Params p;
     p.stream = M->mstream; p.hdr = M->hdr3; p.tiekey = M->tiekey;
     p.tile_start = M->tile3_start; p.tile_w0 = M->tile3_w0; p.tile_lvl = M->tile3_lvl; p.tile_sseg = M->tile3_sseg;
-    p.seed_end = M->seed_end;
+    p.seed_end = M->seed_end; p.blk_words = M->blk_words;
     p.n_nodes = M->n; p.n_tiles = M->n_tiles3; p.L = M->L;
     p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.gbest = S->gbest;
     p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups;
@@ -214,7 +215,7 @@ int launch_score3(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngro
     CU(cudaMemsetAsync(S->tile_counter, 0, 64, M->stream));
     const uint32_t grid = std::max<uint32_t>(ngroups, ((uint32_t)M->num_sms / ngroups) * ngroups);
     *grid_out = grid;
-    const uint32_t fixed = kLut3Bytes + (uint32_t)kWarps3 * kWarpSmem3;
+    const uint32_t fixed = kLut3Bytes + (uint32_t)kPairs3 * kWarpSmem3;
     const uint32_t bm_need = (S->bitmap_words * 4u + 127u) & ~127u;
     const bool smem_bitmap = fixed + bm_need <= kSmemLimit3;
     const size_t smem = fixed + (smem_bitmap ? bm_need : 0u);
@@ -275,7 +276,7 @@ void ub200_mat_destroy(ub200_mat* M) {
     cudaFree(M->anc); cudaFree(M->key_to_node); cudaFree(M->tie_index); cudaFree(M->num_leaves);
     cudaFree(M->gstack);
     cudaFree(M->mstream); cudaFree(M->hdr3); cudaFree(M->tiekey); cudaFree(M->tile3_start); cudaFree(M->tile3_w0);
-    cudaFree(M->tile3_lvl); cudaFree(M->tile3_sseg); cudaFree(M->seed_end); cudaFree(M->gstack3);
+    cudaFree(M->tile3_lvl); cudaFree(M->tile3_sseg); cudaFree(M->seed_end); cudaFree(M->blk_words); cudaFree(M->gstack3);
     if (M->scratch) ub200_samples_free(M->scratch);
     for (auto e : M->ev) cudaEventDestroy(e);
     if (M->own_stream) cudaStreamDestroy(M->own_stream);
@@ -295,8 +296,8 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     M->device = device;
     M->num_sms = prop.multiProcessorCount;
     M->grid = (uint32_t)M->num_sms * 2u;
-    // workers of either kernel (k_score: 2 CTAs x 8 warps per SM, k_score3: 1 CTA x kWarps3)
-    const uint32_t warps3 = (uint32_t)std::max(M->num_sms, 8) * ub200::kWarps3;
+    // workers of either kernel (k_score: 2 CTAs x 8 warps per SM, k_score3: 1 CTA x kPairs3 warp pairs)
+    const uint32_t warps3 = (uint32_t)std::max(M->num_sms, 8) * ub200::kPairs3;   // tile workers = warp pairs
     const uint32_t total_warps = std::max<uint32_t>(M->grid * ub200::kWarpsPerCta, warps3);
     std::string err;
     const char* mt = getenv("UB200_MIN_TILE");   // test hook: cut small trees into many tiles
@@ -322,8 +323,9 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
         guard(dev_upload(&M->tile3_lvl, d.tile3_lvl.data(), d.tile3_lvl.size(), M->stream));
         guard(dev_upload(&M->tile3_sseg, d.tile3_sseg.data(), d.tile3_sseg.size(), M->stream));
         guard(dev_upload(&M->seed_end, d.seed_end.data(), d.seed_end.size(), M->stream));
+        guard(dev_upload(&M->blk_words, d.blk_words.data(), d.blk_words.size(), M->stream));
         M->device_bytes += d.stream.size() * 4 + d.hdr3.size() * 16 + d.tiekey.size() * 4 +
-                           (d.tile3_start.size() * 4 + d.seed_end.size()) * 4;
+                           (d.tile3_start.size() * 4 + d.seed_end.size() + d.blk_words.size()) * 4;
         if (!rc && d.max_level + 1 > (uint32_t)ub200::kStack3) {
             M->gstack3_levels = d.max_level + 1 - ub200::kStack3;
             const size_t bytes = (size_t)warps3 * M->gstack3_levels * 32 * sizeof(int32_t);

@@ -76,6 +76,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     d.tile3_lvl.assign(T, 0);
     d.tile3_sseg.assign(T + 1, 0);
     d.seed_end.clear();
+    d.blk_words.assign(nblk, 0);
     d.stream.clear();
     d.stream.reserve(d.m + d.m / 6 + 4 * kChunk3);
     const uint32_t pad = pack_mut3(d.L, 0, 0, 0);
@@ -102,9 +103,11 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         d.seed_words += d.stream.size() - before;
         d.tile3_sseg[t + 1] = (uint32_t)d.seed_end.size();
         for (uint32_t b = n0; b < n1; b += 32) {
+            const size_t s0 = d.stream.size();
             for (uint32_t i = b; i < std::min(n1, b + 32); i++)
                 for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) d.stream.push_back(conv(d.mutw[k], i & 31u));
             align_to(4);
+            d.blk_words[b >> 5] = (uint32_t)(d.stream.size() - s0);
         }
     }
     align_to(kChunk3);
@@ -332,7 +335,7 @@ struct ub200_derived_view {
     uint32_t n_tiles3, n_seed_segs;
     uint64_t stream_words;
     const uint32_t* stream; const void* hdr3; const uint32_t* tile3_start; const uint32_t* tile3_w0;
-    const uint32_t* tile3_lvl; const uint32_t* tile3_sseg; const uint32_t* seed_end;
+    const uint32_t* tile3_lvl; const uint32_t* tile3_sseg; const uint32_t* seed_end; const uint32_t* blk_words;
 };
 
 int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32_t min_tile_cost, void** handle,
@@ -357,6 +360,7 @@ int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32
     view->stream = d->stream.data(); view->hdr3 = d->hdr3.data(); view->tile3_start = d->tile3_start.data();
     view->tile3_w0 = d->tile3_w0.data(); view->tile3_lvl = d->tile3_lvl.data();
     view->tile3_sseg = d->tile3_sseg.data(); view->seed_end = d->seed_end.data();
+    view->blk_words = d->blk_words.data();
     *handle = d;
     return UB200_OK;
 }

@@ -1,24 +1,30 @@
 // k_score3 — streaming best-placement kernel on the segment layout (ub200_internal.h, DESIGN.md "Kernels").
 //
-// One persistent launch scores every node of the tree against NG groups of 32 samples.  A warp is an independent
-// worker on tiles (contiguous DFS ranges of whole 32-node blocks).  A tile is ONE contiguous piece of the
-// mutation stream — [seed segments][block segments] — that the warp pulls through its own shared-memory ring
-// with 1 KB bulk async copies (cp.async.bulk -> UBLKCP) completing on per-stage mbarriers; headers come through a
-// second ring, 512 B (one block) per copy.  Per segment the lane role switches by phase:
-//   A  lane = node      header decode; the segment length is the warp sum of the rows (no offsets are read)
-//   B  lane = 16 words  up to four LDS.128 per lane per step (512 words); every word's position is tested against
-//                       the group's bitmap (3 instructions + 1 funnel shift that collects the hit bits); the
-//                       hit words are compacted into a 256-word list (one warp prefix sum per step)
-//   C  lane = hit       hit word -> node lane (stored in the word), table row of the position (32 B, L2) ->
-//                       for every sample calling the position: packed (dcorr, da, dcommon) from a 1024-entry
-//                       LUT, shared-memory atomics into dnode[node][sample], hm[sample] |= node,
-//                       neg[sample] += min(dcorr, 0)
-//   bound               exact lower bound of every pair of the block:  min(G - nmut) + gmin + neg  against the
-//                       running best; blocks that cannot hold an optimum skip E and F entirely
-//   E  lane = node      non-hit pairs of a sample that can still improve or tie
-//   F  lane = sample    hit pairs, exactly (score, validity, tie key)
-//   G  lane = sample    path corrections of the block's OPEN chain (nodes with descendants in later blocks) ->
-//                       stack rows the following blocks read
+// One persistent launch scores every node of the tree against NG groups of 32 samples.  The unit of work is a
+// tile: a contiguous DFS range of whole 32-node blocks whose mutations are ONE contiguous piece of the stream,
+// [seed segments][block segments].  A CTA holds 16 warp PAIRS; a pair works on one tile at a time:
+//
+//   scanner warp   pulls the tile's stream through a shared-memory ring with 1 KB bulk async copies
+//                  (cp.async.bulk -> UBLKCP) completing on per-stage mbarriers, and tests every word's position
+//                  against the group's bitmap (lane = 16 words per 512-word step: four LDS.128, per word one
+//                  bitmap LDS, one wrap shift, one funnel shift that collects the hit bits).  Hit words are
+//                  compacted (one warp prefix sum per step) into one of four 64-word message slots and handed
+//                  to the consumer through full/empty mbarriers; a segment is one or more messages, the last
+//                  one flagged.  The scanner needs no sample state, only the bitmap.
+//   consumer warp  owns the sample state.  Per block:
+//     A  lane = node     header decode (headers arrive through its own bulk-copy ring, 512 B = one block)
+//     C  lane = hit      hit word -> node lane (stored in the word), table row of the position (32 B, L2) ->
+//                        for every sample calling the position: packed (dcorr, da, dcommon) from a 1024-entry
+//                        LUT, shared-memory atomics into dnode[node][sample], hm[sample] |= node,
+//                        neg[sample] += min(dcorr, 0)
+//     bound              exact lower bound of every pair of the block:  min(G - nmut) + gmin + neg  against the
+//                        running best; blocks that cannot hold an optimum skip E and F entirely
+//     E  lane = node     non-hit pairs of a sample that can still improve or tie
+//     F  lane = sample   hit pairs, exactly (score, validity, tie key)
+//     G  lane = sample   path corrections of the block's OPEN chain (nodes with descendants in later blocks)
+//                        -> stack rows the following blocks read
+//   Seed segments (the rows of the tile's root path, 32 levels per segment) go through the same scanner ->
+//   consumer path and initialise the stack.
 // The correction of the path above a node inside its own block is never materialised: it is
 // stack[level above the block] + sum of dnode over (in-block ancestors & hit nodes of the sample), with the
 // in-block ancestor mask precomputed in the header.  All pruning is exact, so results are schedule-independent.
@@ -27,23 +33,26 @@
 
 namespace ub200 {
 
-constexpr int kWarps3 = 16;
-constexpr int kThreads3 = kWarps3 * 32;
+constexpr int kPairs3 = 16;
+constexpr int kThreads3 = kPairs3 * 64;
 constexpr int kMutStages3 = 4;
 constexpr uint32_t kRingWords3 = kChunk3 * kMutStages3;   // 1024 words = 4 KB
 constexpr int kHdrStages3 = 2;
-constexpr uint32_t kListCap = 256;                         // hit words waiting for phase C
+constexpr uint32_t kSlots3 = 4, kSlotCap3 = 64;            // scanner -> consumer messages
 constexpr int kStack3 = 40;                                // levels kept in shared memory (deeper: HBM spill)
-// per-warp shared memory (bytes)
-constexpr uint32_t kO3Mring = 0;                           // u32[1024]
-constexpr uint32_t kO3Hring = 4096;                        // uint4[64]
+// per-pair shared memory (bytes)
+constexpr uint32_t kO3Mring = 0;                           // u32[1024]            scanner
+constexpr uint32_t kO3Hring = 4096;                        // uint4[64]            consumer
 constexpr uint32_t kO3Dnode = 5120;                        // i32[32][32] packed deltas
 constexpr uint32_t kO3Stack = 9216;                        // i16[40][32]
-constexpr uint32_t kO3List = kO3Stack + kStack3 * 64;      // u32[256]
-constexpr uint32_t kO3Info = kO3List + kListCap * 4;       // u32[6][32]: G, z, w, am, hm, neg
-constexpr uint32_t kO3Bars = kO3Info + 6 * 128;            // mbarriers
-constexpr uint32_t kWarpSmem3 = (kO3Bars + 64 + 127) & ~127u;
+constexpr uint32_t kO3List = kO3Stack + kStack3 * 64;      // u32[4][64] hit words
+constexpr uint32_t kO3Info = kO3List + kSlots3 * kSlotCap3 * 4;   // u32[6][32]: G, z, w, am, hm, neg
+constexpr uint32_t kO3Msg = kO3Info + 6 * 128;             // uint2[4]: (count | flags << 16, payload)
+constexpr uint32_t kO3Bars = kO3Msg + kSlots3 * 8;         // mbarriers: 4 ring, 2 header, 4 full, 4 empty
+constexpr uint32_t kWarpSmem3 = (kO3Bars + 14 * 8 + 127) & ~127u;
 constexpr uint32_t kI3G = 0, kI3Z = 32, kI3W = 64, kI3Am = 96, kI3Hm = 128, kI3Neg = 160;
+constexpr uint32_t kBarHdr = kMutStages3, kBarFull = kMutStages3 + kHdrStages3, kBarEmpty = kBarFull + kSlots3;
+constexpr uint32_t kMsgLast = 1u << 16, kMsgTile = 2u << 16, kMsgEnd = 4u << 16;
 constexpr uint32_t kLut3Bytes = 4096;
 constexpr uint32_t kMaxRowV3 = 500;      // packed 10-bit delta fields
 constexpr uint32_t kMaxCallsV3 = 32000;  // path corrections are int16
@@ -53,6 +62,7 @@ struct Score3Params {
     const uint32_t* stream;
     const NodeHdr* hdr;           // hdr3
     const uint32_t* tiekey;
+    const uint32_t* blk_words;    // [blocks] stream words of each 32-node block segment (multiple of 4)
     const uint32_t* tile_start;   // [T+1]
     const uint32_t* tile_w0;      // [T+1]
     const uint32_t* tile_lvl;     // [T]
@@ -84,6 +94,9 @@ __device__ __forceinline__ uint4 lds128_3(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __noinline__ int spill_read3(const int32_t* gstk, uint32_t level, uint32_t s) {
     return gstk[(size_t)(level - kStack3) * 32u + s];
 }
@@ -112,10 +125,15 @@ __device__ __forceinline__ void unpack_delta3(int v, int& dcorr, int& da, int& d
     dcorr = (v1 - da) >> 10;
 }
 
+// COLLECT = false: best placement per sample.  COLLECT = true: second pass that lists every optimal node of each
+// sample (best_j_vec + node_has_unique); the final best score is the bound, so almost every block is pruned.
 template <bool SMEM_BITMAP, bool COLLECT>
 __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t pair = warp >> 1;
+    // scanner / consumer alternate so that every SM sub-partition (warp % 4) gets both kinds
+    const bool is_scanner = (warp & 1u) == ((warp >> 2) & 1u);
     const uint32_t group = blockIdx.x % p.ngroups;
     const uint32_t cta_in_group = blockIdx.x / p.ngroups;
     const uint32_t ctas_per_group = gridDim.x / p.ngroups;
@@ -123,19 +141,19 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     const uint32_t FULL = 0xffffffffu;
     constexpr int BIG = 0x3fffffff;
 
-    // ---- shared memory: [bitmap][lut][warp 0 .. warp 15]
+    // ---- shared memory: [bitmap][lut][pair 0 .. pair 15]
     uint32_t* bm_s = reinterpret_cast<uint32_t*>(smem);
     const uint32_t bm_bytes = SMEM_BITMAP ? ((p.bitmap_words * 4u + 127u) & ~127u) : 0u;
     int* lut = reinterpret_cast<int*>(smem + bm_bytes);
-    uint8_t* wbase = smem + bm_bytes + kLut3Bytes + warp * kWarpSmem3;
+    uint8_t* wbase = smem + bm_bytes + kLut3Bytes + pair * kWarpSmem3;
     uint32_t* mring = reinterpret_cast<uint32_t*>(wbase + kO3Mring);
     uint4* hring = reinterpret_cast<uint4*>(wbase + kO3Hring);
     int* dnode = reinterpret_cast<int*>(wbase + kO3Dnode);
     int16_t* stk = reinterpret_cast<int16_t*>(wbase + kO3Stack);
     uint32_t* list = reinterpret_cast<uint32_t*>(wbase + kO3List);
     uint32_t* info = reinterpret_cast<uint32_t*>(wbase + kO3Info);
+    volatile uint2* msg = reinterpret_cast<volatile uint2*>(wbase + kO3Msg);
     const uint32_t mring_a = smem_u32(mring), hring_a = smem_u32(hring), bars_a = smem_u32(wbase + kO3Bars);
-    const uint32_t bm_a = smem_u32(bm_s);
 
     const uint32_t* bm_g = p.bitmap + (size_t)ggroup * p.bitmap_words;
     if (SMEM_BITMAP) {
@@ -144,356 +162,420 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
         for (uint32_t i = threadIdx.x; i < p.bitmap_words / 4; i += kThreads3) dst[i] = __ldg(src + i);
     }
     for (uint32_t i = threadIdx.x; i < 1024; i += kThreads3) lut[i] = lut_delta3(i);
-    // lanes past a segment's end still index the bitmap with what the ring holds: only ever valid words
-    for (uint32_t i = lane; i < kRingWords3; i += 32) mring[i] = 0u;
-    if (lane == 0) {
-        for (int i = 0; i < kMutStages3 + kHdrStages3; i++) mbar_init(bars_a + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (is_scanner) {
+        // lanes past a segment's end still index the bitmap with what the ring holds: only ever valid words
+        for (uint32_t i = lane; i < kRingWords3; i += 32) mring[i] = 0u;
+        if (lane == 0) {
+            for (uint32_t i = 0; i < kBarEmpty + kSlots3; i++) mbar_init(bars_a + 8 * i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
 
-    const uint32_t* tabg = p.tab + (size_t)ggroup * p.L * 8u;
-    int32_t* gstk = p.gstack ? p.gstack + ((size_t)(blockIdx.x * kWarps3 + warp) * p.gstack_levels) * 32u : nullptr;
-    const uint32_t sample = ggroup * 32u + lane;
-    const bool live = sample < p.n_samples;
+    if (is_scanner) {
+        // =====================================================================================================
+        // scanner
+        // =====================================================================================================
+        uint32_t mphase = 0;
+        uint32_t mc_issue = 0, mc_end = 0, mc_wait = 0;
+        uint32_t nmsg = 0;        // messages sent so far; the open one lives in slot nmsg % kSlots3
+        uint32_t fill = 0;        // hit words in the open message
+        auto open_msg = [&]() {   // wait until the consumer has released the slot
+            const uint32_t s = nmsg % kSlots3;
+            mbar_wait(bars_a + 8 * (kBarEmpty + s), ((nmsg / kSlots3) & 1u) ^ 1u);
+            fill = 0;
+        };
+        auto send_msg = [&](uint32_t flags, uint32_t payload) {
+            const uint32_t s = nmsg % kSlots3;
+            __syncwarp();
+            if (elect_one()) {
+                msg[s].x = fill | flags;
+                msg[s].y = payload;
+                mbar_arrive(bars_a + 8 * (kBarFull + s));
+            }
+            nmsg++;
+        };
 
-    auto stack_read = [&](uint32_t level, uint32_t s) -> int {
-        if (__builtin_expect(level >= (uint32_t)kStack3, 0)) return spill_read3(gstk, level, s);
-        return stk[level * 32u + s];
-    };
-    auto stack_write = [&](uint32_t level, uint32_t s, int v) {
-        if (__builtin_expect(level >= (uint32_t)kStack3, 0)) spill_write3(gstk, level, s, v);
-        else stk[level * 32u + s] = (int16_t)v;
-    };
-
-    // per-lane (= sample) running best (COLLECT: the known final best, fixed)
-    int bsc = COLLECT ? (live ? p.target_rel[sample] : (int)0x80000000) : 0x7fffffff;
-    unsigned long long bkey = ~0ull;
-    uint32_t cnt = 0;
-    auto merge = [&](int sc, uint32_t hu, uint32_t node) {
-        if (COLLECT) {
-            if (sc == bsc) {
-                const uint32_t k = atomicAdd(p.set_fill + sample, 1u);
-                p.set_out[p.set_ptr[sample] + k] = node | (hu ? 0x80000000u : 0u);
-            }
-            return;
-        }
-        const uint32_t tiekey = __ldg(p.tiekey + node);
-        const unsigned long long key =
-            ((unsigned long long)(uint32_t)(sc + kScoreBias) << 33) | ((unsigned long long)tiekey << 1) | hu;
-        if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
-        else if (sc == bsc) { cnt++; if (key < bkey) bkey = key; }
-    };
-
-    uint32_t mphase = 0, hphase = 0;
-    uint32_t head = 0, tail = 0;     // hit list (warp-uniform counters, slots mod kListCap)
-    uint32_t mc_issue = 0, mc_end = 0, mc_wait = 0;
-
-    // C: the oldest `n` hit words (lane = hit)
-    auto process = [&](uint32_t n) {
-        if (lane < n) {
-            const uint32_t w = list[(head + lane) & (kListCap - 1u)];
-            const uint32_t* row = tabg + (size_t)mut3_pos(w) * 8u;
-            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row));
-            const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
-            const uint32_t nl = (w >> 9) & 31u;
-            const uint32_t lo = r0.y | ((w >> 5) & 15u);
-            uint32_t pm = r0.x;
-            while (pm) {
-                const uint32_t s = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
-                const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
-                const int d = lut[(e4 << 6) | lo];
-                atomicAdd(&dnode[nl * 32u + s], d);
-                atomicOr(&info[kI3Hm + s], 1u << nl);
-                const int dc = dc_of(d);
-                if (dc < 0) atomicAdd(reinterpret_cast<int*>(&info[kI3Neg + s]), dc);
-            }
-        }
-        head += n;
-    };
-
-    // B: scan stream words [o0, o1) (both multiples of 4) of the current tile, 512 words per step
-    auto scan = [&](uint32_t o0, uint32_t o1) {
-        for (uint32_t off = o0; off < o1; off += 512u) {
-            const uint32_t lim = min(off + 512u, o1);
-            // chunks below off / kChunk3 are dead: refill their stages; then wait for the step's words
-            while (mc_issue < mc_end && mc_issue < off / kChunk3 + kMutStages3) {
-                if (elect_one()) {
-                    const uint32_t s = mc_issue % kMutStages3;
-                    mbar_expect_tx(bars_a + 8 * s, kChunk3 * 4);
-                    bulk_g2s(mring_a + s * kChunk3 * 4, p.stream + (size_t)mc_issue * kChunk3, kChunk3 * 4, bars_a + 8 * s);
-                }
-                mc_issue++;
-            }
-            while (mc_wait <= (lim - 1u) / kChunk3) {
-                const uint32_t s = mc_wait % kMutStages3;
-                mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
-                mphase ^= 1u << s;
-                mc_wait++;
-            }
-            const uint32_t nq = (lim - off + 127u) >> 7;      // quads (LDS.128) per lane in this step, 1..4
-            const uint32_t idx = off + 4u * lane;
-            uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
-#pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
-                if (k < nq) {
-                    const uint4 q = lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2));
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.x >> 14), 0u, q.x), 1u);
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.y >> 14), 0u, q.y), 1u);
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.z >> 14), 0u, q.z), 1u);
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.w >> 14), 0u, q.w), 1u);
-                } else {
-                    acc >>= 4;
-                }
-            }
-            uint32_t hb = acc >> 16;                           // bit 4k+j = word j of quad k
-            if (lim - off < 512u) {                            // lanes past the segment read whatever the ring holds
-                const int dwords = (int)(lim - idx);
-                const uint32_t nv = dwords > 0 ? min((uint32_t)(dwords + 127) >> 7, 4u) : 0u;
-                hb &= (1u << (4u * nv)) - 1u;
-            }
-            // compact the hit words into the list: lane l gets the slots after those of lanes < l
-            const uint32_t c = __popc(hb);
-            uint32_t incl = c;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
-                if (lane >= (uint32_t)dlt) incl += v;
-            }
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
-            if (total == 0) continue;
-            // more hits than the list can take at once (dense call sets): one quad at a time
-            const bool split = total + 32u > kListCap;
-            for (uint32_t part = 0; part < (split ? 4u : 1u); part++) {
-                uint32_t hbp = hb, slot = tail + incl - c, tot = total;
-                if (split) {
-                    hbp = hb & (15u << (4u * part));
-                    const uint32_t cp = __popc(hbp);
-                    uint32_t ip = cp;
-#pragma unroll
-                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                        const uint32_t v = __shfl_up_sync(FULL, ip, dlt);
-                        if (lane >= (uint32_t)dlt) ip += v;
+        // scan stream words [o0, o1) (both multiples of 4) of the current tile, 512 words per step; the hit
+        // words go to the open message, which is sent (not flagged last) and reopened whenever it is full
+        auto scan = [&](uint32_t o0, uint32_t o1) {
+            for (uint32_t off = o0; off < o1; off += 512u) {
+                const uint32_t lim = min(off + 512u, o1);
+                // chunks below off / kChunk3 are dead: refill their stages; then wait for the step's words
+                while (mc_issue < mc_end && mc_issue < off / kChunk3 + kMutStages3) {
+                    if (elect_one()) {
+                        const uint32_t s = mc_issue % kMutStages3;
+                        mbar_expect_tx(bars_a + 8 * s, kChunk3 * 4);
+                        bulk_g2s(mring_a + s * kChunk3 * 4, p.stream + (size_t)mc_issue * kChunk3, kChunk3 * 4,
+                                 bars_a + 8 * s);
                     }
-                    tot = __shfl_sync(FULL, ip, 31);
-                    slot = tail + ip - cp;
+                    mc_issue++;
                 }
-                while (hbp) {
-                    const uint32_t bit = __ffs(hbp) - 1;
-                    hbp &= hbp - 1;
-                    const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
-                    list[slot & (kListCap - 1u)] = lds32_3(mring_a + ((wi & (kRingWords3 - 1u)) << 2));
-                    slot++;
+                while (mc_wait <= (lim - 1u) / kChunk3) {
+                    const uint32_t s = mc_wait % kMutStages3;
+                    mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
+                    mphase ^= 1u << s;
+                    mc_wait++;
                 }
-                tail += tot;
+                const uint32_t nq = (lim - off + 127u) >> 7;      // quads (LDS.128) per lane in this step, 1..4
+                const uint32_t idx = off + 4u * lane;
+                uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    if (k < nq) {
+                        const uint4 q = lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2));
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.x >> 14), 0u, q.x), 1u);
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.y >> 14), 0u, q.y), 1u);
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.z >> 14), 0u, q.z), 1u);
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.w >> 14), 0u, q.w), 1u);
+                    } else {
+                        acc >>= 4;
+                    }
+                }
+                uint32_t hb = acc >> 16;                           // bit 4k+j = word j of quad k
+                if (lim - off < 512u) {                            // lanes past the segment read whatever the ring holds
+                    const int dwords = (int)(lim - idx);
+                    const uint32_t nv = dwords > 0 ? min((uint32_t)(dwords + 127) >> 7, 4u) : 0u;
+                    hb &= (1u << (4u * nv)) - 1u;
+                }
+                // compact: lane l's hits follow those of lanes < l
+                const uint32_t c = __popc(hb);
+                uint32_t incl = c;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
+                    if (lane >= (uint32_t)dlt) incl += v;
+                }
+                uint32_t remaining = __shfl_sync(FULL, incl, 31);
+                uint32_t mine = incl - c;       // index of this lane's next hit among the step's hits
+                uint32_t done = 0;              // hits of this step already placed in messages
+                while (remaining) {
+                    const uint32_t take = min(kSlotCap3 - fill, remaining);
+                    const uint32_t slot_a = (nmsg % kSlots3) * kSlotCap3 + fill;
+                    while (hb && mine < done + take) {
+                        const uint32_t bit = __ffs(hb) - 1;
+                        hb &= hb - 1;
+                        const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
+                        list[slot_a + (mine - done)] = lds32_3(mring_a + ((wi & (kRingWords3 - 1u)) << 2));
+                        mine++;
+                    }
+                    fill += take;
+                    remaining -= take;
+                    done += take;
+                    if (fill == kSlotCap3) {
+                        send_msg(0u, 0u);
+                        open_msg();
+                    }
+                }
+            }
+        };
+
+        for (;;) {
+            // tiles are handed out in DFS order by a per-group counter: balances uneven tiles, and the CTAs of
+            // different groups still walk the tree in the same order (one HBM read, the rest from L2)
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(p.tile_counter + group, 1u);
+            t = __shfl_sync(FULL, t, 0);
+            open_msg();
+            if (t >= p.n_tiles) {
+                send_msg(kMsgEnd, 0u);
+                break;
+            }
+            send_msg(kMsgTile, t);
+            const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
+            const uint32_t lvl0 = p.tile_lvl[t];
+            const uint32_t sseg = p.tile_sseg[t];
+            mc_issue = p.tile_w0[t];
+            mc_end = p.tile_w0[t + 1];
+            mc_wait = mc_issue;
+            uint32_t o0 = mc_issue * kChunk3;
+            // seed segments, then one segment per block
+            for (uint32_t l0 = 0; l0 < lvl0; l0 += 32u) {
+                const uint32_t o1 = p.seed_end[sseg + (l0 >> 5)] * 4u;
+                open_msg();
+                scan(o0, o1);
+                send_msg(kMsgLast, 0u);
+                o0 = o1;
+            }
+            const uint32_t b0 = n0 >> 5, nb = (n1 - n0 + 31u) >> 5;
+            uint32_t bw = 0;
+            for (uint32_t b = 0; b < nb; b++) {
+                if ((b & 31u) == 0) bw = (b + lane < nb) ? __ldg(p.blk_words + b0 + b + lane) : 0u;
+                const uint32_t o1 = o0 + __shfl_sync(FULL, bw, b & 31u);
+                open_msg();
+                scan(o0, o1);
+                send_msg(kMsgLast, 0u);
+                o0 = o1;
+            }
+        }
+    } else {
+        // =====================================================================================================
+        // consumer
+        // =====================================================================================================
+        const uint32_t* tabg = p.tab + (size_t)ggroup * p.L * 8u;
+        int32_t* gstk = p.gstack ? p.gstack + ((size_t)(blockIdx.x * kPairs3 + pair) * p.gstack_levels) * 32u : nullptr;
+        const uint32_t sample = ggroup * 32u + lane;
+        const bool live = sample < p.n_samples;
+
+        auto stack_read = [&](uint32_t level, uint32_t s) -> int {
+            if (__builtin_expect(level >= (uint32_t)kStack3, 0)) return spill_read3(gstk, level, s);
+            return stk[level * 32u + s];
+        };
+        auto stack_write = [&](uint32_t level, uint32_t s, int v) {
+            if (__builtin_expect(level >= (uint32_t)kStack3, 0)) spill_write3(gstk, level, s, v);
+            else stk[level * 32u + s] = (int16_t)v;
+        };
+
+        // per-lane (= sample) running best (COLLECT: the known final best, fixed)
+        int bsc = COLLECT ? (live ? p.target_rel[sample] : (int)0x80000000) : 0x7fffffff;
+        unsigned long long bkey = ~0ull;
+        uint32_t cnt = 0;
+        auto merge = [&](int sc, uint32_t hu, uint32_t node) {
+            if (COLLECT) {
+                if (sc == bsc) {
+                    const uint32_t k = atomicAdd(p.set_fill + sample, 1u);
+                    p.set_out[p.set_ptr[sample] + k] = node | (hu ? 0x80000000u : 0u);
+                }
+                return;
+            }
+            const uint32_t tiekey = __ldg(p.tiekey + node);
+            const unsigned long long key =
+                ((unsigned long long)(uint32_t)(sc + kScoreBias) << 33) | ((unsigned long long)tiekey << 1) | hu;
+            if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
+            else if (sc == bsc) { cnt++; if (key < bkey) bkey = key; }
+        };
+        auto zero_dnode = [&]() {
+#pragma unroll
+            for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(dnode)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
+            info[kI3Hm + lane] = 0;
+            info[kI3Neg + lane] = 0;
+        };
+        // C: the hit words of one message (lane = hit)
+        auto process = [&](uint32_t slot, uint32_t n) {
+            for (uint32_t k0 = 0; k0 < n; k0 += 32u) {
+                if (k0 + lane < n) {
+                    const uint32_t w = list[slot * kSlotCap3 + k0 + lane];
+                    const uint32_t* row = tabg + (size_t)mut3_pos(w) * 8u;
+                    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row));
+                    const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+                    const uint32_t nl = (w >> 9) & 31u;
+                    const uint32_t lo = r0.y | ((w >> 5) & 15u);
+                    uint32_t pm = r0.x;
+                    while (pm) {
+                        const uint32_t s = __ffs(pm) - 1;
+                        pm &= pm - 1;
+                        const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
+                        const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
+                        const int d = lut[(e4 << 6) | lo];
+                        atomicAdd(&dnode[nl * 32u + s], d);
+                        atomicOr(&info[kI3Hm + s], 1u << nl);
+                        const int dc = dc_of(d);
+                        if (dc < 0) atomicAdd(reinterpret_cast<int*>(&info[kI3Neg + s]), dc);
+                    }
+                }
+            }
+        };
+        uint32_t nmsg = 0;
+        // receive the messages of one segment and fold their hits into dnode / hm / neg
+        auto take_segment = [&]() {
+            for (;;) {
+                const uint32_t s = nmsg % kSlots3;
+                mbar_wait(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
+                const uint32_t m = msg[s].x;
+                process(s, m & 0xffffu);
                 __syncwarp();
-                while (tail - head >= 32u) process(32u);
+                if (elect_one()) mbar_arrive(bars_a + 8 * (kBarEmpty + s));
+                nmsg++;
+                if (m & kMsgLast) break;
+            }
+            __syncwarp();
+        };
+
+        uint32_t hphase = 0;
+        for (;;) {
+            uint32_t t;
+            {
+                const uint32_t s = nmsg % kSlots3;
+                mbar_wait(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
+                const uint32_t m = msg[s].x;
+                t = msg[s].y;
                 __syncwarp();
+                if (elect_one()) mbar_arrive(bars_a + 8 * (kBarEmpty + s));
+                nmsg++;
+                if (m & kMsgEnd) break;
             }
-        }
-    };
-    auto drain = [&]() {
-        __syncwarp();
-        if (tail != head) process(tail - head);
-        __syncwarp();
-    };
-    auto zero_dnode = [&]() {
-#pragma unroll
-        for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(dnode)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
-        info[kI3Hm + lane] = 0;
-        info[kI3Neg + lane] = 0;
-    };
-
-    for (;;) {
-        // tiles are handed out in DFS order by a per-group counter: balances uneven tiles, and the CTAs of
-        // different groups still walk the tree in the same order (one HBM read, the rest from L2)
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(p.tile_counter + group, 1u);
-        t = __shfl_sync(FULL, t, 0);
-        if (t >= p.n_tiles) break;
-        const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
-        const uint32_t lvl0 = p.tile_lvl[t];
-        const uint32_t sseg = p.tile_sseg[t];
-        mc_issue = p.tile_w0[t];
-        mc_end = p.tile_w0[t + 1];
-        mc_wait = mc_issue;
-        uint32_t o0 = mc_issue * kChunk3;
-        uint32_t hc_issue = n0 / kHdrChunk;
-        const uint32_t hc_end = (n1 - 1) / kHdrChunk + 1;
-        if (lane == 0) {
-            for (int i = 0; i < kMutStages3 && mc_issue + i < mc_end; i++) {
-                const uint32_t c = mc_issue + i, s = c % kMutStages3;
-                mbar_expect_tx(bars_a + 8 * s, kChunk3 * 4);
-                bulk_g2s(mring_a + s * kChunk3 * 4, p.stream + (size_t)c * kChunk3, kChunk3 * 4, bars_a + 8 * s);
-            }
-            for (int i = 0; i < kHdrStages3 && hc_issue + i < hc_end; i++) {
-                const uint32_t c = hc_issue + i, s = c % kHdrStages3;
-                mbar_expect_tx(bars_a + 8 * (kMutStages3 + s), kHdrChunk * 16);
-                bulk_g2s(hring_a + s * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
-                         bars_a + 8 * (kMutStages3 + s));
-            }
-        }
-        mc_issue = min(mc_issue + kMutStages3, mc_end);
-        hc_issue = min(hc_issue + kHdrStages3, hc_end);
-
-        // cross-warp bound of this lane's sample, and the tile-local floor of every stack value
-        const int gb = COLLECT ? bsc : (live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff);
-        int gmin = 0;
-
-        // ================= seed: path corrections of levels 0 .. lvl0-1, 32 levels per segment =================
-        for (uint32_t l0 = 0; l0 < lvl0; l0 += 32u) {
-            zero_dnode();
-            __syncwarp();
-            const uint32_t o1 = p.seed_end[sseg + (l0 >> 5)] * 4u;
-            scan(o0, o1);
-            o0 = o1;
-            drain();
-            const uint32_t cn = min(32u, lvl0 - l0);
-            int v = l0 ? stack_read(l0 - 1u, lane) : 0;
-            for (uint32_t j = 0; j < cn; j++) {
-                v += dc_of(dnode[j * 32u + lane]);
-                stack_write(l0 + j, lane, v);
-                gmin = min(gmin, v);
-            }
-            __syncwarp();
-        }
-
-        for (uint32_t blk = n0; blk < n1; blk += 32u) {
-            // ================= A: headers (lane = node) =================
-            const uint32_t hc = blk / kHdrChunk, hs = hc % kHdrStages3;
-            mbar_wait(bars_a + 8 * (kMutStages3 + hs), (hphase >> hs) & 1u);
-            hphase ^= 1u << hs;
-            const uint4 h = hring[hs * kHdrChunk + lane];
-            const bool act = blk + lane < n1;
-            const uint32_t level = h.z >> kLevelShift, flags = h.z & 0x3fffu;
-            const uint32_t nmut = act ? (h.w >> 16) : 0u;
-            const uint32_t o1 = o0 + ((__reduce_add_sync(FULL, nmut) + 3u) & ~3u);
-            const bool dense_ok = act && (flags & kFlagValid0);
-            const int min_g = __reduce_min_sync(FULL, dense_ok ? h.x : BIG);
-            const int min_gn = __reduce_min_sync(FULL, act ? h.x - (int)nmut : BIG);
-            info[kI3G + lane] = (uint32_t)h.x;
-            info[kI3Z + lane] = h.z;
-            info[kI3W + lane] = h.w;
-            info[kI3Am + lane] = h.y;
-            zero_dnode();
-            __syncwarp();
-            if (hc_issue < hc_end) {   // this block's header stage is free again
-                if (lane == 0) {
-                    const uint32_t c = hc_issue, s2 = c % kHdrStages3;
-                    mbar_expect_tx(bars_a + 8 * (kMutStages3 + s2), kHdrChunk * 16);
-                    bulk_g2s(hring_a + s2 * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
-                             bars_a + 8 * (kMutStages3 + s2));
-                }
-                hc_issue++;
-            }
-
-            // ================= B + C =================
-            scan(o0, o1);
-            o0 = o1;
-            drain();
-
-            // ================= bound: can any pair of this block still be optimal? =================
-            const uint32_t hmv = info[kI3Hm + lane];             // lane = sample: its hit nodes
-            const int lbase = gmin + (int)info[kI3Neg + lane];
-            const int bound = min(bsc, gb);
-            const uint32_t needs = __ballot_sync(FULL, live && min_gn + lbase <= bound);
-            if (needs) {
-                // correction of the path above node (level, am) for sample s
-                auto above = [&](uint32_t lvl, uint32_t am, uint32_t hmask, uint32_t s) -> int {
-                    const uint32_t top = lvl - __popc(am);
-                    int v = top ? stack_read(top - 1u, s) : 0;
-                    uint32_t m = am & hmask;
-                    while (m) {
-                        const uint32_t a = __ffs(m) - 1;
-                        m &= m - 1;
-                        v += dc_of(dnode[a * 32u + s]);
-                    }
-                    return v;
-                };
-                // ---- E: non-hit pairs (lane = node), one sample at a time
-                uint32_t need_e = __ballot_sync(FULL, live && min_g < BIG && min_g + lbase <= bound);
-                while (need_e) {
-                    const uint32_t s = __ffs(need_e) - 1;
-                    need_e &= need_e - 1;
-                    const uint32_t hm_s = info[kI3Hm + s];
-                    const int sc = h.x + above(level, h.y, hm_s, s);
-                    const int bs = __shfl_sync(FULL, bsc, s);
-                    uint32_t cm = __ballot_sync(FULL, dense_ok && !((hm_s >> lane) & 1u) && sc <= bs);
-                    while (cm) {
-                        const uint32_t j = __ffs(cm) - 1;
-                        cm &= cm - 1;
-                        const int scj = __shfl_sync(FULL, sc, j);
-                        const uint32_t huj = __shfl_sync(FULL, (flags & kFlagHu0) ? 1u : 0u, j);
-                        if (lane == s) merge(scj, huj, blk + j);
-                    }
-                }
-                // ---- F: hit pairs, exact (lane = sample)
-                if ((needs >> lane) & 1u) {
-                    uint32_t hmw = hmv;
-                    while (hmw) {
-                        const uint32_t n = __ffs(hmw) - 1;
-                        hmw &= hmw - 1;
-                        int dcorr, da, dcom;
-                        unpack_delta3(dnode[n * 32u + lane], dcorr, da, dcom);
-                        const uint32_t z = info[kI3Z + n], w = info[kI3W + n];
-                        const uint32_t fl = z & 0x3fffu;
-                        const int g = (int)info[kI3G + n];
-                        int sc;
-                        bool valid;
-                        uint32_t hu;
-                        if (fl & kFlagRoot) {
-                            sc = g + dcorr; valid = true; hu = 0;
-                        } else {
-                            const bool masked = fl & kFlagMasked;
-                            if (masked) { da = 0; dcom = 0; }
-                            sc = g + above(z >> kLevelShift, info[kI3Am + n], hmv, lane) - da;
-                            const int common = (int)(w & 0xffffu) + dcom;
-                            hu = (masked || (int)(w >> 16) > common) ? 1u : 0u;
-                            valid = (fl & kFlagLeaf) ? common > 0 : (!hu || common > 0);
-                        }
-                        if (valid && sc <= bsc) merge(sc, hu, blk + n);
-                    }
+            const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
+            const uint32_t lvl0 = p.tile_lvl[t];
+            uint32_t hc_issue = n0 / kHdrChunk;
+            const uint32_t hc_end = (n1 - 1) / kHdrChunk + 1;
+            if (elect_one()) {
+                for (int i = 0; i < kHdrStages3 && hc_issue + i < hc_end; i++) {
+                    const uint32_t c = hc_issue + i, s = c % kHdrStages3;
+                    mbar_expect_tx(bars_a + 8 * (kBarHdr + s), kHdrChunk * 16);
+                    bulk_g2s(hring_a + s * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
+                             bars_a + 8 * (kBarHdr + s));
                 }
             }
-            __syncwarp();
+            hc_issue = min(hc_issue + kHdrStages3, hc_end);
 
-            // ================= G: stack rows of the open chain (lane = sample) =================
-            uint32_t chain = __ballot_sync(FULL, act && (flags & kFlagOpen));
-            if (chain) {
-                uint32_t lv = __shfl_sync(FULL, level, __ffs(chain) - 1);
-                int v = lv ? stack_read(lv - 1u, lane) : 0;
-                while (chain) {
-                    const uint32_t n = __ffs(chain) - 1;
-                    chain &= chain - 1;
-                    v += dc_of(dnode[n * 32u + lane]);
-                    stack_write(lv, lane, v);
+            // cross-pair bound of this lane's sample, and the tile-local floor of every stack value
+            const int gb = COLLECT ? bsc : (live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff);
+            int gmin = 0;
+
+            // ================= seed: path corrections of levels 0 .. lvl0-1, 32 levels per segment =============
+            for (uint32_t l0 = 0; l0 < lvl0; l0 += 32u) {
+                zero_dnode();
+                __syncwarp();
+                take_segment();
+                const uint32_t cn = min(32u, lvl0 - l0);
+                int v = l0 ? stack_read(l0 - 1u, lane) : 0;
+                for (uint32_t j = 0; j < cn; j++) {
+                    v += dc_of(dnode[j * 32u + lane]);
+                    stack_write(l0 + j, lane, v);
                     gmin = min(gmin, v);
-                    lv++;
                 }
+                __syncwarp();
             }
+
+            for (uint32_t blk = n0; blk < n1; blk += 32u) {
+                // ================= A: headers (lane = node) =================
+                const uint32_t hc = blk / kHdrChunk, hs = hc % kHdrStages3;
+                mbar_wait(bars_a + 8 * (kBarHdr + hs), (hphase >> hs) & 1u);
+                hphase ^= 1u << hs;
+                const uint4 h = hring[hs * kHdrChunk + lane];
+                const bool act = blk + lane < n1;
+                const uint32_t level = h.z >> kLevelShift, flags = h.z & 0x3fffu;
+                const uint32_t nmut = act ? (h.w >> 16) : 0u;
+                const bool dense_ok = act && (flags & kFlagValid0);
+                const int min_g = __reduce_min_sync(FULL, dense_ok ? h.x : BIG);
+                const int min_gn = __reduce_min_sync(FULL, act ? h.x - (int)nmut : BIG);
+                info[kI3G + lane] = (uint32_t)h.x;
+                info[kI3Z + lane] = h.z;
+                info[kI3W + lane] = h.w;
+                info[kI3Am + lane] = h.y;
+                zero_dnode();
+                __syncwarp();
+                if (hc_issue < hc_end) {   // this block's header stage is free again
+                    if (elect_one()) {
+                        const uint32_t c = hc_issue, s2 = c % kHdrStages3;
+                        mbar_expect_tx(bars_a + 8 * (kBarHdr + s2), kHdrChunk * 16);
+                        bulk_g2s(hring_a + s2 * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
+                                 bars_a + 8 * (kBarHdr + s2));
+                    }
+                    hc_issue++;
+                }
+
+                // ================= C: the block's hits from the scanner =================
+                take_segment();
+
+                // ================= bound: can any pair of this block still be optimal? =================
+                const uint32_t hmv = info[kI3Hm + lane];             // lane = sample: its hit nodes
+                const int lbase = gmin + (int)info[kI3Neg + lane];
+                const int bound = min(bsc, gb);
+                const uint32_t needs = __ballot_sync(FULL, live && min_gn + lbase <= bound);
+                if (needs) {
+                    // correction of the path above node (level, am) for sample s
+                    auto above = [&](uint32_t lvl, uint32_t am, uint32_t hmask, uint32_t s) -> int {
+                        const uint32_t top = lvl - __popc(am);
+                        int v = top ? stack_read(top - 1u, s) : 0;
+                        uint32_t m = am & hmask;
+                        while (m) {
+                            const uint32_t a = __ffs(m) - 1;
+                            m &= m - 1;
+                            v += dc_of(dnode[a * 32u + s]);
+                        }
+                        return v;
+                    };
+                    // ---- E: non-hit pairs (lane = node), one sample at a time
+                    uint32_t need_e = __ballot_sync(FULL, live && min_g < BIG && min_g + lbase <= bound);
+                    while (need_e) {
+                        const uint32_t s = __ffs(need_e) - 1;
+                        need_e &= need_e - 1;
+                        const uint32_t hm_s = info[kI3Hm + s];
+                        const int sc = h.x + above(level, h.y, hm_s, s);
+                        const int bs = __shfl_sync(FULL, bsc, s);
+                        uint32_t cm = __ballot_sync(FULL, dense_ok && !((hm_s >> lane) & 1u) && sc <= bs);
+                        while (cm) {
+                            const uint32_t j = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            const int scj = __shfl_sync(FULL, sc, j);
+                            const uint32_t huj = __shfl_sync(FULL, (flags & kFlagHu0) ? 1u : 0u, j);
+                            if (lane == s) merge(scj, huj, blk + j);
+                        }
+                    }
+                    // ---- F: hit pairs, exact (lane = sample)
+                    if ((needs >> lane) & 1u) {
+                        uint32_t hmw = hmv;
+                        while (hmw) {
+                            const uint32_t n = __ffs(hmw) - 1;
+                            hmw &= hmw - 1;
+                            int dcorr, da, dcom;
+                            unpack_delta3(dnode[n * 32u + lane], dcorr, da, dcom);
+                            const uint32_t z = info[kI3Z + n], w = info[kI3W + n];
+                            const uint32_t fl = z & 0x3fffu;
+                            const int g = (int)info[kI3G + n];
+                            int sc;
+                            bool valid;
+                            uint32_t hu;
+                            if (fl & kFlagRoot) {
+                                sc = g + dcorr; valid = true; hu = 0;
+                            } else {
+                                const bool masked = fl & kFlagMasked;
+                                if (masked) { da = 0; dcom = 0; }
+                                sc = g + above(z >> kLevelShift, info[kI3Am + n], hmv, lane) - da;
+                                const int common = (int)(w & 0xffffu) + dcom;
+                                hu = (masked || (int)(w >> 16) > common) ? 1u : 0u;
+                                valid = (fl & kFlagLeaf) ? common > 0 : (!hu || common > 0);
+                            }
+                            if (valid && sc <= bsc) merge(sc, hu, blk + n);
+                        }
+                    }
+                }
+                __syncwarp();
+
+                // ================= G: stack rows of the open chain (lane = sample) =================
+                uint32_t chain = __ballot_sync(FULL, act && (flags & kFlagOpen));
+                if (chain) {
+                    uint32_t lv = __shfl_sync(FULL, level, __ffs(chain) - 1);
+                    int v = lv ? stack_read(lv - 1u, lane) : 0;
+                    while (chain) {
+                        const uint32_t n = __ffs(chain) - 1;
+                        chain &= chain - 1;
+                        v += dc_of(dnode[n * 32u + lane]);
+                        stack_write(lv, lane, v);
+                        gmin = min(gmin, v);
+                        lv++;
+                    }
+                }
+                __syncwarp();
+            }
+            // publish an improved bound for the other pairs working on this sample group
+            if (!COLLECT && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
             __syncwarp();
         }
-        // publish an improved bound for the other warps working on this sample group
-        if (!COLLECT && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
-        __syncwarp();
+
+        if (!COLLECT) {
+            // park the pair's result in its own rows for the fold below
+            reinterpret_cast<unsigned long long*>(dnode)[lane] = bkey;
+            info[lane] = cnt;
+        }
     }
 
     if (COLLECT) return;
-    // fold the CTA's warps in shared memory (the rings are dead now), one partial row per CTA
-    __syncthreads();
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
-    uint32_t* scnt = reinterpret_cast<uint32_t*>(smem + kWarps3 * 32 * 8);
-    skey[warp * 32 + lane] = bkey;
-    scnt[warp * 32 + lane] = cnt;
+    // fold the CTA's pairs, one partial row per CTA
     __syncthreads();
     if (warp == 0) {
         unsigned long long best = ~0ull;
-        for (int w = 0; w < kWarps3; w++) best = min(best, skey[w * 32 + lane]);
+        for (int w = 0; w < kPairs3; w++) {
+            const uint8_t* pb = smem + bm_bytes + kLut3Bytes + w * kWarpSmem3;
+            best = min(best, reinterpret_cast<const unsigned long long*>(pb + kO3Dnode)[lane]);
+        }
         uint32_t c = 0;
-        for (int w = 0; w < kWarps3; w++)
-            if ((skey[w * 32 + lane] >> 33) == (best >> 33)) c += scnt[w * 32 + lane];
+        for (int w = 0; w < kPairs3; w++) {
+            const uint8_t* pb = smem + bm_bytes + kLut3Bytes + w * kWarpSmem3;
+            if ((reinterpret_cast<const unsigned long long*>(pb + kO3Dnode)[lane] >> 33) == (best >> 33))
+                c += reinterpret_cast<const uint32_t*>(pb + kO3Info)[lane];
+        }
         const size_t o = ((size_t)group * ctas_per_group + cta_in_group) * 32u + lane;
         p.part_key[o] = best;
         p.part_cnt[o] = c;

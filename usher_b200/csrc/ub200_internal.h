@@ -96,6 +96,7 @@ struct Derived {
     std::vector<uint32_t> tile3_lvl;  // [T3]   level of the tile's first node = number of seeded levels
     std::vector<uint32_t> tile3_sseg; // [T3+1] offsets into seed_end
     std::vector<uint32_t> seed_end;   // end of each seed segment, in 4-word units
+    std::vector<uint32_t> blk_words;  // [blocks] stream words of each block segment (row lengths, rounded up to 4)
     uint64_t seed_words = 0;          // stream words spent on seed segments
 };
 

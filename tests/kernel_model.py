@@ -98,7 +98,7 @@ def place3(d, s_ptr, calls):
             out = {}
             for k in range(o0, o1):
                 w = int(stream[k])
-                e = tab.get(((w >> 14) << 5) | (w & 31))
+                e = tab.get(((w >> (16 if d["narrow3"] else 14)) << 5) | (w & 31))
                 if e is None:
                     continue
                 e, refc = e

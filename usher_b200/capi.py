@@ -46,7 +46,8 @@ class DerivedView(C.Structure):
                 ("n_tiles", C.c_uint32), ("n_mutations", C.c_uint64)] + [
         (k, C.c_void_p) for k in ("level", "tie_index", "num_leaves", "tiekey", "key_to_node", "row32", "mutw",
                                   "hdr", "ref_of", "tile_start", "anc_ptr", "anc")] + [
-        ("n_tiles3", C.c_uint32), ("n_seed_segs", C.c_uint32), ("stream_words", C.c_uint64)] + [
+        ("n_tiles3", C.c_uint32), ("n_seed_segs", C.c_uint32), ("narrow3", C.c_uint32), ("reserved3", C.c_uint32),
+        ("stream_words", C.c_uint64)] + [
         (k, C.c_void_p) for k in ("stream", "hdr3", "tile3_start", "tile3_w0", "tile3_lvl", "tile3_sseg", "seed_end", "blk_words")]
 
 
@@ -171,6 +172,7 @@ def debug_derive(parent, row_ptr, muts, tie_index=None, target_tiles=64, min_til
     T3 = v.n_tiles3
     if T3:   # k_score3 layout
         out.update({
+            "narrow3": int(v.narrow3),
             "stream": _view(v.stream, np.uint32, int(v.stream_words)).copy(),
             "hdr3": _view(v.hdr3, HDR_DTYPE, n).copy(),
             "tile3_start": _view(v.tile3_start, np.uint32, T3 + 1).copy(),

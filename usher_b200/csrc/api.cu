@@ -225,8 +225,13 @@ int launch_score3(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngro
         return 0;
     };
     int rc;
-    if (smem_bitmap) rc = collect ? go(k_score3<true, true>) : go(k_score3<true, false>);
-    else rc = collect ? go(k_score3<false, true>) : go(k_score3<false, false>);
+    if (M->d.narrow3) {
+        if (smem_bitmap) rc = collect ? go(k_score3<true, true, true>) : go(k_score3<true, false, true>);
+        else rc = collect ? go(k_score3<false, true, true>) : go(k_score3<false, false, true>);
+    } else {
+        if (smem_bitmap) rc = collect ? go(k_score3<true, true, false>) : go(k_score3<true, false, false>);
+        else rc = collect ? go(k_score3<false, true, false>) : go(k_score3<false, false, false>);
+    }
     if (rc) return rc;
     CU(cudaGetLastError());
     return 0;
@@ -301,7 +306,8 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     const uint32_t total_warps = std::max<uint32_t>(M->grid * ub200::kWarpsPerCta, warps3);
     std::string err;
     const char* mt = getenv("UB200_MIN_TILE");   // test hook: cut small trees into many tiles
-    int rc = ub200::derive(*flat, total_warps * 8u, M->d, err, mt ? (uint32_t)atoi(mt) : 0u);
+    const char* tw = getenv("UB200_TILES_PER_WORKER");
+    int rc = ub200::derive(*flat, total_warps * (tw ? (uint32_t)atoi(tw) : 8u), M->d, err, mt ? (uint32_t)atoi(mt) : 0u);
     if (rc != UB200_OK) { delete M; return fail(rc, err); }
     auto& d = M->d;
     M->n = d.n; M->m = d.m; M->L = d.L; M->n_tiles = (uint32_t)d.tile_start.size() - 1;

@@ -14,6 +14,7 @@
 //   * num_leaves (mutation_annotated_tree.cpp:866-879), BFS index (:1225-1251), level.
 // The kernel then only has to correct these for the few mutations that hit a position the sample calls.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -26,6 +27,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     const uint32_t n = d.n;
     d.have3 = d.L <= kMaxPos3;
     if (!d.have3) return;
+    d.narrow3 = d.L <= kMaxPos3Narrow && !getenv("UB200_WIDE_WORDS");   // env: test hook for the wide form
     const uint32_t nblk = (n + 31) / 32;
     // subtree ends (DFS pre-order: subtree of i = [i, send[i])), words on the root path above each node
     std::vector<uint32_t> send(n);
@@ -54,7 +56,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     const uint64_t node_cost = 4;
     const uint64_t total = d.m + node_cost * n;
     uint64_t per = total / (target_tiles ? target_tiles : 1);
-    per = std::min<uint64_t>(std::max<uint64_t>(per, min_tile_cost ? min_tile_cost : 6144), 1u << 16);
+    per = std::min<uint64_t>(std::max<uint64_t>(per, min_tile_cost ? min_tile_cost : 4096), 1u << 16);
     for (;;) {
         d.tile3_start.assign(1, 0);
         uint64_t acc = 0, seed = 0;
@@ -79,8 +81,9 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     d.blk_words.assign(nblk, 0);
     d.stream.clear();
     d.stream.reserve(d.m + d.m / 6 + 4 * kChunk3);
-    const uint32_t pad = pack_mut3(d.L, 0, 0, 0);
-    auto conv = [&](uint32_t w, uint32_t lane) { return pack_mut3(w >> 6, lane, (w >> 2) & 3u, w & 3u); };
+    const bool nw = d.narrow3;
+    const uint32_t pad = pack_mut3(nw, d.L, 0, 0, 0);
+    auto conv = [&](uint32_t w, uint32_t lane) { return pack_mut3(nw, w >> 6, lane, (w >> 2) & 3u, w & 3u); };
     auto align_to = [&](size_t a) { while (d.stream.size() % a) d.stream.push_back(pad); };
     std::vector<uint32_t> chain;
     d.seed_words = 0;
@@ -332,7 +335,7 @@ struct ub200_derived_view {
     const uint32_t* key_to_node; const uint32_t* row32; const uint32_t* mutw; const void* hdr;
     const uint8_t* ref_of; const uint32_t* tile_start; const uint32_t* anc_ptr; const uint32_t* anc;
     // k_score3 layout
-    uint32_t n_tiles3, n_seed_segs;
+    uint32_t n_tiles3, n_seed_segs, narrow3, reserved3;
     uint64_t stream_words;
     const uint32_t* stream; const void* hdr3; const uint32_t* tile3_start; const uint32_t* tile3_w0;
     const uint32_t* tile3_lvl; const uint32_t* tile3_sseg; const uint32_t* seed_end; const uint32_t* blk_words;
@@ -356,6 +359,7 @@ int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32
     view->tile_start = d->tile_start.data(); view->anc_ptr = d->anc_ptr.data(); view->anc = d->anc.data();
     view->n_tiles3 = d->have3 ? (uint32_t)d->tile3_start.size() - 1 : 0;
     view->n_seed_segs = (uint32_t)d->seed_end.size();
+    view->narrow3 = d->narrow3 ? 1u : 0u; view->reserved3 = 0;
     view->stream_words = d->stream.size();
     view->stream = d->stream.data(); view->hdr3 = d->hdr3.data(); view->tile3_start = d->tile3_start.data();
     view->tile3_w0 = d->tile3_w0.data(); view->tile3_lvl = d->tile3_lvl.data();

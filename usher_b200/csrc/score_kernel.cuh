@@ -95,6 +95,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 24)) __trap();
     }
 }
+// same, for waits on another warp (not on a copy in flight): the hardware may keep the warp suspended longer
+// between polls, so that a waiting warp does not eat issue slots
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+// L2 prefetch of a contiguous global range (no shared memory, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA unit, no tensor map)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

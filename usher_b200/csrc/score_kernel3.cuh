@@ -89,6 +89,9 @@ __device__ __forceinline__ uint32_t lds32_3(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void sts32_3(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint4 lds128_3(uint32_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -113,9 +116,15 @@ __device__ __forceinline__ int lut_delta3(uint32_t i) {
     const int dcom = tk - t0;
     return dcorr * (1 << 20) + da * (1 << 10) + dcom;
 }
-template <bool SMEM_BITMAP>
-__device__ __forceinline__ uint32_t bitmap_word(const uint32_t* bm_s, const uint32_t* bm_g, uint32_t i) {
-    return SMEM_BITMAP ? bm_s[i] : __ldg(bm_g + i);
+// bitmap word of a stream word's position: narrow words carry the byte offset at bit 14
+template <bool SMEM_BITMAP, bool NARROW>
+__device__ __forceinline__ uint32_t bitmap_word(const uint32_t* bm_s, const uint32_t* bm_g, uint32_t w) {
+    if (NARROW) {
+        const uint32_t off = w >> 14;
+        return SMEM_BITMAP ? *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bm_s) + off)
+                           : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bm_g) + off));
+    }
+    return SMEM_BITMAP ? bm_s[w >> 14] : __ldg(bm_g + (w >> 14));
 }
 __device__ __forceinline__ int dc_of(int v) { return (v + (1 << 19)) >> 20; }
 __device__ __forceinline__ void unpack_delta3(int v, int& dcorr, int& da, int& dcom) {
@@ -127,7 +136,7 @@ __device__ __forceinline__ void unpack_delta3(int v, int& dcorr, int& da, int& d
 
 // COLLECT = false: best placement per sample.  COLLECT = true: second pass that lists every optimal node of each
 // sample (best_j_vec + node_has_unique); the final best score is the bound, so almost every block is pruned.
-template <bool SMEM_BITMAP, bool COLLECT>
+template <bool SMEM_BITMAP, bool COLLECT, bool NARROW>
 __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -154,6 +163,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     uint32_t* info = reinterpret_cast<uint32_t*>(wbase + kO3Info);
     volatile uint2* msg = reinterpret_cast<volatile uint2*>(wbase + kO3Msg);
     const uint32_t mring_a = smem_u32(mring), hring_a = smem_u32(hring), bars_a = smem_u32(wbase + kO3Bars);
+    const uint32_t list_a = smem_u32(list);
 
     const uint32_t* bm_g = p.bitmap + (size_t)ggroup * p.bitmap_words;
     if (SMEM_BITMAP) {
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
         uint32_t fill = 0;        // hit words in the open message
         auto open_msg = [&]() {   // wait until the consumer has released the slot
             const uint32_t s = nmsg % kSlots3;
-            mbar_wait(bars_a + 8 * (kBarEmpty + s), ((nmsg / kSlots3) & 1u) ^ 1u);
+            mbar_wait_long(bars_a + 8 * (kBarEmpty + s), ((nmsg / kSlots3) & 1u) ^ 1u);
             fill = 0;
         };
         auto send_msg = [&](uint32_t flags, uint32_t payload) {
@@ -224,10 +234,10 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 for (uint32_t k = 0; k < 4; k++) {
                     if (k < nq) {
                         const uint4 q = lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2));
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.x >> 14), 0u, q.x), 1u);
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.y >> 14), 0u, q.y), 1u);
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.z >> 14), 0u, q.z), 1u);
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP>(bm_s, bm_g, q.w >> 14), 0u, q.w), 1u);
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.x), 0u, q.x), 1u);
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.y), 0u, q.y), 1u);
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.z), 0u, q.z), 1u);
+                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.w), 0u, q.w), 1u);
                     } else {
                         acc >>= 4;
                     }
@@ -247,9 +257,27 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                     if (lane >= (uint32_t)dlt) incl += v;
                 }
                 uint32_t remaining = __shfl_sync(FULL, incl, 31);
+                if (remaining <= kSlotCap3 - fill) {
+                    // common case: all of the step's hits fit the open message
+                    uint32_t pa = list_a + (((nmsg % kSlots3) * kSlotCap3 + fill + incl - c) << 2);
+                    while (hb) {
+                        uint32_t bit;
+                        asm("bfind.u32 %0, %1;" : "=r"(bit) : "r"(hb));   // highest set bit (FLO)
+                        hb ^= 1u << bit;
+                        const uint32_t wi = idx + ((bit & 12u) << 5) + (bit & 3u);
+                        sts32_3(pa, lds32_3(mring_a + ((wi & (kRingWords3 - 1u)) << 2)));
+                        pa += 4u;
+                    }
+                    fill += remaining;
+                    continue;
+                }
                 uint32_t mine = incl - c;       // index of this lane's next hit among the step's hits
                 uint32_t done = 0;              // hits of this step already placed in messages
                 while (remaining) {
+                    if (fill == kSlotCap3) {
+                        send_msg(0u, 0u);
+                        open_msg();
+                    }
                     const uint32_t take = min(kSlotCap3 - fill, remaining);
                     const uint32_t slot_a = (nmsg % kSlots3) * kSlotCap3 + fill;
                     while (hb && mine < done + take) {
@@ -262,10 +290,6 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                     fill += take;
                     remaining -= take;
                     done += take;
-                    if (fill == kSlotCap3) {
-                        send_msg(0u, 0u);
-                        open_msg();
-                    }
                 }
             }
         };
@@ -355,7 +379,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             for (uint32_t k0 = 0; k0 < n; k0 += 32u) {
                 if (k0 + lane < n) {
                     const uint32_t w = list[slot * kSlotCap3 + k0 + lane];
-                    const uint32_t* row = tabg + (size_t)mut3_pos(w) * 8u;
+                    const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w) * 8u;
                     const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row));
                     const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
                     const uint32_t nl = (w >> 9) & 31u;
@@ -380,7 +404,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
         auto take_segment = [&]() {
             for (;;) {
                 const uint32_t s = nmsg % kSlots3;
-                mbar_wait(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
+                mbar_wait_long(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
                 const uint32_t m = msg[s].x;
                 process(s, m & 0xffffu);
                 __syncwarp();
@@ -396,7 +420,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             uint32_t t;
             {
                 const uint32_t s = nmsg % kSlots3;
-                mbar_wait(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
+                mbar_wait_long(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
                 const uint32_t m = msg[s].x;
                 t = msg[s].y;
                 __syncwarp();

@@ -54,16 +54,18 @@ constexpr uint32_t kMutChunk = 256;   // mutation words per bulk copy (1 KB)
 constexpr uint32_t kHdrChunk = 32;    // headers per bulk copy (512 B)
 
 // ---- k_score3 layout (score_kernel3.cuh, DESIGN.md "Data layout") ----
-// stream word: pos>>5 :18 | lane:5 | prev:2 | mut:2 | pos&31 :5   (lane = node & 31 in a block segment,
-// level & 31 in a seed segment; the reference allele comes from the sample table row).  The split position
-// gives the bitmap word index with one shift and the bit index with none (funnel shifts wrap at 32).
-// Pad words carry pos = L (never called).
-constexpr uint32_t kPosBits3 = 23;
-constexpr uint32_t kMaxPos3 = (1u << kPosBits3) - 2;
-UB200_HD inline uint32_t pack_mut3(uint32_t pos, uint32_t lane, uint32_t prevc, uint32_t mutc) {
-    return ((pos >> 5) << 14) | (lane << 9) | (prevc << 7) | (mutc << 5) | (pos & 31u);
+// stream word, wide form  : pos>>5 :18 | lane:5 | prev:2 | mut:2 | pos&31 :5
+//              narrow form: pos>>5 :16 | 00 | lane:5 | prev:2 | mut:2 | pos&31 :5      (genomes < 2^21 positions)
+// lane = node & 31 in a block segment, level & 31 in a seed segment; the reference allele comes from the sample
+// table row.  The split position gives the bit index for free (funnel shifts wrap at 32) and, in the narrow
+// form, the byte offset of the bitmap word with one shift (w >> 14).  Pad words carry pos = L (never called).
+constexpr uint32_t kMaxPos3 = (1u << 23) - 2;
+constexpr uint32_t kMaxPos3Narrow = (1u << 21) - 2;
+UB200_HD inline uint32_t pack_mut3(bool narrow, uint32_t pos, uint32_t lane, uint32_t prevc, uint32_t mutc) {
+    return ((pos >> 5) << (narrow ? 16 : 14)) | (lane << 9) | (prevc << 7) | (mutc << 5) | (pos & 31u);
 }
-UB200_HD inline uint32_t mut3_pos(uint32_t w) { return ((w >> 14) << 5) | (w & 31u); }
+template <bool NARROW>
+UB200_HD inline uint32_t mut3_pos(uint32_t w) { return ((w >> (NARROW ? 16 : 14)) << 5) | (w & 31u); }
 // header of the k_score3 layout: x = G, y = bitmask of the node's ancestors inside its own aligned 32-node
 // block, z = level:18 | flags:14, w = nmut<<16 | c0
 constexpr uint32_t kFlagOpen = 32u;    // internal node with a descendant beyond its 32-node block
@@ -89,6 +91,7 @@ struct Derived {
     // a seed segment holds the rows of up to 32 consecutive levels of the root path of the tile's first node,
     // a block segment the rows of one aligned 32-node block; every segment starts on a 4-word boundary.
     bool have3 = false;               // false: genome too long for the 23-bit position field
+    bool narrow3 = false;             // stream words in the narrow form
     std::vector<uint32_t> stream;     // padded to kChunk3
     std::vector<NodeHdr> hdr3;        // padded like hdr
     std::vector<uint32_t> tile3_start;// [T3+1] first node of each tile (multiple of 32)

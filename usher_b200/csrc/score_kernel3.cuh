@@ -12,7 +12,7 @@
 //                  to the consumer through full/empty mbarriers; a segment is one or more messages, the last
 //                  one flagged.  The scanner needs no sample state, only the bitmap.
 //   consumer warp  owns the sample state.  Per block:
-//     A  lane = node     header decode (headers arrive through its own bulk-copy ring, 512 B = one block)
+//     A  lane = node     header decode (one coalesced 512 B load per block, fetched a block ahead)
 //     C  lane = hit      hit word -> node lane (stored in the word), table row of the position (32 B, L2) ->
 //                        for every sample calling the position: packed (dcorr, da, dcommon) from a 1024-entry
 //                        LUT, shared-memory atomics into dnode[node][sample], hm[sample] |= node,
@@ -37,21 +37,19 @@ constexpr int kPairs3 = 16;
 constexpr int kThreads3 = kPairs3 * 64;
 constexpr int kMutStages3 = 4;
 constexpr uint32_t kRingWords3 = kChunk3 * kMutStages3;   // 1024 words = 4 KB
-constexpr int kHdrStages3 = 2;
-constexpr uint32_t kSlots3 = 4, kSlotCap3 = 64;            // scanner -> consumer messages
-constexpr int kStack3 = 40;                                // levels kept in shared memory (deeper: HBM spill)
+constexpr uint32_t kSlots3 = 8, kSlotCap3 = 64;            // scanner -> consumer messages
+constexpr int kStack3 = 32;                                // levels kept in shared memory (deeper: HBM spill)
 // per-pair shared memory (bytes)
 constexpr uint32_t kO3Mring = 0;                           // u32[1024]            scanner
-constexpr uint32_t kO3Hring = 4096;                        // uint4[64]            consumer
-constexpr uint32_t kO3Dnode = 5120;                        // i32[32][32] packed deltas
-constexpr uint32_t kO3Stack = 9216;                        // i16[40][32]
-constexpr uint32_t kO3List = kO3Stack + kStack3 * 64;      // u32[4][64] hit words
+constexpr uint32_t kO3Dnode = 4096;                        // i32[32][32] packed deltas   consumer
+constexpr uint32_t kO3Stack = 8192;                        // i16[32][32]
+constexpr uint32_t kO3List = kO3Stack + kStack3 * 64;      // u32[8][64] hit words
 constexpr uint32_t kO3Info = kO3List + kSlots3 * kSlotCap3 * 4;   // u32[6][32]: G, z, w, am, hm, neg
-constexpr uint32_t kO3Msg = kO3Info + 6 * 128;             // uint2[4]: (count | flags << 16, payload)
-constexpr uint32_t kO3Bars = kO3Msg + kSlots3 * 8;         // mbarriers: 4 ring, 2 header, 4 full, 4 empty
-constexpr uint32_t kWarpSmem3 = (kO3Bars + 14 * 8 + 127) & ~127u;
+constexpr uint32_t kO3Msg = kO3Info + 6 * 128;             // uint2[8]: (count | flags << 16, payload)
+constexpr uint32_t kO3Bars = kO3Msg + kSlots3 * 8;         // mbarriers: 4 ring, 8 full, 8 empty
+constexpr uint32_t kWarpSmem3 = (kO3Bars + (kMutStages3 + 2 * kSlots3) * 8 + 127) & ~127u;
 constexpr uint32_t kI3G = 0, kI3Z = 32, kI3W = 64, kI3Am = 96, kI3Hm = 128, kI3Neg = 160;
-constexpr uint32_t kBarHdr = kMutStages3, kBarFull = kMutStages3 + kHdrStages3, kBarEmpty = kBarFull + kSlots3;
+constexpr uint32_t kBarFull = kMutStages3, kBarEmpty = kBarFull + kSlots3;
 constexpr uint32_t kMsgLast = 1u << 16, kMsgTile = 2u << 16, kMsgEnd = 4u << 16;
 constexpr uint32_t kLut3Bytes = 4096;
 constexpr uint32_t kMaxRowV3 = 500;      // packed 10-bit delta fields
@@ -148,6 +146,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     const uint32_t ctas_per_group = gridDim.x / p.ngroups;
     const uint32_t ggroup = p.group0 + group;
     const uint32_t FULL = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     constexpr int BIG = 0x3fffffff;
 
     // ---- shared memory: [bitmap][lut][pair 0 .. pair 15]
@@ -156,13 +155,12 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
     int* lut = reinterpret_cast<int*>(smem + bm_bytes);
     uint8_t* wbase = smem + bm_bytes + kLut3Bytes + pair * kWarpSmem3;
     uint32_t* mring = reinterpret_cast<uint32_t*>(wbase + kO3Mring);
-    uint4* hring = reinterpret_cast<uint4*>(wbase + kO3Hring);
     int* dnode = reinterpret_cast<int*>(wbase + kO3Dnode);
     int16_t* stk = reinterpret_cast<int16_t*>(wbase + kO3Stack);
     uint32_t* list = reinterpret_cast<uint32_t*>(wbase + kO3List);
     uint32_t* info = reinterpret_cast<uint32_t*>(wbase + kO3Info);
     volatile uint2* msg = reinterpret_cast<volatile uint2*>(wbase + kO3Msg);
-    const uint32_t mring_a = smem_u32(mring), hring_a = smem_u32(hring), bars_a = smem_u32(wbase + kO3Bars);
+    const uint32_t mring_a = smem_u32(mring), bars_a = smem_u32(wbase + kO3Bars);
     const uint32_t list_a = smem_u32(list);
 
     const uint32_t* bm_g = p.bitmap + (size_t)ggroup * p.bitmap_words;
@@ -248,18 +246,27 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                     const uint32_t nv = dwords > 0 ? min((uint32_t)(dwords + 127) >> 7, 4u) : 0u;
                     hb &= (1u << (4u * nv)) - 1u;
                 }
-                // compact: lane l's hits follow those of lanes < l
+                // compact: lane l's hits follow those of lanes < l.  Exclusive prefix of the per-lane counts:
+                // two ballots when no lane has more than 3 hits (the usual case), else a shuffle scan
                 const uint32_t c = __popc(hb);
-                uint32_t incl = c;
+                uint32_t excl, remaining;
+                if (__ballot_sync(FULL, c > 3u) == 0u) {
+                    const uint32_t v0 = __ballot_sync(FULL, c & 1u), v1 = __ballot_sync(FULL, c & 2u);
+                    excl = __popc(v0 & lt_mask) + 2u * __popc(v1 & lt_mask);
+                    remaining = __popc(v0) + 2u * __popc(v1);
+                } else {
+                    uint32_t incl = c;
 #pragma unroll
-                for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                    const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
-                    if (lane >= (uint32_t)dlt) incl += v;
+                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                        const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
+                        if (lane >= (uint32_t)dlt) incl += v;
+                    }
+                    remaining = __shfl_sync(FULL, incl, 31);
+                    excl = incl - c;
                 }
-                uint32_t remaining = __shfl_sync(FULL, incl, 31);
                 if (remaining <= kSlotCap3 - fill) {
                     // common case: all of the step's hits fit the open message
-                    uint32_t pa = list_a + (((nmsg % kSlots3) * kSlotCap3 + fill + incl - c) << 2);
+                    uint32_t pa = list_a + (((nmsg % kSlots3) * kSlotCap3 + fill + excl) << 2);
                     while (hb) {
                         uint32_t bit;
                         asm("bfind.u32 %0, %1;" : "=r"(bit) : "r"(hb));   // highest set bit (FLO)
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                     fill += remaining;
                     continue;
                 }
-                uint32_t mine = incl - c;       // index of this lane's next hit among the step's hits
+                uint32_t mine = excl;           // index of this lane's next hit among the step's hits
                 uint32_t done = 0;              // hits of this step already placed in messages
                 while (remaining) {
                     if (fill == kSlotCap3) {
@@ -374,30 +381,44 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             info[kI3Hm + lane] = 0;
             info[kI3Neg + lane] = 0;
         };
-        // C: the hit words of one message (lane = hit)
-        auto process = [&](uint32_t slot, uint32_t n) {
-            for (uint32_t k0 = 0; k0 < n; k0 += 32u) {
-                if (k0 + lane < n) {
-                    const uint32_t w = list[slot * kSlotCap3 + k0 + lane];
-                    const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w) * 8u;
-                    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row));
-                    const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
-                    const uint32_t nl = (w >> 9) & 31u;
-                    const uint32_t lo = r0.y | ((w >> 5) & 15u);
-                    uint32_t pm = r0.x;
-                    while (pm) {
-                        const uint32_t s = __ffs(pm) - 1;
-                        pm &= pm - 1;
-                        const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
-                        const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
-                        const int d = lut[(e4 << 6) | lo];
-                        atomicAdd(&dnode[nl * 32u + s], d);
-                        atomicOr(&info[kI3Hm + s], 1u << nl);
-                        const int dc = dc_of(d);
-                        if (dc < 0) atomicAdd(reinterpret_cast<int*>(&info[kI3Neg + s]), dc);
-                    }
-                }
+        // C: the hit words of one message (lane = hit, two hits per lane so that all table rows are in flight
+        // together)
+        auto apply_hit = [&](uint32_t w, const uint4& r0, const uint2& r1) {
+            const uint32_t nl = (w >> 9) & 31u;
+            const uint32_t lo = r0.y | ((w >> 5) & 15u);
+            uint32_t pm = r0.x;
+            while (pm) {
+                const uint32_t s = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
+                const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
+                const int d = lut[(e4 << 6) | lo];
+                atomicAdd(&dnode[nl * 32u + s], d);
+                atomicOr(&info[kI3Hm + s], 1u << nl);
+                const int dc = dc_of(d);
+                if (dc < 0) atomicAdd(reinterpret_cast<int*>(&info[kI3Neg + s]), dc);
             }
+        };
+        auto process = [&](uint32_t slot, uint32_t n) {
+            static_assert(kSlotCap3 == 64, "two hits per lane");
+            const bool h0 = lane < n, h1 = lane + 32u < n;
+            uint32_t w0 = 0, w1 = 0;
+            uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0;
+            uint2 a1 = make_uint2(0, 0), b1 = a1;
+            if (h0) {
+                w0 = list[slot * kSlotCap3 + lane];
+                const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w0) * 8u;
+                a0 = __ldg(reinterpret_cast<const uint4*>(row));
+                a1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+            }
+            if (h1) {
+                w1 = list[slot * kSlotCap3 + 32u + lane];
+                const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w1) * 8u;
+                b0 = __ldg(reinterpret_cast<const uint4*>(row));
+                b1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+            }
+            if (h0) apply_hit(w0, a0, a1);
+            if (h1) apply_hit(w1, b0, b1);
         };
         uint32_t nmsg = 0;
         // receive the messages of one segment and fold their hits into dnode / hm / neg
@@ -415,7 +436,6 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             __syncwarp();
         };
 
-        uint32_t hphase = 0;
         for (;;) {
             uint32_t t;
             {
@@ -430,17 +450,8 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             }
             const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
             const uint32_t lvl0 = p.tile_lvl[t];
-            uint32_t hc_issue = n0 / kHdrChunk;
-            const uint32_t hc_end = (n1 - 1) / kHdrChunk + 1;
-            if (elect_one()) {
-                for (int i = 0; i < kHdrStages3 && hc_issue + i < hc_end; i++) {
-                    const uint32_t c = hc_issue + i, s = c % kHdrStages3;
-                    mbar_expect_tx(bars_a + 8 * (kBarHdr + s), kHdrChunk * 16);
-                    bulk_g2s(hring_a + s * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
-                             bars_a + 8 * (kBarHdr + s));
-                }
-            }
-            hc_issue = min(hc_issue + kHdrStages3, hc_end);
+            // headers: one coalesced 512 B load per block, fetched one block ahead into registers
+            uint4 hnext = __ldg(reinterpret_cast<const uint4*>(p.hdr) + n0 + lane);
 
             // cross-pair bound of this lane's sample, and the tile-local floor of every stack value
             const int gb = COLLECT ? bsc : (live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff);
@@ -463,10 +474,8 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
 
             for (uint32_t blk = n0; blk < n1; blk += 32u) {
                 // ================= A: headers (lane = node) =================
-                const uint32_t hc = blk / kHdrChunk, hs = hc % kHdrStages3;
-                mbar_wait(bars_a + 8 * (kBarHdr + hs), (hphase >> hs) & 1u);
-                hphase ^= 1u << hs;
-                const uint4 h = hring[hs * kHdrChunk + lane];
+                const uint4 h = hnext;
+                if (blk + 32u < n1) hnext = __ldg(reinterpret_cast<const uint4*>(p.hdr) + blk + 32u + lane);
                 const bool act = blk + lane < n1;
                 const uint32_t level = h.z >> kLevelShift, flags = h.z & 0x3fffu;
                 const uint32_t nmut = act ? (h.w >> 16) : 0u;
@@ -479,15 +488,6 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 info[kI3Am + lane] = h.y;
                 zero_dnode();
                 __syncwarp();
-                if (hc_issue < hc_end) {   // this block's header stage is free again
-                    if (elect_one()) {
-                        const uint32_t c = hc_issue, s2 = c % kHdrStages3;
-                        mbar_expect_tx(bars_a + 8 * (kBarHdr + s2), kHdrChunk * 16);
-                        bulk_g2s(hring_a + s2 * kHdrChunk * 16, p.hdr + (size_t)c * kHdrChunk, kHdrChunk * 16,
-                                 bars_a + 8 * (kBarHdr + s2));
-                    }
-                    hc_issue++;
-                }
 
                 // ================= C: the block's hits from the scanner =================
                 take_segment();

@@ -120,6 +120,26 @@ def test_config2_shape_vs_reference_and_batch_invariance():
     s.close()
 
 
+@pytest.mark.parametrize("seed,shape,fam", [(1, capi.Synth.UNIFORM, capi.Synth.SNV40), (2, capi.Synth.SC2, capi.Synth.LEAF),
+                                            (3, capi.Synth.UNIFORM, capi.Synth.AMBIG), (4, capi.Synth.SC2, capi.Synth.SNV40)])
+def test_optimal_sets_vs_port_many_tiles(seed, shape, fam, monkeypatch):
+    """The second (collect) pass runs with the final best as its bound from the first block on, so any block whose
+    exact lower bound is wrong loses optimal nodes: whole optimal sets against the port on trees cut into many
+    tiles, shallow and deep optima, all three sample families."""
+    monkeypatch.setenv("UB200_MIN_TILE", "512")
+    s = capi.Synth(40_000, [6.0, 2.0, 12.0, 1.2][seed - 1], 4000, shape, 777 + seed)
+    p, r, mu = s.arrays()
+    sp, sc, _ = s.samples(160, fam, 31 + seed)
+    m = capi.Mat.from_flat_struct(s.flat)
+    assert m.info.n_tiles > 50
+    got = common.placements_to_dict(m.place_batch(sp, sc, best_set=True))
+    pt = port.PortTree(p, r, mu)
+    q = pt.search(sp, sc)
+    for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
+        assert np.array_equal(np.asarray(got[k]).astype(np.int64), q[k].astype(np.int64)), (seed, k)
+    pt.close(); m.close(); s.close()
+
+
 def test_resident_api_matches_batch_api_and_times():
     g = common.load(common.GOLDEN + "/random_15.npz")
     m = capi.Mat(g["parent"], g["row_ptr"], g["muts"])

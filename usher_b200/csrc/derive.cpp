@@ -59,11 +59,15 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     per = std::min<uint64_t>(std::max<uint64_t>(per, min_tile_cost ? min_tile_cost : 4096), 1u << 16);
     for (;;) {
         d.tile3_start.assign(1, 0);
-        uint64_t acc = 0, seed = 0;
+        uint64_t acc = 0, seed = 0, seen = 0;
         for (uint32_t b = 0; b < nblk; b++) {
             const uint32_t e = std::min(n, b * 32 + 32);
-            acc += (d.row32[e] - d.row32[b * 32]) + node_cost * (e - b * 32);
-            if (acc >= per && e < n) {
+            const uint64_t cost = (d.row32[e] - d.row32[b * 32]) + node_cost * (e - b * 32);
+            acc += cost;
+            seen += cost;
+            // the last tiles handed out are smaller, so that the workers finish closer together
+            const uint64_t lim = seen * 10 > total * 9 ? per / 4 : (seen * 10 > total * 7 ? per / 2 : per);
+            if (acc >= std::max<uint64_t>(lim, min_tile_cost ? min_tile_cost : 2048) && e < n) {
                 d.tile3_start.push_back(e);
                 seed += pathw[e];
                 acc = 0;

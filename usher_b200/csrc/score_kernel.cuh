@@ -114,6 +114,14 @@ __device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();
     }
 }
+// waits of a warp that has slack (the consumer on its scanner): back off between polls
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(200);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
 // L2 prefetch of a contiguous global range (no shared memory, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");

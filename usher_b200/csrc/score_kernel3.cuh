@@ -301,43 +301,55 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             }
         };
 
-        for (;;) {
-            // tiles are handed out in DFS order by a per-group counter: balances uneven tiles, and the CTAs of
-            // different groups still walk the tree in the same order (one HBM read, the rest from L2)
+        // tiles are handed out in DFS order by a per-group counter: balances uneven tiles, and the CTAs of
+        // different groups still walk the tree in the same order (one HBM read, the rest from L2).  The next
+        // tile and its metadata are fetched while the last blocks of the current one are scanned.
+        struct TileMeta { uint32_t t, n0, n1, lvl0, sseg, w0, w1; };
+        auto fetch_tile = [&]() -> TileMeta {
+            TileMeta m;
             uint32_t t = 0;
             if (lane == 0) t = atomicAdd(p.tile_counter + group, 1u);
-            t = __shfl_sync(FULL, t, 0);
+            m.t = __shfl_sync(FULL, t, 0);
+            const uint32_t tt = min(m.t, p.n_tiles - 1u);
+            m.n0 = p.tile_start[tt]; m.n1 = p.tile_start[tt + 1];
+            m.lvl0 = p.tile_lvl[tt]; m.sseg = p.tile_sseg[tt];
+            m.w0 = p.tile_w0[tt]; m.w1 = p.tile_w0[tt + 1];
+            return m;
+        };
+        TileMeta cur = fetch_tile();
+        for (;;) {
             open_msg();
-            if (t >= p.n_tiles) {
+            if (cur.t >= p.n_tiles) {
                 send_msg(kMsgEnd, 0u);
                 break;
             }
-            send_msg(kMsgTile, t);
-            const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
-            const uint32_t lvl0 = p.tile_lvl[t];
-            const uint32_t sseg = p.tile_sseg[t];
-            mc_issue = p.tile_w0[t];
-            mc_end = p.tile_w0[t + 1];
+            send_msg(kMsgTile, cur.t);
+            mc_issue = cur.w0;
+            mc_end = cur.w1;
             mc_wait = mc_issue;
             uint32_t o0 = mc_issue * kChunk3;
             // seed segments, then one segment per block
-            for (uint32_t l0 = 0; l0 < lvl0; l0 += 32u) {
-                const uint32_t o1 = p.seed_end[sseg + (l0 >> 5)] * 4u;
+            for (uint32_t l0 = 0; l0 < cur.lvl0; l0 += 32u) {
+                const uint32_t o1 = p.seed_end[cur.sseg + (l0 >> 5)] * 4u;
                 open_msg();
                 scan(o0, o1);
                 send_msg(kMsgLast, 0u);
                 o0 = o1;
             }
-            const uint32_t b0 = n0 >> 5, nb = (n1 - n0 + 31u) >> 5;
+            const uint32_t b0 = cur.n0 >> 5, nb = (cur.n1 - cur.n0 + 31u) >> 5;
+            const uint32_t b_fetch = nb > 3u ? nb - 3u : 0u;
+            TileMeta nxt = cur;
             uint32_t bw = 0;
             for (uint32_t b = 0; b < nb; b++) {
                 if ((b & 31u) == 0) bw = (b + lane < nb) ? __ldg(p.blk_words + b0 + b + lane) : 0u;
+                if (b == b_fetch) nxt = fetch_tile();
                 const uint32_t o1 = o0 + __shfl_sync(FULL, bw, b & 31u);
                 open_msg();
                 scan(o0, o1);
                 send_msg(kMsgLast, 0u);
                 o0 = o1;
             }
+            cur = nxt;
         }
     } else {
         // =====================================================================================================
@@ -425,7 +437,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
         auto take_segment = [&]() {
             for (;;) {
                 const uint32_t s = nmsg % kSlots3;
-                mbar_wait_long(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
+                mbar_wait_idle(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
                 const uint32_t m = msg[s].x;
                 process(s, m & 0xffffu);
                 __syncwarp();
@@ -480,8 +492,8 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 const uint32_t level = h.z >> kLevelShift, flags = h.z & 0x3fffu;
                 const uint32_t nmut = act ? (h.w >> 16) : 0u;
                 const bool dense_ok = act && (flags & kFlagValid0);
-                const int min_g = __reduce_min_sync(FULL, dense_ok ? h.x : BIG);
-                const int min_gn = __reduce_min_sync(FULL, act ? h.x - (int)nmut : BIG);
+                const int min_g = __reduce_min_sync(FULL, dense_ok ? (int)h.x : BIG);            // signed: G can be < 0
+                const int min_gn = __reduce_min_sync(FULL, act ? (int)h.x - (int)nmut : BIG);
                 info[kI3G + lane] = (uint32_t)h.x;
                 info[kI3Z + lane] = h.z;
                 info[kI3W + lane] = h.w;
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                         const uint32_t s = __ffs(need_e) - 1;
                         need_e &= need_e - 1;
                         const uint32_t hm_s = info[kI3Hm + s];
-                        const int sc = h.x + above(level, h.y, hm_s, s);
+                        const int sc = (int)h.x + above(level, h.y, hm_s, s);
                         const int bs = __shfl_sync(FULL, bsc, s);
                         uint32_t cm = __ballot_sync(FULL, dense_ok && !((hm_s >> lane) & 1u) && sc <= bs);
                         while (cm) {

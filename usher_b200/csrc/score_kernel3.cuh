@@ -35,8 +35,8 @@ namespace ub200 {
 
 constexpr int kPairs3 = 16;
 constexpr int kThreads3 = kPairs3 * 64;
-constexpr int kMutStages3 = 4;
-constexpr uint32_t kRingWords3 = kChunk3 * kMutStages3;   // 1024 words = 4 KB
+constexpr uint32_t kRingRows3 = 8;                         // rows of 128 words (512 B)
+constexpr uint32_t kRingWords3 = kRingRows3 * 128;         // 1024 words = 4 KB
 constexpr uint32_t kSlots3 = 8, kSlotCap3 = 64;            // scanner -> consumer messages
 constexpr int kStack3 = 32;                                // levels kept in shared memory (deeper: HBM spill)
 // per-pair shared memory (bytes)
@@ -46,10 +46,10 @@ constexpr uint32_t kO3Stack = 8192;                        // i16[32][32]
 constexpr uint32_t kO3List = kO3Stack + kStack3 * 64;      // u32[8][64] hit words
 constexpr uint32_t kO3Info = kO3List + kSlots3 * kSlotCap3 * 4;   // u32[6][32]: G, z, w, am, hm, neg
 constexpr uint32_t kO3Msg = kO3Info + 6 * 128;             // uint2[8]: (count | flags << 16, payload)
-constexpr uint32_t kO3Bars = kO3Msg + kSlots3 * 8;         // mbarriers: 4 ring, 8 full, 8 empty
-constexpr uint32_t kWarpSmem3 = (kO3Bars + (kMutStages3 + 2 * kSlots3) * 8 + 127) & ~127u;
+constexpr uint32_t kO3Bars = kO3Msg + kSlots3 * 8;         // mbarriers: 8 full, 8 empty
+constexpr uint32_t kWarpSmem3 = (kO3Bars + 2 * kSlots3 * 8 + 127) & ~127u;
 constexpr uint32_t kI3G = 0, kI3Z = 32, kI3W = 64, kI3Am = 96, kI3Hm = 128, kI3Neg = 160;
-constexpr uint32_t kBarFull = kMutStages3, kBarEmpty = kBarFull + kSlots3;
+constexpr uint32_t kBarFull = 0, kBarEmpty = kSlots3;
 constexpr uint32_t kMsgLast = 1u << 16, kMsgTile = 2u << 16, kMsgEnd = 4u << 16;
 constexpr uint32_t kLut3Bytes = 4096;
 constexpr uint32_t kMaxRowV3 = 500;      // packed 10-bit delta fields
@@ -95,6 +95,12 @@ __device__ __forceinline__ uint4 lds128_3(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -184,8 +190,8 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
         // =====================================================================================================
         // scanner
         // =====================================================================================================
-        uint32_t mphase = 0;
-        uint32_t mc_issue = 0, mc_end = 0, mc_wait = 0;
+        uint32_t lrow = 0, rows_end = 0;   // next ring row to load, end of the tile's rows
+        bool fresh = true;                 // first step of a tile: nothing is in flight yet
         uint32_t nmsg = 0;        // messages sent so far; the open one lives in slot nmsg % kSlots3
         uint32_t fill = 0;        // hit words in the open message
         auto open_msg = [&]() {   // wait until the consumer has released the slot
@@ -206,27 +212,32 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
 
         // scan stream words [o0, o1) (both multiples of 4) of the current tile, 512 words per step; the hit
         // words go to the open message, which is sent (not flagged last) and reopened whenever it is full
+        // ring loader: rows of 128 words (512 B, absolute-aligned), one 16-byte cp.async per lane per row
+        // (LDGSTS, L2 -> shared memory without registers).  The bookkeeping is two counters and cp.async groups;
+        // a one-warp producer pays ~3 issue slots per 512 B this way, against ~12 for a bulk copy with its
+        // mbarrier — and this kernel is bound by issue slots, not by copy bandwidth.
+        auto ring_fill = [&](uint32_t cur_row) {
+            const uint32_t lim_row = min(rows_end, cur_row + kRingRows3);
+            while (lrow < lim_row) {
+                cp_async16(mring_a + (((lrow & (kRingRows3 - 1u)) << 9) + (lane << 4)),
+                           p.stream + ((size_t)lrow << 7) + (lane << 2));
+                lrow++;
+            }
+            cp_async_commit();
+        };
         auto scan = [&](uint32_t o0, uint32_t o1) {
-            for (uint32_t off = o0; off < o1; off += 512u) {
-                const uint32_t lim = min(off + 512u, o1);
-                // chunks below off / kChunk3 are dead: refill their stages; then wait for the step's words
-                while (mc_issue < mc_end && mc_issue < off / kChunk3 + kMutStages3) {
-                    if (elect_one()) {
-                        const uint32_t s = mc_issue % kMutStages3;
-                        mbar_expect_tx(bars_a + 8 * s, kChunk3 * 4);
-                        bulk_g2s(mring_a + s * kChunk3 * 4, p.stream + (size_t)mc_issue * kChunk3, kChunk3 * 4,
-                                 bars_a + 8 * s);
-                    }
-                    mc_issue++;
-                }
-                while (mc_wait <= (lim - 1u) / kChunk3) {
-                    const uint32_t s = mc_wait % kMutStages3;
-                    mbar_wait(bars_a + 8 * s, (mphase >> s) & 1u);
-                    mphase ^= 1u << s;
-                    mc_wait++;
-                }
-                const uint32_t nq = (lim - off + 127u) >> 7;      // quads (LDS.128) per lane in this step, 1..4
-                const uint32_t idx = off + 4u * lane;
+            for (uint32_t off = o0; off < o1;) {
+                // a step = the (up to) 4 rows from the one holding `off`, clipped to the segment
+                const uint32_t r0 = off >> 7;
+                const uint32_t lim = min((r0 + 4u) << 7, o1);
+                // rows below r0 are dead: top the ring up (these rows are needed one step from now), then wait
+                // for everything issued before this top-up
+                ring_fill(r0);
+                if (fresh) { cp_async_wait<0>(); fresh = false; } else cp_async_wait<1>();
+                __syncwarp();
+                const uint32_t base = r0 << 7;
+                const uint32_t nq = (lim - base + 127u) >> 7;     // rows (LDS.128 per lane) in this step, 1..4
+                const uint32_t idx = base + 4u * lane;
                 uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
@@ -241,11 +252,13 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                     }
                 }
                 uint32_t hb = acc >> 16;                           // bit 4k+j = word j of quad k
-                if (lim - off < 512u) {                            // lanes past the segment read whatever the ring holds
-                    const int dwords = (int)(lim - idx);
-                    const uint32_t nv = dwords > 0 ? min((uint32_t)(dwords + 127) >> 7, 4u) : 0u;
-                    hb &= (1u << (4u * nv)) - 1u;
+                if (off != base || lim != base + 512u) {          // quads outside [off, lim) belong to other segments
+                    const int lo = (int)(off - idx), hi = (int)(lim - idx);   // multiples of 4
+                    const uint32_t k_lo = lo > 0 ? min((uint32_t)(lo + 127) >> 7, 4u) : 0u;
+                    const uint32_t k_hi = hi > 0 ? min((uint32_t)(hi + 127) >> 7, 4u) : 0u;
+                    hb &= ((1u << (4u * k_hi)) - 1u) & ~((1u << (4u * k_lo)) - 1u);
                 }
+                off = lim;
                 // compact: lane l's hits follow those of lanes < l.  Exclusive prefix of the per-lane counts:
                 // two ballots when no lane has more than 3 hits (the usual case), else a shuffle scan
                 const uint32_t c = __popc(hb);
@@ -324,10 +337,11 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 break;
             }
             send_msg(kMsgTile, cur.t);
-            mc_issue = cur.w0;
-            mc_end = cur.w1;
-            mc_wait = mc_issue;
-            uint32_t o0 = mc_issue * kChunk3;
+            lrow = cur.w0 * (kChunk3 / 128u);
+            rows_end = cur.w1 * (kChunk3 / 128u);
+            fresh = true;
+            uint32_t o0 = cur.w0 * kChunk3;
+            ring_fill(lrow);
             // seed segments, then one segment per block
             for (uint32_t l0 = 0; l0 < cur.lvl0; l0 += 32u) {
                 const uint32_t o1 = p.seed_end[cur.sseg + (l0 >> 5)] * 4u;

@@ -89,8 +89,31 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     const uint32_t pad = pack_mut3(nw, d.L, 0, 0, 0);
     auto conv = [&](uint32_t w, uint32_t lane) { return pack_mut3(nw, w >> 6, lane, (w >> 2) & 3u, w & 3u); };
     auto align_to = [&](size_t a) { while (d.stream.size() % a) d.stream.push_back(pad); };
-    std::vector<uint32_t> chain;
+    std::vector<uint32_t> chain, seg;
     d.seed_words = 0;
+    // A segment's words go out sorted by position and transposed inside every 128-word row piece: the scanner
+    // reads a row with one 16-byte load per lane, so component j of the 32 lanes should hold 32 CONSECUTIVE
+    // sorted words -> their bitmap words are consecutive too and the 32 bitmap reads fall into distinct
+    // shared-memory banks (a random order costs ~3.5 wavefronts per read).  Which node (or level) a word belongs
+    // to is in the word, so the order inside a segment is free.
+    const uint32_t pshift = nw ? 16 : 14;
+    auto emit_segment = [&]() {
+        std::sort(seg.begin(), seg.end(), [&](uint32_t a, uint32_t b) {
+            const uint32_t pa = ((a >> pshift) << 5) | (a & 31u), pb = ((b >> pshift) << 5) | (b & 31u);
+            return pa != pb ? pa < pb : a < b;
+        });
+        while (seg.size() % 4) seg.push_back(pad);
+        size_t s0 = 0;
+        while (s0 < seg.size()) {
+            const size_t off = d.stream.size();
+            const size_t m = std::min<size_t>(128 - off % 128, seg.size() - s0), nl = m / 4;
+            d.stream.resize(off + m);
+            for (size_t i = 0; i < nl; i++)
+                for (size_t j = 0; j < 4; j++) d.stream[off + 4 * i + j] = seg[s0 + j * nl + i];
+            s0 += m;
+        }
+        seg.clear();
+    };
     for (size_t t = 0; t < T; t++) {
         align_to(kChunk3);
         d.tile3_w0[t] = (uint32_t)(d.stream.size() / kChunk3);
@@ -103,8 +126,8 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         for (uint32_t l0 = 0; l0 < lvl0; l0 += 32) {
             for (uint32_t l = l0; l < std::min(lvl0, l0 + 32); l++)
                 for (uint32_t k = d.row32[chain[l]]; k < d.row32[chain[l] + 1]; k++)
-                    d.stream.push_back(conv(d.mutw[k], l & 31u));
-            align_to(4);
+                    seg.push_back(conv(d.mutw[k], l & 31u));
+            emit_segment();
             d.seed_end.push_back((uint32_t)(d.stream.size() / 4));
         }
         d.seed_words += d.stream.size() - before;
@@ -112,8 +135,8 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         for (uint32_t b = n0; b < n1; b += 32) {
             const size_t s0 = d.stream.size();
             for (uint32_t i = b; i < std::min(n1, b + 32); i++)
-                for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) d.stream.push_back(conv(d.mutw[k], i & 31u));
-            align_to(4);
+                for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) seg.push_back(conv(d.mutw[k], i & 31u));
+            emit_segment();
             d.blk_words[b >> 5] = (uint32_t)(d.stream.size() - s0);
         }
     }

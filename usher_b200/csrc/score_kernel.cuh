@@ -114,11 +114,13 @@ __device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();
     }
 }
-// waits of a warp that has slack (the consumer on its scanner): back off between polls
+// waits of a warp that has slack (the consumer on its scanner): sleep between polls, longer each time, so that
+// the waiting warp leaves the issue slots and the shared-memory pipe to the warps it is waiting for
 __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
+    uint32_t spins = 0, ns = 256;
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(200);
+        __nanosleep(ns);
+        if (ns < 2048u) ns <<= 1;
         if (++spins > (1u << 22)) __trap();
     }
 }

@@ -329,7 +329,7 @@ def main():
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": "ub200::k_score2<true>", "peak_source": peak_src,
+        "traffic": traffic, "kernel": "ub200::k_score3<smem bitmap, best, narrow words>", "peak_source": peak_src,
         "bytes_per_launch": int(mat.info.algorithmic_bytes), "launches": int(score_launches),
         "us_per_launch": 1000.0 * score_ms / max(score_launches, 1),
         "share_of_step": score_ms / (ev0.elapsed_time(ev1)) if ms_total > 0 else None,

@@ -38,11 +38,11 @@ constexpr int kThreads3 = kPairs3 * 64;
 constexpr uint32_t kRingRows3 = 8;                         // rows of 128 words (512 B)
 constexpr uint32_t kRingWords3 = kRingRows3 * 128;         // 1024 words = 4 KB
 constexpr uint32_t kSlots3 = 8, kSlotCap3 = 64;            // scanner -> consumer messages
-constexpr int kStack3 = 32;                                // levels kept in shared memory (deeper: HBM spill)
+constexpr int kStack3 = 40;                                // levels kept in shared memory (deeper: HBM spill)
 // per-pair shared memory (bytes)
 constexpr uint32_t kO3Mring = 0;                           // u32[1024]            scanner
 constexpr uint32_t kO3Dnode = 4096;                        // i32[32][32] packed deltas   consumer
-constexpr uint32_t kO3Stack = 8192;                        // i16[32][32]
+constexpr uint32_t kO3Stack = 8192;                        // i16[40][32]
 constexpr uint32_t kO3List = kO3Stack + kStack3 * 64;      // u32[8][64] hit words
 constexpr uint32_t kO3Info = kO3List + kSlots3 * kSlotCap3 * 4;   // u32[6][32]: G, z, w, am, hm, neg
 constexpr uint32_t kO3Msg = kO3Info + 6 * 128;             // uint2[8]: (count | flags << 16, payload)

@@ -140,6 +140,22 @@ def test_optimal_sets_vs_port_many_tiles(seed, shape, fam, monkeypatch):
     pt.close(); m.close(); s.close()
 
 
+@pytest.mark.parametrize("genome_len", [200_000, 3_000_000])
+def test_long_genomes_vs_port(genome_len):
+    """Genomes whose position bitmap does not fit shared memory (global bitmap path) and, at 3 Mb, positions beyond
+    2^21 (wide stream words)."""
+    s = capi.Synth(6_000, 5.0, genome_len, capi.Synth.UNIFORM, 4242)
+    p, r, mu = s.arrays()
+    sp, sc, _ = s.samples(48, capi.Synth.AMBIG, 9)
+    m = capi.Mat.from_flat_struct(s.flat)
+    got = common.placements_to_dict(m.place_batch(sp, sc, best_set=True))
+    pt = port.PortTree(p, r, mu)
+    q = pt.search(sp, sc)
+    for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
+        assert np.array_equal(np.asarray(got[k]).astype(np.int64), q[k].astype(np.int64)), (genome_len, k)
+    pt.close(); m.close(); s.close()
+
+
 def test_resident_api_matches_batch_api_and_times():
     g = common.load(common.GOLDEN + "/random_15.npz")
     m = capi.Mat(g["parent"], g["row_ptr"], g["muts"])

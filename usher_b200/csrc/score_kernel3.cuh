@@ -239,16 +239,20 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 const uint32_t nq = (lim - base + 127u) >> 7;     // rows (LDS.128 per lane) in this step, 1..4
                 const uint32_t idx = base + 4u * lane;
                 uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
+                auto quad = [&](uint32_t k) {
+                    const uint4 q = lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2));
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.x), 0u, q.x), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.y), 0u, q.y), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.z), 0u, q.z), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.w), 0u, q.w), 1u);
+                };
+                if (nq == 4u) {   // the usual step: one basic block, so that the loads of all four rows overlap
+                    quad(0); quad(1); quad(2); quad(3);
+                } else {
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++) {
-                    if (k < nq) {
-                        const uint4 q = lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2));
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.x), 0u, q.x), 1u);
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.y), 0u, q.y), 1u);
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.z), 0u, q.z), 1u);
-                        acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.w), 0u, q.w), 1u);
-                    } else {
-                        acc >>= 4;
+                    for (uint32_t k = 0; k < 4; k++) {
+                        if (k < nq) quad(k);
+                        else acc >>= 4;
                     }
                 }
                 uint32_t hb = acc >> 16;                           // bit 4k+j = word j of quad k
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
         auto take_segment = [&]() {
             for (;;) {
                 const uint32_t s = nmsg % kSlots3;
-                mbar_wait_idle(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u);
+                mbar_wait_idle(bars_a + 8 * (kBarFull + s), (nmsg / kSlots3) & 1u, p.gbest);
                 const uint32_t m = msg[s].x;
                 process(s, m & 0xffffu);
                 __syncwarp();

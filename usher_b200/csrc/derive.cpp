@@ -133,8 +133,20 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         d.seed_words += d.stream.size() - before;
         d.tile3_sseg[t + 1] = (uint32_t)d.seed_end.size();
         for (uint32_t b = n0; b < n1; b += 32) {
+            // The scanner takes a segment in steps of 4 absolute 128-word rows.  If starting here costs a step
+            // more than starting on a row boundary would, pad up to the boundary (the pad words are appended
+            // to the previous segment; ~2 % of the stream at C4, and every block then takes 2 steps, not 2.4).
+            const uint32_t e = std::min(n1, b + 32);
+            const size_t len4 = ((size_t)(d.row32[e] - d.row32[b]) + 3) & ~(size_t)3;
+            const size_t off = d.stream.size() % 128;
+            if (off && ((off + len4 + 127) / 128 + 3) / 4 > ((len4 + 127) / 128 + 3) / 4) {
+                const size_t padw = 128 - off;
+                d.stream.resize(d.stream.size() + padw, pad);
+                if (b > n0) d.blk_words[(b >> 5) - 1] += (uint32_t)padw;
+                else if (lvl0) d.seed_end.back() += (uint32_t)(padw / 4);
+            }
             const size_t s0 = d.stream.size();
-            for (uint32_t i = b; i < std::min(n1, b + 32); i++)
+            for (uint32_t i = b; i < e; i++)
                 for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) seg.push_back(conv(d.mutw[k], i & 31u));
             emit_segment();
             d.blk_words[b >> 5] = (uint32_t)(d.stream.size() - s0);

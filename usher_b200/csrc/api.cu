@@ -307,7 +307,7 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     std::string err;
     const char* mt = getenv("UB200_MIN_TILE");   // test hook: cut small trees into many tiles
     const char* tw = getenv("UB200_TILES_PER_WORKER");
-    int rc = ub200::derive(*flat, total_warps * (tw ? (uint32_t)atoi(tw) : 8u), M->d, err, mt ? (uint32_t)atoi(mt) : 0u);
+    int rc = ub200::derive(*flat, total_warps * (tw ? (uint32_t)atoi(tw) : 3u), M->d, err, mt ? (uint32_t)atoi(mt) : 0u);
     if (rc != UB200_OK) { delete M; return fail(rc, err); }
     auto& d = M->d;
     M->n = d.n; M->m = d.m; M->L = d.L; M->n_tiles = (uint32_t)d.tile_start.size() - 1;

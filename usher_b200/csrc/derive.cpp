@@ -14,9 +14,11 @@
 //   * num_leaves (mutation_annotated_tree.cpp:866-879), BFS index (:1225-1251), level.
 // The kernel then only has to correct these for the few mutations that hit a position the sample calls.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "ub200_internal.h"
 
@@ -83,77 +85,103 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     d.tile3_sseg.assign(T + 1, 0);
     d.seed_end.clear();
     d.blk_words.assign(nblk, 0);
-    d.stream.clear();
-    d.stream.reserve(d.m + d.m / 6 + 4 * kChunk3);
     const bool nw = d.narrow3;
     const uint32_t pad = pack_mut3(nw, d.L, 0, 0, 0);
     auto conv = [&](uint32_t w, uint32_t lane) { return pack_mut3(nw, w >> 6, lane, (w >> 2) & 3u, w & 3u); };
-    auto align_to = [&](size_t a) { while (d.stream.size() % a) d.stream.push_back(pad); };
-    std::vector<uint32_t> chain, seg;
-    d.seed_words = 0;
-    // A segment's words go out sorted by position and transposed inside every 128-word row piece: the scanner
-    // reads a row with one 16-byte load per lane, so component j of the 32 lanes should hold 32 CONSECUTIVE
-    // sorted words -> their bitmap words are consecutive too and the 32 bitmap reads fall into distinct
-    // shared-memory banks (a random order costs ~3.5 wavefronts per read).  Which node (or level) a word belongs
-    // to is in the word, so the order inside a segment is free.
     const uint32_t pshift = nw ? 16 : 14;
-    auto emit_segment = [&]() {
-        std::sort(seg.begin(), seg.end(), [&](uint32_t a, uint32_t b) {
-            const uint32_t pa = ((a >> pshift) << 5) | (a & 31u), pb = ((b >> pshift) << 5) | (b & 31u);
-            return pa != pb ? pa < pb : a < b;
-        });
-        while (seg.size() % 4) seg.push_back(pad);
-        size_t s0 = 0;
-        while (s0 < seg.size()) {
-            const size_t off = d.stream.size();
-            const size_t m = std::min<size_t>(128 - off % 128, seg.size() - s0), nl = m / 4;
-            d.stream.resize(off + m);
-            for (size_t i = 0; i < nl; i++)
-                for (size_t j = 0; j < 4; j++) d.stream[off + 4 * i + j] = seg[s0 + j * nl + i];
-            s0 += m;
-        }
-        seg.clear();
-    };
-    for (size_t t = 0; t < T; t++) {
-        align_to(kChunk3);
-        d.tile3_w0[t] = (uint32_t)(d.stream.size() / kChunk3);
+    // Every tile's piece of the stream starts on a 1 KB boundary, so the pieces are built independently (one
+    // host thread per slice of tiles) and concatenated afterwards.
+    struct Piece { std::vector<uint32_t> words; std::vector<uint32_t> seed_end4; uint64_t seed_words = 0; };
+    std::vector<Piece> pieces(T);
+    auto build_tile = [&](size_t t, std::vector<uint32_t>& chain, std::vector<uint32_t>& seg) {
+        Piece& pc = pieces[t];
+        std::vector<uint32_t>& out = pc.words;
+        // A segment's words go out sorted by position and transposed inside every 128-word row piece: the
+        // scanner reads a row with one 16-byte load per lane, so component j of the 32 lanes should hold 32
+        // CONSECUTIVE sorted words -> their bitmap words are consecutive too and the 32 bitmap reads fall into
+        // distinct shared-memory banks (a random order costs ~3.5 wavefronts per read).  Which node (or level) a
+        // word belongs to is in the word, so the order inside a segment is free.
+        auto emit_segment = [&]() {
+            std::sort(seg.begin(), seg.end(), [&](uint32_t x, uint32_t y) {
+                const uint32_t px = ((x >> pshift) << 5) | (x & 31u), py = ((y >> pshift) << 5) | (y & 31u);
+                return px != py ? px < py : x < y;
+            });
+            while (seg.size() % 4) seg.push_back(pad);
+            size_t s0 = 0;
+            while (s0 < seg.size()) {
+                const size_t off = out.size();
+                const size_t m = std::min<size_t>(128 - off % 128, seg.size() - s0), nl = m / 4;
+                out.resize(off + m);
+                for (size_t i = 0; i < nl; i++)
+                    for (size_t j = 0; j < 4; j++) out[off + 4 * i + j] = seg[s0 + j * nl + i];
+                s0 += m;
+            }
+            seg.clear();
+        };
         const uint32_t n0 = d.tile3_start[t], n1 = d.tile3_start[t + 1];
         const uint32_t lvl0 = d.level[n0];
         d.tile3_lvl[t] = lvl0;
         chain.assign(lvl0, 0);
         for (int32_t a = f.parent[n0]; a >= 0; a = f.parent[a]) chain[d.level[a]] = (uint32_t)a;
-        const size_t before = d.stream.size();
+        out.reserve((size_t)(d.row32[n1] - d.row32[n0]) + (size_t)(pathw[n0]) + (n1 - n0) * 3 + 1024);
         for (uint32_t l0 = 0; l0 < lvl0; l0 += 32) {
             for (uint32_t l = l0; l < std::min(lvl0, l0 + 32); l++)
                 for (uint32_t k = d.row32[chain[l]]; k < d.row32[chain[l] + 1]; k++)
                     seg.push_back(conv(d.mutw[k], l & 31u));
             emit_segment();
-            d.seed_end.push_back((uint32_t)(d.stream.size() / 4));
+            pc.seed_end4.push_back((uint32_t)(out.size() / 4));
         }
-        d.seed_words += d.stream.size() - before;
-        d.tile3_sseg[t + 1] = (uint32_t)d.seed_end.size();
+        pc.seed_words = out.size();
         for (uint32_t b = n0; b < n1; b += 32) {
             // The scanner takes a segment in steps of 4 absolute 128-word rows.  If starting here costs a step
             // more than starting on a row boundary would, pad up to the boundary (the pad words are appended
             // to the previous segment; ~2 % of the stream at C4, and every block then takes 2 steps, not 2.4).
             const uint32_t e = std::min(n1, b + 32);
             const size_t len4 = ((size_t)(d.row32[e] - d.row32[b]) + 3) & ~(size_t)3;
-            const size_t off = d.stream.size() % 128;
+            const size_t off = out.size() % 128;
             if (off && ((off + len4 + 127) / 128 + 3) / 4 > ((len4 + 127) / 128 + 3) / 4) {
                 const size_t padw = 128 - off;
-                d.stream.resize(d.stream.size() + padw, pad);
+                out.resize(out.size() + padw, pad);
                 if (b > n0) d.blk_words[(b >> 5) - 1] += (uint32_t)padw;
-                else if (lvl0) d.seed_end.back() += (uint32_t)(padw / 4);
+                else if (lvl0) pc.seed_end4.back() += (uint32_t)(padw / 4);
             }
-            const size_t s0 = d.stream.size();
+            const size_t s0 = out.size();
             for (uint32_t i = b; i < e; i++)
                 for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) seg.push_back(conv(d.mutw[k], i & 31u));
             emit_segment();
-            d.blk_words[b >> 5] = (uint32_t)(d.stream.size() - s0);
+            d.blk_words[b >> 5] = (uint32_t)(out.size() - s0);
         }
+        while (out.size() % kChunk3) out.push_back(pad);
+    };
+    {
+        unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (d.m < (1u << 20)) nthr = 1;
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            std::vector<uint32_t> chain, seg;
+            for (size_t t = next.fetch_add(1); t < T; t = next.fetch_add(1)) build_tile(t, chain, seg);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned i = 1; i < nthr; i++) pool.emplace_back(worker);
+        worker();
+        for (auto& th : pool) th.join();
     }
-    align_to(kChunk3);
-    d.tile3_w0[T] = (uint32_t)(d.stream.size() / kChunk3);
+    uint64_t total_words = 0;
+    for (size_t t = 0; t < T; t++) total_words += pieces[t].words.size();
+    d.stream.resize(total_words);
+    d.seed_words = 0;
+    uint64_t w = 0;
+    for (size_t t = 0; t < T; t++) {
+        Piece& pc = pieces[t];
+        d.tile3_w0[t] = (uint32_t)(w / kChunk3);
+        for (uint32_t e4 : pc.seed_end4) d.seed_end.push_back((uint32_t)(w / 4) + e4);
+        d.tile3_sseg[t + 1] = (uint32_t)d.seed_end.size();
+        d.seed_words += pc.seed_words;
+        std::memcpy(d.stream.data() + w, pc.words.data(), pc.words.size() * sizeof(uint32_t));
+        w += pc.words.size();
+        std::vector<uint32_t>().swap(pc.words);
+    }
+    d.tile3_w0[T] = (uint32_t)(w / kChunk3);
     d.seed_end.push_back(0);   // never empty
 }
 

@@ -192,6 +192,12 @@ def main():
         run_reference(args, wl, rank, world)
         return
 
+    # stdout carries exactly ONE line, the JSON record: anything a library prints meanwhile (NCCL's version banner
+    # at init, for one) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from usher_b200 import capi
@@ -367,7 +373,10 @@ def main():
             "gpu_launches": int(total_launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

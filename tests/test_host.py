@@ -129,3 +129,64 @@ def test_synth_generator_is_a_valid_mat():
             pos = sc["position"][int(sp[i]):int(sp[i + 1])]
             assert np.all(np.diff(pos) > 0)
     s.close()
+
+
+def test_segment_layout_structure():
+    """k_score3 layout invariants, straight from the arrays: every mutation of a block appears exactly once in the
+    block's segment with its node's lane; a tile's seed segments hold exactly the rows of the root path of its
+    first node; segment sizes, tile starts, in-block ancestor masks and open flags are what the kernel assumes."""
+    parent, row_ptr, muts, _ = small_synth.random_mat(5, 1500, 400, 3.0)
+    d = capi.debug_derive(parent, row_ptr, muts, target_tiles=40, min_tile_cost=300)
+    n, hdr, stream, nar = d["n"], d["hdr3"], d["stream"], d["narrow3"]
+    pos_of = lambda w: ((int(w) >> (16 if nar else 14)) << 5) | (int(w) & 31)
+    ts, w0, lvl, sseg, send, bw = (d[k] for k in ("tile3_start", "tile3_w0", "tile3_lvl", "tile3_sseg", "seed_end", "blk_words"))
+    assert ts[0] == 0 and ts[-1] == n and all(int(t) % 32 == 0 for t in ts[:-1]) and len(ts) > 4
+    level = d["level"]
+    old = d["mutw"]          # node-major words of the first layout: pos<<6 | ref<<4 | prev<<2 | mut
+    row32 = d["row32"]
+    def row_words(i, lane):
+        return sorted((int(w) >> 6, lane, (int(w) >> 2) & 3, int(w) & 3) for w in old[int(row32[i]):int(row32[i + 1])])
+    def seg_words(o0, o1):
+        out = []
+        for w in stream[o0:o1]:
+            w = int(w)
+            if pos_of(w) == d["L"]:
+                continue   # pad
+            out.append((pos_of(w), (w >> 9) & 31, (w >> 7) & 3, (w >> 5) & 3))
+        return sorted(out)
+    for t in range(len(ts) - 1):
+        n0, n1 = int(ts[t]), int(ts[t + 1])
+        o0 = int(w0[t]) * 256
+        assert int(lvl[t]) == int(level[n0])
+        chain = []
+        a = parent[n0]
+        while a >= 0:
+            chain.append(int(a)); a = parent[a]
+        chain = chain[::-1]
+        assert int(sseg[t + 1]) - int(sseg[t]) == (len(chain) + 31) // 32
+        for g in range((len(chain) + 31) // 32):
+            o1 = int(send[int(sseg[t]) + g]) * 4
+            exp = sorted(x for l in range(32 * g, min(len(chain), 32 * g + 32)) for x in row_words(chain[l], l & 31))
+            assert seg_words(o0, o1) == exp
+            o0 = o1
+        for blk in range(n0, n1, 32):
+            o1 = o0 + int(bw[blk >> 5])
+            assert o0 % 4 == 0 and o1 % 4 == 0
+            exp = sorted(x for i in range(blk, min(blk + 32, n1)) for x in row_words(i, i & 31))
+            assert seg_words(o0, o1) == exp
+            o0 = o1
+        assert o0 <= int(w0[t + 1]) * 256
+    # in-block ancestor masks and open flags
+    kids_beyond = np.zeros(n, bool)
+    for i in range(1, n):
+        a = parent[i]
+        while a >= 0:
+            if (a | 31) < i:
+                kids_beyond[a] = True
+            a = parent[a]
+    for i in range(n):
+        am, a = 0, parent[i]
+        while a >= 0 and a >= (i & ~31):
+            am |= 1 << (a & 31); a = parent[a]
+        assert int(hdr[i]["tiekey"]) == am
+        assert bool(int(hdr[i]["level_flags"]) & 32) == bool(kids_beyond[i])

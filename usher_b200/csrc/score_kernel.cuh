@@ -128,10 +128,6 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, co
     }
     if (acc == 0x9e3779b9u && spins == 0x7fffffffu) __trap();   // keeps the load's result live
 }
-// L2 prefetch of a contiguous global range (no shared memory, no completion tracking)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA unit, no tensor map)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

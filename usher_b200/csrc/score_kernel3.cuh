@@ -191,7 +191,6 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
         // scanner
         // =====================================================================================================
         uint32_t lrow = 0, rows_end = 0;   // next ring row to load, end of the tile's rows
-        bool fresh = true;                 // first step of a tile: nothing is in flight yet
         uint32_t nmsg = 0;        // messages sent so far; the open one lives in slot nmsg % kSlots3
         uint32_t fill = 0;        // hit words in the open message
         auto open_msg = [&]() {   // wait until the consumer has released the slot
@@ -230,28 +229,30 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 // a step = the (up to) 4 rows from the one holding `off`, clipped to the segment
                 const uint32_t r0 = off >> 7;
                 const uint32_t lim = min((r0 + 4u) << 7, o1);
-                // rows below r0 are dead: top the ring up (these rows are needed one step from now), then wait
-                // for everything issued before this top-up
-                ring_fill(r0);
-                if (fresh) { cp_async_wait<0>(); fresh = false; } else cp_async_wait<1>();
+                // everything issued so far has to be there (this step's rows went out one step ago)
+                cp_async_wait<0>();
                 __syncwarp();
                 const uint32_t base = r0 << 7;
                 const uint32_t nq = (lim - base + 127u) >> 7;     // rows (LDS.128 per lane) in this step, 1..4
                 const uint32_t idx = base + 4u * lane;
                 uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
-                auto quad = [&](uint32_t k) {
-                    const uint4 q = lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2));
+                auto row_of = [&](uint32_t k) { return lds128_3(mring_a + (((idx + 128u * k) & (kRingWords3 - 1u)) << 2)); };
+                auto test4 = [&](const uint4& q) {
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.x), 0u, q.x), 1u);
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.y), 0u, q.y), 1u);
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.z), 0u, q.z), 1u);
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.w), 0u, q.w), 1u);
                 };
                 if (nq == 4u) {   // the usual step: one basic block, so that the loads of all four rows overlap
-                    quad(0); quad(1); quad(2); quad(3);
+                    const uint4 q0 = row_of(0), q1 = row_of(1), q2 = row_of(2), q3 = row_of(3);
+                    // rows below r0 are dead: top the ring up (needed one step from now) while the loads are in flight
+                    ring_fill(r0);
+                    test4(q0); test4(q1); test4(q2); test4(q3);
                 } else {
+                    ring_fill(r0);
 #pragma unroll
                     for (uint32_t k = 0; k < 4; k++) {
-                        if (k < nq) quad(k);
+                        if (k < nq) test4(row_of(k));
                         else acc >>= 4;
                     }
                 }
@@ -343,7 +344,6 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
             send_msg(kMsgTile, cur.t);
             lrow = cur.w0 * (kChunk3 / 128u);
             rows_end = cur.w1 * (kChunk3 / 128u);
-            fresh = true;
             uint32_t o0 = cur.w0 * kChunk3;
             ring_fill(lrow);
             // seed segments, then one segment per block

@@ -512,10 +512,6 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 const bool dense_ok = act && (flags & kFlagValid0);
                 const int min_g = __reduce_min_sync(FULL, dense_ok ? (int)h.x : BIG);            // signed: G can be < 0
                 const int min_gn = __reduce_min_sync(FULL, act ? (int)h.x - (int)nmut : BIG);
-                info[kI3G + lane] = (uint32_t)h.x;
-                info[kI3Z + lane] = h.z;
-                info[kI3W + lane] = h.w;
-                info[kI3Am + lane] = h.y;
                 zero_dnode();
                 __syncwarp();
 
@@ -528,6 +524,12 @@ __global__ void __launch_bounds__(kThreads3, 1) k_score3(const Score3Params p) {
                 const int bound = min(bsc, gb);
                 const uint32_t needs = __ballot_sync(FULL, live && min_gn + lbase <= bound);
                 if (needs) {
+                    // node-indexed copies of the headers for the lane = sample phase (only blocks that get here pay)
+                    info[kI3G + lane] = (uint32_t)h.x;
+                    info[kI3Z + lane] = h.z;
+                    info[kI3W + lane] = h.w;
+                    info[kI3Am + lane] = h.y;
+                    __syncwarp();
                     // correction of the path above node (level, am) for sample s
                     auto above = [&](uint32_t lvl, uint32_t am, uint32_t hmask, uint32_t s) -> int {
                         const uint32_t top = lvl - __popc(am);

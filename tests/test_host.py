@@ -190,3 +190,27 @@ def test_segment_layout_structure():
             am |= 1 << (a & 31); a = parent[a]
         assert int(hdr[i]["tiekey"]) == am
         assert bool(int(hdr[i]["level_flags"]) & 32) == bool(kids_beyond[i])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_trees_segment_model_vs_port(seed):
+    """Fresh randomized trees (chains deeper than 64 levels, stars, masked mutations, tiny genomes with position
+    collisions) cut into many tiles: the derivation + the k_score3 layout model against the oracle port."""
+    from oracle import port
+    n = [40, 150, 400, 700][seed % 4]
+    L = [25, 90, 300][seed % 3]
+    mu = [1.0, 3.0, 6.0][(seed // 2) % 3]
+    shape = ["uniform", "chain", "star"][seed % 3]
+    parent, row_ptr, muts, refg = small_synth.random_mat(7100 + seed, n, L, mu, shape=shape)
+    s_ptr, calls = small_synth.random_samples(7200 + seed, parent, row_ptr, muts, refg, 6)
+    d = capi.debug_derive(parent, row_ptr, muts, target_tiles=64, min_tile_cost=[64, 200][seed % 2])
+    res3 = kernel_model.place3(d, s_ptr, calls)
+    pt = port.PortTree(parent, row_ptr, muts)
+    q = pt.search(s_ptr, calls)
+    for i, r in enumerate(res3):
+        assert (r["score"], r["best_node"], r["best_j"], r["num_best"], r["has_unique"]) == (
+            int(q["score"][i]), int(q["best_dfs"][i]), int(q["best_j"][i]), int(q["num_best"][i]),
+            int(q["has_unique"][i])), (seed, i)
+        a, b = int(q["best_set_ptr"][i]), int(q["best_set_ptr"][i + 1])
+        assert [x for x, _ in r["optimal"]] == q["best_set"][a:b].tolist()
+    pt.close()

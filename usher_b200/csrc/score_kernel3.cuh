@@ -4,16 +4,18 @@
 // tile: a contiguous DFS range of whole 32-node blocks whose mutations are ONE contiguous piece of the stream,
 // [seed segments][block segments].  A CTA holds 16 warp PAIRS; a pair works on one tile at a time:
 //
-//   scanner warp   pulls the tile's stream through a shared-memory ring with 1 KB bulk async copies
-//                  (cp.async.bulk -> UBLKCP) completing on per-stage mbarriers, and tests every word's position
-//                  against the group's bitmap (lane = 16 words per 512-word step: four LDS.128, per word one
-//                  bitmap LDS, one wrap shift, one funnel shift that collects the hit bits).  Hit words are
-//                  compacted (one warp prefix sum per step) into one of four 64-word message slots and handed
-//                  to the consumer through full/empty mbarriers; a segment is one or more messages, the last
-//                  one flagged.  The scanner needs no sample state, only the bitmap.
+//   scanner warp   pulls the tile's stream through a 4 KB shared-memory ring of 512 B rows, one 16-byte cp.async
+//                  per lane per row (LDGSTS, cp.async groups; a one-warp producer pays ~3 issue slots per row
+//                  this way, a bulk copy with its mbarrier ~12), and tests every word's position against the
+//                  group's bitmap: a step = 4 rows = 16 words per lane: four LDS.128, then per word LEA.HI (byte
+//                  offset of the bitmap word), LDS, a wrap shift (bit to bit 0) and a funnel shift that collects
+//                  the hit bits.  Hit words are compacted (two ballots per step) into one of eight 64-word
+//                  message slots and handed to the consumer through full/empty mbarriers; a segment is one or
+//                  more messages, the last one flagged.  The scanner needs no sample state, only the bitmap.
 //   consumer warp  owns the sample state.  Per block:
-//     A  lane = node     header decode (one coalesced 512 B load per block, fetched a block ahead)
-//     C  lane = hit      hit word -> node lane (stored in the word), table row of the position (32 B, L2) ->
+//     A  lane = node     header decode (one coalesced 512 B load per block, fetched a block ahead into registers)
+//     C  lane = hit      hit word -> node lane (stored in the word), table row of the position (32 B, L2; two
+//                        rows per lane in flight) ->
 //                        for every sample calling the position: packed (dcorr, da, dcommon) from a 1024-entry
 //                        LUT, shared-memory atomics into dnode[node][sample], hm[sample] |= node,
 //                        neg[sample] += min(dcorr, 0)

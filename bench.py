@@ -28,10 +28,13 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (nodes, mu, genome_len, shape, seed, family)
     "c4": (10_000_000, 30.0, 30_000, 0, 20260929, 0),
+    "c5": (10_000_000, 30.0, 30_000, 0, 20260929, 2),   # config 5: the C4 tree, ambiguous calls + N runs
     "c2": (100_000, 30.0, 30_000, 0, 20260927, 0),
     "c3": (2_000_000, 1.2, 29_903, 1, 20260928, 1),
     "mid": (2_000_000, 30.0, 30_000, 0, 20260930, 0),
 }
+FAMILIES = {"snv40": 0, "leaf": 1, "ambig": 2}
+FAMILY_NAME = {v: k for k, v in FAMILIES.items()}
 
 
 def log(*a):
@@ -110,8 +113,8 @@ def measured_peak():
 
 
 def cpu_reference_rate(synth, calls_list, threads, target_seconds, log_prefix):
-    """Time the reference's own mapper2_body search (oracle/_ref) on this host's cores.
-    Returns (placements_per_s, description)."""
+    """Build the reference's own MAT::Tree (oracle/_ref) of the synthetic tree and pick the BFS stride at which one
+    two-pass mapper2_body search fits `target_seconds` on this host's cores.  Returns (tree, stride, estimate, n)."""
     from oracle import ref
     if not ref.available():
         raise RuntimeError("oracle/_ref/libusher_ref.so missing")
@@ -131,6 +134,17 @@ def cpu_reference_rate(synth, calls_list, threads, target_seconds, log_prefix):
     return rt, stride, est_full, n
 
 
+def cpu_bracket(rt, calls_list, true_best, stride, threads):
+    """Seconds per full reference search, bracketed (oracle/ref_driver.cpp usher_ref_search_strided2): a strided
+    visit with the reference's own initial bound over-states the stride-1 time (early exits fire late), the same
+    visit seeded with the TRUE best score under-states it.  Returns (lower_s, upper_s) per sample, averaged."""
+    lo, hi = [], []
+    for c, b in zip(calls_list, true_best):
+        hi.append(rt.search_strided(c, stride, 0, threads)[0] * stride)
+        lo.append(rt.search_strided(c, stride, 0, threads, seed_best=int(b))[0] * stride)
+    return float(np.mean(lo)), float(np.mean(hi))
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the reference's TBB-style CPU search (verbatim mapper2_body) on the host cores."""
     if rank != 0:
@@ -141,9 +155,13 @@ def run_reference(args, wl, rank, world):
     t = time.time()
     synth = capi.Synth(nodes, mu, L, shape, seed)
     log(f"[ref] synthetic MAT: {nodes} nodes, {synth.m} mutations in {time.time() - t:.1f}s")
+    if args.family:
+        fam = FAMILIES[args.family]
     sp, sc, _ = synth.samples(args.steps + args.warmup, fam, 777)
     calls = [sc[int(sp[i]):int(sp[i + 1])] for i in range(args.steps + args.warmup)]
     rt, stride, est_full, n = cpu_reference_rate(synth, calls, threads, 10.0, "[ref]")
+    if args.cpu_full_search:
+        stride = 1
     log(f"[ref] one full search ~{est_full:.1f}s on {threads} threads -> stride {stride}")
     for i in range(args.warmup):
         rt.search_strided(calls[i], stride, 0, threads)
@@ -164,7 +182,7 @@ def run_reference(args, wl, rank, world):
         "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": wl, "nodes": nodes, "mutations": int(synth.m), "genome_len": L,
-                   "sample_family": "snv40" if fam == 0 else "leaf", "threading": "std::thread shim of tbb::parallel_for"},
+                   "sample_family": FAMILY_NAME[fam], "threading": "std::thread shim of tbb::parallel_for"},
         "cpu_baseline": {"value": value, "unit": "placements/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -181,6 +199,10 @@ def main():
     ap.add_argument("--samples-per-rank", type=int, default=1280)
     ap.add_argument("--pass-samples", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--family", default=None, choices=sorted(FAMILIES), help="sample family (default: the workload's)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs' records (extra)")
+    ap.add_argument("--cpu-full-search", action="store_true",
+                    help="time full (stride 1) reference searches instead of a strided sample (minutes per sample at c4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -210,6 +232,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     nodes, mu, L, shape, seed, fam = WORKLOADS[wl]
+    if args.family:
+        fam = FAMILIES[args.family]
     t = time.time()
     synth = capi.Synth(nodes, mu, L, shape, seed)
     t_gen = time.time() - t
@@ -285,11 +309,8 @@ def main():
     value = world * B * args.steps / (ms_total / 1000.0)
     total_launches = sum_over_ranks(launches)
 
-    # parity spot check against an independent launch path (host-buffer API) on the last batch
-    sp, sc, _ = batches[-1]
-    chk = mat.place_batch(sp, sc)["placements"]
-    got = np.frombuffer(local.cpu().numpy().tobytes(), dtype=capi.PLACEMENT_DTYPE)
-    assert np.array_equal(chk, got), "resident and host-buffer paths disagree"
+    # the last batch's records, kept for the reference spot check below (outside every timed region)
+    last_records = np.frombuffer(local.cpu().numpy().tobytes(), dtype=capi.PLACEMENT_DTYPE).copy()
 
     # ------------------------------------------------------------------ end-to-end timing ("e2e")
     pinned = []
@@ -342,22 +363,94 @@ def main():
         "prep_ms": prep_ms, "reduce_ms": reduce_ms, "score_ms": score_ms,
     }
 
-    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    # ------------------------------------------------------------------ the other BASELINE configs (rank 0, N=1)
+    def time_family(m, syn, family, n_samples, pass_samples, reps, seed):
+        """placements/s, us per launch and roofline fraction of `reps` resident-batch place calls (CUDA events of the
+        library, same stream) for one (tree, sample family, pass width)."""
+        m.set_pass_samples(pass_samples)
+        spx, scx, _ = syn.samples(n_samples, family, seed)
+        S = m.upload(spx, scx)
+        for _ in range(2):
+            S.place(0, sync=True)
+        ms = sc_ms = 0.0
+        nl = by = 0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            S.place(0, sync=False)
+            e1.record()
+            tmx = m.timing()
+            ms += e0.elapsed_time(e1); sc_ms += tmx.score_ms; nl += tmx.score_launches; by += tmx.score_bytes
+        S.close()
+        calls_mean = float(np.diff(spx.astype(np.int64)).mean())
+        gbs = (by / 1e9) / (sc_ms / 1000.0)
+        return {"placements_per_s": n_samples * reps / (ms / 1000.0), "us_per_launch": 1000.0 * sc_ms / nl,
+                "samples_per_launch": pass_samples, "samples": n_samples, "launches": int(nl),
+                "achieved_gbs": gbs, "frac": gbs / peak, "mean_calls_per_sample": calls_mean,
+                "family": FAMILY_NAME[family]}, (spx, scx)
+
+    extra = None
+    extra_samples = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = {}
+        try:
+            for name, family in (("c4_snv40", 0), ("c4_leaf", 1), ("c5_ambig", 2)):
+                if family == fam or nodes != 10_000_000:
+                    continue
+                extra[name], extra_samples[family] = time_family(mat, synth, family, 256, 32, 3, 4242 + family)
+                log(f"[bench] extra {name}: {extra[name]}")
+            mat.set_pass_samples(args.pass_samples)
+            if wl != "c3":
+                n3, mu3, L3, shape3, seed3, fam3 = WORKLOADS["c3"]
+                syn3 = capi.Synth(n3, mu3, L3, shape3, seed3)
+                mat3 = capi.Mat.from_flat_struct(syn3.flat, device=local_rank)
+                mat3.set_stream(stream.cuda_stream)
+                extra["c3_256"], _ = time_family(mat3, syn3, fam3, 2048, 256, 3, 4250)
+                extra["c3_256"]["note"] = "2 M-node SARS-CoV-2-shaped MAT (41.6 MB, L2-resident), 256 samples per launch"
+                log(f"[bench] extra c3_256: {extra['c3_256']}")
+                mat3.close(); syn3.close()
+        except Exception as e:
+            extra["error"] = repr(e)
+
+    # ------------------------------------------------------------------ CPU baseline + reference spot check
+    # (rank 0, N=1 only; after every timed region).  The reference's own mapper2_body (oracle/_ref) checks the GPU
+    # results of this tree AT SIZE: whole optimal sets and per-node scores at the sets + 10^5 random nodes per sample.
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            from oracle import spotcheck
             threads = usable_cpus()
-            calls = [batches[0][1][int(batches[0][0][i]):int(batches[0][0][i + 1])] for i in range(2)]
-            rt, stride, est_full, n = cpu_reference_rate(synth, calls, threads, 8.0, "[bench]")
-            secs = [rt.search_strided(c, stride, 0, threads)[0] * stride for c in calls]
-            v = 1.0 / float(np.mean(secs))
-            cpu = {"value": v, "unit": "placements/s", "cores": threads, "kind": "reference",
+            sp0, sc0, _ = batches[-1]
+            calls = [sc0[int(sp0[i]):int(sp0[i + 1])] for i in range(2)]
+            rt, stride, est_full, n = cpu_reference_rate(synth, calls, threads, 6.0, "[bench]")
+            t = time.time()
+            parity = {"checked_against": "oracle/_ref mapper2_body (usher_ref_score_nodes)", "families": {}}
+            r = spotcheck.spot_check(mat, rt, sp0, sc0, [0, B - 1], 100_000, 1, threads, FAMILY_NAME[fam])
+            parity["families"][FAMILY_NAME[fam]] = r
+            for family, (spx, scx) in extra_samples.items():
+                parity["families"][FAMILY_NAME[family]] = spotcheck.spot_check(
+                    mat, rt, spx, scx, [7], 100_000, 2 + family, threads, FAMILY_NAME[family])
+            parity["ok"] = True
+            parity["seconds"] = time.time() - t
+            log(f"[bench] reference spot check ok: {parity}")
+            true_best = [int(last_records["score"][0]), int(last_records["score"][1])]
+            if args.cpu_full_search:
+                stride = 1
+            lo_s, hi_s = cpu_bracket(rt, calls, true_best, stride, threads)
+            cpu = {"value": 1.0 / lo_s, "unit": "placements/s", "cores": threads, "kind": "reference",
+                   "seconds_per_sample_lower": lo_s, "seconds_per_sample_upper": hi_s, "stride": stride,
                    "sample": f"{len(calls)} samples x every {stride}-th BFS node of the {n}-node tree, reference two-pass "
-                             f"search (verbatim mapper2_body, std::thread shim of tbb::parallel_for), seconds x {stride}"}
+                             f"search (verbatim mapper2_body, std::thread shim of tbb::parallel_for, not oneTBB), seconds x "
+                             f"{stride}; value = the faster end of the bracket (running best seeded with the true best "
+                             f"score, so early exits fire at least as often as in a stride-1 search); upper = the "
+                             f"reference's own initial bound"}
             rt.close()
+        except AssertionError:
+            raise
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
             cpu = {"value": None, "unit": "placements/s", "cores": os.cpu_count(), "kind": "reference",
-                   "sample": f"unavailable: {e}"}
+                   "sample": f"unavailable: {e!r}"}
 
     if rank == 0:
         line = {
@@ -365,13 +458,13 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": wl, "nodes": nodes, "mutations": int(synth.m), "genome_len": L,
-                       "sample_family": "snv40" if fam == 0 else "leaf", "samples_per_rank_per_step": B,
+                       "sample_family": FAMILY_NAME[fam], "samples_per_rank_per_step": B,
                        "samples_per_launch": args.pass_samples, "parallelism": f"samples sharded x{world}, 1 allgather/step",
                        "l2": "inputs (%.2f GB MAT) exceed the 126 MB L2; no flush needed" % (mat.info.algorithmic_bytes / 1e9)},
             "e2e": {"value": e2e_value, "unit": "placements/s", "h2d_bytes_per_step": int(h2d / args.steps),
                     "d2h_bytes_per_step": int(d2h / args.steps)},
             "gpu_launches": int(total_launches),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "extra": extra, "parity_at_size": parity,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -52,6 +52,10 @@ def lib():
         L.usher_ref_condensed_export.argtypes = [vp, vp, u64]
         L.usher_ref_search_strided.restype = C.c_double
         L.usher_ref_search_strided.argtypes = [vp, u64, vp, u32, u32, C.c_int, vp]
+        L.usher_ref_search_strided2.restype = C.c_double
+        L.usher_ref_search_strided2.argtypes = [vp, u64, vp, u32, u32, C.c_int, C.c_int32, vp]
+        L.usher_ref_score_nodes.restype = C.c_int
+        L.usher_ref_score_nodes.argtypes = [vp, u64, vp, u64, vp, C.c_int, vp, vp]
         _lib = L
     return _lib
 
@@ -126,12 +130,27 @@ class RefTree:
             self.h, outdir.encode(), threads, int(print_parsimony_scores), int(no_add)
         )
 
-    def search_strided(self, calls, stride, offset=0, threads=1):
-        """Seconds the reference's two-pass search of one sample takes over every `stride`-th BFS node."""
+    def search_strided(self, calls, stride, offset=0, threads=1, seed_best=-1):
+        """Seconds the reference's two-pass search of one sample takes over every `stride`-th BFS node.  With
+        seed_best >= 0 the running best starts from the (known) true best score: see usher_ref_search_strided2."""
         calls = np.ascontiguousarray(calls, dtype=MUT_DTYPE)
         best = C.c_int32()
-        sec = lib().usher_ref_search_strided(self.h, len(calls), _p(calls), stride, offset, threads, C.byref(best))
+        sec = lib().usher_ref_search_strided2(self.h, len(calls), _p(calls), stride, offset, threads, int(seed_best),
+                                              C.byref(best))
         return float(sec), int(best.value)
+
+    def score_nodes(self, calls, dfs_nodes, threads=1):
+        """The reference's -p score (mapper2_body(inp, true, false); +1 on invalid nodes) of one sample at the
+        listed DFS nodes of a from_flat tree, and per node 0 = not a valid placement, 1 = valid, 3 = valid with
+        has_unique (sibling placement)."""
+        calls = np.ascontiguousarray(calls, dtype=MUT_DTYPE)
+        nodes = np.ascontiguousarray(dfs_nodes, dtype=np.uint32)
+        out = np.zeros(len(nodes), np.int32)
+        valid = np.zeros(len(nodes), np.uint8)
+        rc = lib().usher_ref_score_nodes(self.h, len(calls), _p(calls), len(nodes), _p(nodes), threads, _p(out), _p(valid))
+        if rc != 0:
+            raise ValueError("usher_ref_score_nodes: node index out of range")
+        return out, valid
 
     def search(self, s_ptr, sm, n_nodes, threads=1, per_node=False, want_set=True, set_cap=None):
         """Reference two-pass search (or -p single pass when per_node) of each sample on the frozen tree."""

@@ -37,6 +37,7 @@ namespace {
 struct RefTree {
     MAT::Tree T;
     std::vector<Missing_Sample> samples;
+    std::vector<MAT::Node*> bfs_cache, dfs_cache;   // usher_ref_score_nodes: DFS expansion of a frozen from_flat tree
 };
 
 // What save_mutation_annotated_tree + load_mutation_annotated_tree do to a tree
@@ -334,10 +335,20 @@ int usher_ref_search(void* hv, uint32_t n_samples, const uint64_t* s_ptr, const 
 
 // Timing aid for trees where one full search is minutes of CPU: run the reference's two-pass search of ONE
 // sample over every `stride`-th BFS node (k = offset, offset+stride, ...) with `threads` workers and return
-// the seconds spent.  mapper2_body's cost per node does not depend on which other nodes are visited (its
-// work before the early-exit tests is the ancestor gather), so seconds*stride estimates the full search.
+// the seconds spent.  seconds*stride only ESTIMATES the full search: the ancestor gather of a node costs the same
+// whichever nodes are visited, but the early exits depend on the best found so far (see _strided2).
+double usher_ref_search_strided2(void* hv, uint64_t n_calls, const ref_mut* sm, uint32_t stride, uint32_t offset,
+                                 int threads, int32_t seed_best, int32_t* best_score_seen);
 double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, uint32_t stride, uint32_t offset,
                                 int threads, int32_t* best_score_seen) {
+    return usher_ref_search_strided2(hv, n_calls, sm, stride, offset, threads, -1, best_score_seen);
+}
+// seed_best >= 0: the running best starts from min(reference's initial bound, seed_best).  A strided visit finds
+// its best later than the full search does, so its early exits (src/usher_mapper.cpp:383,437) fire less often and
+// seconds*stride OVER-states the full search; seeded with the true best score they fire at least as often as in
+// the full search and seconds*stride UNDER-states it.  The two bracket the stride-1 time.
+double usher_ref_search_strided2(void* hv, uint64_t n_calls, const ref_mut* sm, uint32_t stride, uint32_t offset,
+                                 int threads, int32_t seed_best, int32_t* best_score_seen) {
     auto* h = (RefTree*)hv;
     MAT::Tree* T = &h->T;
     tbb::oracle_threads = threads < 1 ? 1 : threads;
@@ -351,9 +362,9 @@ double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, u
         m.is_missing = sm[k].is_missing != 0;
         sample.push_back(m);
     }
-    static std::vector<MAT::Node*> bfs;   // the O(N) expansion is done once per tree, outside the timed part
-    static MAT::Tree* bfs_of = nullptr;
-    if (bfs_of != T) { bfs = T->breadth_first_expansion(); bfs_of = T; }
+    // the O(N) expansion is done once per (frozen) tree, outside the timed part
+    if (h->bfs_cache.empty()) h->bfs_cache = T->breadth_first_expansion();
+    const std::vector<MAT::Node*>& bfs = h->bfs_cache;
     if (stride < 1) stride = 1;
     const size_t total_nodes = bfs.size();
     const size_t visits = (total_nodes > offset) ? (total_nodes - offset + stride - 1) / stride : 0;
@@ -363,6 +374,7 @@ double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, u
     std::vector<std::vector<MAT::Mutation>> node_imputed_mutations(visits + 1);
     size_t best_node_num_leaves = 0;
     int best_set_difference = (int)(sample.size() + T->root->mutations.size() + 1);
+    if (seed_best >= 0 && seed_best < best_set_difference) best_set_difference = seed_best;
     size_t best_j = 0;
     bool best_node_has_unique = false;
     std::vector<bool> node_has_unique(total_nodes, false);
@@ -405,6 +417,66 @@ double usher_ref_search_strided(void* hv, uint64_t n_calls, const ref_mut* sm, u
     auto t1 = std::chrono::steady_clock::now();
     if (best_score_seen) *best_score_seen = best_set_difference;
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// -p semantics at a LIST of nodes: mapper2_body(inp, true, false) of ONE sample at the nodes whose DFS indices
+// are given (the tree must come from usher_ref_tree_from_flat, whose DFS order is the flat order).  scores_out[i]
+// = the reported score of dfs_nodes[i] (score+1 on invalid nodes, src/usher_mapper.cpp:448-450,498-503).  Used by
+// bench.py / tests to spot-check 10M-node results without a full O(N) reference search.
+int usher_ref_score_nodes(void* hv, uint64_t n_calls, const ref_mut* sm, uint64_t n_list, const uint32_t* dfs_nodes,
+                          int threads, int32_t* scores_out, uint8_t* valid_out) {
+    auto* h = (RefTree*)hv;
+    MAT::Tree* T = &h->T;
+    tbb::oracle_threads = threads < 1 ? 1 : threads;
+    if (h->dfs_cache.empty()) h->dfs_cache = T->depth_first_expansion();
+    const std::vector<MAT::Node*>& dfs = h->dfs_cache;
+    std::vector<MAT::Mutation> sample;
+    for (uint64_t k = 0; k < n_calls; k++) {
+        MAT::Mutation m;
+        m.position = sm[k].position;
+        m.ref_nuc = (int8_t)sm[k].ref_nuc;
+        m.par_nuc = (int8_t)sm[k].par_nuc;
+        m.mut_nuc = (int8_t)sm[k].mut_nuc;
+        m.is_missing = sm[k].is_missing != 0;
+        sample.push_back(m);
+    }
+    for (uint64_t i = 0; i < n_list; i++)
+        if (dfs_nodes[i] >= dfs.size()) return -1;
+    tbb::parallel_for(tbb::blocked_range<size_t>(0, (size_t)n_list), [&](tbb::blocked_range<size_t> r) {
+        // a fresh best-state per node: the per-node score does not depend on it when compute_parsimony_scores
+        // is true (no early exit, src/usher_mapper.cpp:383,437), and a node is a VALID placement exactly when the
+        // call folds it into that fresh state (src/usher_mapper.cpp:454-468)
+        for (size_t q = r.begin(); q < r.end(); ++q) {
+            size_t best_node_num_leaves = 0, best_j = 0, num_best = 1;
+            int best_set_difference = 1 << 30;
+            bool best_node_has_unique = false;
+            MAT::Node* best_node = T->root;
+            std::vector<size_t> best_j_vec;
+            std::vector<bool> node_has_unique(1, false);
+            std::vector<MAT::Mutation> excess, imputed;
+            int sd = 0;
+            mapper2_input inp;
+            inp.T = T;
+            inp.node = dfs[dfs_nodes[q]];
+            inp.missing_sample_mutations = &sample;
+            inp.excess_mutations = &excess;
+            inp.imputed_mutations = &imputed;
+            inp.best_node_num_leaves = &best_node_num_leaves;
+            inp.best_set_difference = &best_set_difference;
+            inp.best_node = &best_node;
+            inp.best_j = &best_j;
+            inp.num_best = &num_best;
+            inp.j = 0;
+            inp.has_unique = &best_node_has_unique;
+            inp.set_difference = &sd;
+            inp.best_j_vec = &best_j_vec;
+            inp.node_has_unique = &node_has_unique;
+            mapper2_body(inp, true, false);
+            scores_out[q] = sd;
+            if (valid_out) valid_out[q] = best_set_difference != (1 << 30) ? (best_node_has_unique ? 3 : 1) : 0;
+        }
+    });
+    return 0;
 }
 
 // condensed_nodes of the tree as text: one line per node, "name\tmember1,member2,...\n"

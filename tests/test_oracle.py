@@ -59,3 +59,24 @@ def test_port_matches_reference_random(seed):
                           pt.search(s_ptr, calls, per_node=True)["node_scores"])
     rt.close()
     pt.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("path", common.golden_cases()[::4], ids=lambda p: p.split("/")[-1])
+def test_reference_score_nodes_matches_golden(path):
+    """usher_ref_score_nodes (the at-size spot checker, oracle/spotcheck.py): the reference's per-node score and
+    validity at a node list equal the golden -p scores and the golden optimal sets."""
+    g = common.load(path)
+    n = len(g["parent"])
+    rt = ref.RefTree.from_flat(g["parent"], g["row_ptr"], g["muts"])
+    nodes = np.arange(n, dtype=np.uint32)[::-1].copy()
+    for s in range(min(6, len(g["s_ptr"]) - 1)):
+        c = g["calls"][int(g["s_ptr"][s]):int(g["s_ptr"][s + 1])]
+        sc, valid = rt.score_nodes(c, nodes, threads=1 + s % 3)
+        assert np.array_equal(sc, g["exp_node_scores"][s][nodes])
+        opt = np.sort(nodes[(valid != 0) & (sc == g["exp_score"][s])])
+        lo, hi = int(g["exp_best_set_ptr"][s]), int(g["exp_best_set_ptr"][s + 1])
+        assert np.array_equal(opt, g["exp_best_set"][lo:hi])
+        u = {int(a): int(b) for a, b in zip(nodes, (valid >> 1) & 1)}
+        assert [u[int(a)] for a in g["exp_best_set"][lo:hi]] == g["exp_best_set_unique"][lo:hi].tolist()
+    rt.close()

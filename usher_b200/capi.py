@@ -48,7 +48,8 @@ class DerivedView(C.Structure):
                                   "hdr", "ref_of", "tile_start", "anc_ptr", "anc")] + [
         ("n_tiles3", C.c_uint32), ("n_seed_segs", C.c_uint32), ("narrow3", C.c_uint32), ("reserved3", C.c_uint32),
         ("stream_words", C.c_uint64)] + [
-        (k, C.c_void_p) for k in ("stream", "hdr3", "tile3_start", "tile3_w0", "tile3_lvl", "tile3_sseg", "seed_end", "blk_words")]
+        (k, C.c_void_p) for k in ("stream", "hdr3", "tile3_start", "tile3_w0", "tile3_lvl", "tile3_sseg", "seed_end", "blk_words",
+                                  "blk_rec", "tile3_min")]
 
 
 class UB200Error(RuntimeError):
@@ -181,6 +182,8 @@ def debug_derive(parent, row_ptr, muts, tie_index=None, target_tiles=64, min_til
             "tile3_sseg": _view(v.tile3_sseg, np.uint32, T3 + 1).copy(),
             "seed_end": _view(v.seed_end, np.uint32, v.n_seed_segs).copy(),
             "blk_words": _view(v.blk_words, np.uint32, (n + 31) // 32).copy(),
+            "blk_rec": _view(v.blk_rec, np.uint32, 4 * ((n + 31) // 32)).copy().reshape(-1, 4),
+            "tile3_min": _view(v.tile3_min, np.int32, T3).copy(),
         })
     lib().ub200_debug_derive_free(h)
     return out

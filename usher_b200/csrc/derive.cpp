@@ -133,18 +133,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         }
         pc.seed_words = out.size();
         for (uint32_t b = n0; b < n1; b += 32) {
-            // The scanner takes a segment in steps of 4 absolute 128-word rows.  If starting here costs a step
-            // more than starting on a row boundary would, pad up to the boundary (the pad words are appended
-            // to the previous segment; ~2 % of the stream at C4, and every block then takes 2 steps, not 2.4).
             const uint32_t e = std::min(n1, b + 32);
-            const size_t len4 = ((size_t)(d.row32[e] - d.row32[b]) + 3) & ~(size_t)3;
-            const size_t off = out.size() % 128;
-            if (off && ((off + len4 + 127) / 128 + 3) / 4 > ((len4 + 127) / 128 + 3) / 4) {
-                const size_t padw = 128 - off;
-                out.resize(out.size() + padw, pad);
-                if (b > n0) d.blk_words[(b >> 5) - 1] += (uint32_t)padw;
-                else if (lvl0) pc.seed_end4.back() += (uint32_t)(padw / 4);
-            }
             const size_t s0 = out.size();
             for (uint32_t i = b; i < e; i++)
                 for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) seg.push_back(conv(d.mutw[k], i & 31u));
@@ -183,6 +172,42 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     }
     d.tile3_w0[T] = (uint32_t)(w / kChunk3);
     d.seed_end.push_back(0);   // never empty
+    // ---- block records + static bounds (tile-local subtree minima of G - nmut)
+    {
+        std::vector<int32_t> sub(n);
+        for (uint32_t i = 0; i < n; i++) sub[i] = d.hdr3[i].g - (int32_t)(d.hdr3[i].nmut_c0 >> 16);
+        std::vector<int32_t> own(sub);
+        d.tile3_min.assign(T, 0);
+        d.blk_rec.assign((size_t)nblk * 4, 0);
+        for (size_t t = 0; t < T; t++) {
+            const uint32_t n0 = d.tile3_start[t], n1 = d.tile3_start[t + 1];
+            // reverse DFS order: a node's subtree minimum is complete before it is folded into its parent;
+            // parents outside the tile are not touched (tile-local bound)
+            for (uint32_t i = n1; i-- > n0;) {
+                const int32_t p = f.parent[i];
+                if (p >= (int32_t)n0) sub[p] = std::min(sub[p], sub[i]);
+            }
+            int32_t tmin = INT32_MAX;
+            for (uint32_t b = n0; b < n1; b += 32) {
+                const uint32_t e = std::min(n1, b + 32);
+                int32_t omin = INT32_MAX, smin = INT32_MAX;
+                uint32_t open = 0, lv0 = 0;
+                for (uint32_t i = b; i < e; i++) {
+                    omin = std::min(omin, own[i]);
+                    smin = std::min(smin, sub[i]);
+                    if (d.hdr3[i].level_flags & kFlagOpen) {
+                        if (!open) lv0 = d.level[i];
+                        open |= 1u << (i & 31);
+                    }
+                }
+                uint32_t* r = &d.blk_rec[(size_t)(b >> 5) * 4];
+                r[0] = (uint32_t)omin; r[1] = (uint32_t)smin; r[2] = open;
+                r[3] = (lv0 << 14) | d.blk_words[b >> 5];
+                tmin = std::min(tmin, omin);
+            }
+            d.tile3_min[t] = tmin;
+        }
+    }
 }
 
 int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::string& err, uint32_t min_tile_cost) {
@@ -406,6 +431,7 @@ struct ub200_derived_view {
     uint64_t stream_words;
     const uint32_t* stream; const void* hdr3; const uint32_t* tile3_start; const uint32_t* tile3_w0;
     const uint32_t* tile3_lvl; const uint32_t* tile3_sseg; const uint32_t* seed_end; const uint32_t* blk_words;
+    const uint32_t* blk_rec; const int32_t* tile3_min;
 };
 
 int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32_t min_tile_cost, void** handle,
@@ -432,6 +458,7 @@ int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32
     view->tile3_w0 = d->tile3_w0.data(); view->tile3_lvl = d->tile3_lvl.data();
     view->tile3_sseg = d->tile3_sseg.data(); view->seed_end = d->seed_end.data();
     view->blk_words = d->blk_words.data();
+    view->blk_rec = d->blk_rec.data(); view->tile3_min = d->tile3_min.data();
     *handle = d;
     return UB200_OK;
 }

@@ -241,7 +241,11 @@ def main():
     mat = capi.Mat.from_flat_struct(synth.flat, device=local_rank)
     t_create = time.time() - t
     mat.set_pass_samples(args.pass_samples)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch, NCCL and the library: CUDA events recorded through torch then see
+    # the library's kernels (handle 0 would make the library fall back to its own stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     mat.set_stream(stream.cuda_stream)
     if rank == 0:
         log(f"[bench] {wl}: {nodes} nodes, {synth.m} mutations; generate {t_gen:.1f}s, flatten+upload {t_create:.1f}s, "

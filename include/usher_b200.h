@@ -119,8 +119,11 @@ void ub200_mat_destroy(ub200_mat* mat);
 int ub200_mat_info_get(const ub200_mat* mat, ub200_mat_info* out);
 /* Host copies of the derived per-node arrays (any pointer may be NULL). */
 int ub200_mat_node_arrays(const ub200_mat* mat, uint32_t* bfs_index, uint32_t* num_leaves, uint32_t* level);
-/* Tunables: samples scored per pass over the tree (multiple of 32, 32..256; 0 = default). */
+/* Tunables: samples scored per pass (= launch) over the tree (multiple of 32, 32..768; 0 = default 32), and how
+ * many groups of 32 samples share one scan of the mutation stream inside a pass (1..3; 0 = chosen from the pass
+ * width: the scan is sample-independent, so wide passes share it three ways). */
 int ub200_mat_set_pass_samples(ub200_mat* mat, uint32_t samples_per_pass);
+int ub200_mat_set_scan_sharing(ub200_mat* mat, uint32_t groups_per_scan);
 
 /* The batched replacement of the search loop.  Host buffers in, host buffers out; H2D/D2H inside.
  *   sample_ptr[n_samples+1], sample_calls[sample_ptr[n_samples]]: CSR of Missing_Sample::mutations,

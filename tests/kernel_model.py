@@ -133,6 +133,12 @@ def place3(d, s_ptr, calls):
                 seglen = sum(int(hdr[i]["nmut_c0"]) >> 16 for i in nodes)
                 o1 = o0 + ((seglen + 3) & ~3)
                 assert int(d["blk_words"][blk >> 5]) == o1 - o0   # what the scanner warp reads instead of headers
+                # block record (k_score4 consumer): min(G - nmut), open-chain mask, level of the first open node
+                rec = d["blk_rec"][blk >> 5]
+                assert int(np.int32(rec[0])) == min(int(hdr[i]["g"]) - (int(hdr[i]["nmut_c0"]) >> 16) for i in nodes)
+                opens = [i for i in nodes if int(hdr[i]["level_flags"]) & F_OPEN]
+                assert int(rec[1]) == sum(1 << (i & 31) for i in opens) and int(rec[3]) == o1 - o0
+                assert not opens or int(rec[2]) == int(hdr[opens[0]]["level_flags"]) >> 14
                 dl = seg_deltas(o0, o1)
                 o0 = o1
 
@@ -186,158 +192,3 @@ def place3(d, s_ptr, calls):
                     "num_best": cnt, "has_unique": best[2], "optimal": sorted(optimal)})
     return res
 
-
-def place4(d, s_ptr, calls, root_row_len, workers=3, seed=0, collect_target=None):
-    """Model of k_score4 (usher_b200/csrc/score_kernel4.cuh) INCLUDING its pruning: tile skip (tile3_min), static
-    block skip (blk_rec sub_min + per-sample cmin), the exact block bound (own_min + gmin + neg) and the
-    running-best bound shared between workers through gbest.  Tiles are handed to `workers` independent workers in
-    a shuffled order, as the GPU's warp pairs take them from a counter; the fold over workers is the kernel's.
-    With collect_target (per-sample best score relative to base) it returns the optimal sets instead (second pass)."""
-    import random
-    n, L = d["n"], d["L"]
-    hdr, stream, rec = d["hdr3"], d["stream"], d["blk_rec"]
-    ts, w0, lvl, sseg, send = d["tile3_start"], d["tile3_w0"], d["tile3_lvl"], d["tile3_sseg"], d["seed_end"]
-    F_HU0, F_OPEN = 16, 32
-    B = len(s_ptr) - 1
-    sh = 16 if d["narrow3"] else 14
-    out = []
-    for g0 in range(0, B, 32):
-        S = list(range(g0, min(B, g0 + 32)))
-        tabs, base, cmin, gbest = {}, {}, {}, {}
-        for s in S:
-            tab, b, cm = {}, 0, 0
-            for k in range(int(s_ptr[s]), int(s_ptr[s + 1])):
-                c = calls[k]
-                st, ref = int(c["mut_nuc"]) & 15, int(c["ref_nuc"])
-                if not c["is_missing"] and (st & ref) == 0:
-                    b += 1
-                if int(c["position"]) < L:
-                    tab[int(c["position"])] = (0 if c["is_missing"] else (~st & 15), ref.bit_length() - 1)
-                    cm -= 1 if c["is_missing"] else (int((st & ~ref) != 0) + int((st & ref) == 0))
-            tabs[s], base[s], cmin[s] = tab, b, cm
-            gbest[s] = (int(s_ptr[s + 1]) - int(s_ptr[s])) + root_row_len + 1 - b
-        W = [{s: [0x7fffffff if collect_target is None else int(collect_target[s]), None, 0] for s in S}
-             for _ in range(workers)]
-        sets = {s: [] for s in S}
-        order = list(range(len(ts) - 1))
-        random.Random(seed + g0).shuffle(order)
-
-        def deltas(o0, o1):
-            dl = {}
-            for k in range(o0, o1):
-                w = int(stream[k])
-                pos = ((w >> sh) << 5) | (w & 31)
-                for s in S:
-                    e = tabs[s].get(pos)
-                    if e is None:
-                        continue
-                    e, refc = e
-                    nl, prevc, mutc = (w >> 9) & 31, (w >> 7) & 3, (w >> 5) & 3
-                    rm, rp = int(mutc != refc), int(prevc != refc)
-                    wm, wp = (e >> mutc) & 1, (e >> prevc) & 1
-                    tk, t0 = wm ^ 1, rm ^ 1
-                    a = dl.setdefault((nl, s), [0, 0, 0, 0])
-                    dc = (wm - wp) - (rm - rp)
-                    a[0] += dc
-                    a[1] += (tk & wp) - (t0 & rp)
-                    a[2] += tk - t0
-                    a[3] += min(dc, 0)
-            return dl
-
-        for ti, t in enumerate(order):
-            me = W[ti % workers]
-            n0, n1 = int(ts[t]), int(ts[t + 1])
-            bound = {s: (me[s][0] if collect_target is not None else min(me[s][0], gbest[s])) for s in S}
-            if not any(int(d["tile3_min"][t]) + cmin[s] <= bound[s] for s in S):
-                continue
-            o0 = int(w0[t]) * 256
-            stack = {s: {} for s in S}
-            gmin = {s: 0 for s in S}
-            lvl0 = int(lvl[t])
-            for gi, l0 in enumerate(range(0, lvl0, 32)):
-                o1 = int(send[int(sseg[t]) + gi]) * 4
-                dl = deltas(o0, o1)
-                o0 = o1
-                for s in S:
-                    v = stack[s][l0 - 1] if l0 else 0
-                    for j in range(min(32, lvl0 - l0)):
-                        v += dl.get((j, s), [0, 0, 0, 0])[0]
-                        stack[s][l0 + j] = v
-                        gmin[s] = min(gmin[s], v)
-            for blk in range(n0, n1, 32):
-                r = rec[blk >> 5]
-                own = int(np.int32(r[0])); sub = int(np.int32(r[1])); openm = int(r[2])
-                lv0, words = int(r[3]) >> 14, int(r[3]) & 0x3fff
-                o1 = o0 + words
-                bnd = {s: (me[s][0] if collect_target is not None else min(me[s][0], gbest[s])) for s in S}
-                if not any(sub + cmin[s] <= bnd[s] for s in S):
-                    o0 = o1
-                    # rows of a skipped block must never be read again: poison them
-                    lv = lv0
-                    for a in range(32):
-                        if (openm >> a) & 1:
-                            for s in S:
-                                stack[s][lv] = None
-                            lv += 1
-                    continue
-                dl = deltas(o0, o1)
-                o0 = o1
-                nodes = range(blk, min(blk + 32, n1))
-                neg = {s: sum(v[3] for (nl, ss), v in dl.items() if ss == s) for s in S}
-                needs = [s for s in S if own + gmin[s] + neg[s] <= bnd[s]]
-                for s in needs:
-                    for i in nodes:
-                        h = hdr[i]
-                        flags = int(h["level_flags"]) & 0x3FFF
-                        level, am = int(h["level_flags"]) >> 14, int(h["tiekey"])
-                        nmut, c0 = int(h["nmut_c0"]) >> 16, int(h["nmut_c0"]) & 0xFFFF
-                        dcorr, da, dcom, _ = dl.get((i & 31, s), [0, 0, 0, 0])
-                        root, masked = bool(flags & F_ROOT), bool(flags & F_MASKED)
-                        if masked:
-                            da = dcom = 0
-                        top = level - bin(am).count("1")
-                        v = stack[s][top - 1] if top else 0
-                        for a in range(32):
-                            if (am >> a) & 1:
-                                v += dl.get((a, s), [0, 0, 0, 0])[0]
-                        sc = int(h["g"]) + dcorr if root else int(h["g"]) + v - da
-                        common = c0 + dcom
-                        hu = (not root) and (masked or nmut > common)
-                        valid = root or ((common > 0) if (flags & F_LEAF) else ((not hu) or common > 0))
-                        assert sc >= own + gmin[s] + neg[s], "block bound violated"
-                        if not valid:
-                            continue
-                        if collect_target is not None:
-                            if sc == me[s][0]:
-                                sets[s].append((i, int(hu)))
-                            continue
-                        if sc <= me[s][0]:
-                            key = (sc, int(d["tiekey"][i]), int(hu))
-                            if sc < me[s][0]:
-                                me[s] = [sc, key, 1]
-                            else:
-                                me[s][2] += 1
-                                if key < me[s][1]:
-                                    me[s][1] = key
-                lv = lv0
-                for a in range(32):
-                    if (openm >> a) & 1:
-                        assert int(hdr[blk + a]["level_flags"]) >> 14 == lv
-                        for s in S:
-                            v = (stack[s][lv - 1] if lv else 0) + dl.get((a, s), [0, 0, 0, 0])[0]
-                            stack[s][lv] = v
-                            gmin[s] = min(gmin[s], v)
-                        lv += 1
-            if collect_target is None:
-                for s in S:
-                    gbest[s] = min(gbest[s], me[s][0])
-        for s in S:
-            if collect_target is not None:
-                out.append(sorted(sets[s]))
-                continue
-            best = min(w[s][1] for w in W if w[s][1] is not None)
-            cnt = sum(w[s][2] for w in W if w[s][1] is not None and w[s][0] == best[0])
-            node = int(d["key_to_node"][best[1]])
-            out.append({"score": best[0] + base[s], "rel": best[0], "best_node": node,
-                        "best_j": int(d["tie_index"][node]), "num_best": cnt, "has_unique": best[2]})
-    return out

@@ -49,7 +49,7 @@ class DerivedView(C.Structure):
         ("n_tiles3", C.c_uint32), ("n_seed_segs", C.c_uint32), ("narrow3", C.c_uint32), ("reserved3", C.c_uint32),
         ("stream_words", C.c_uint64)] + [
         (k, C.c_void_p) for k in ("stream", "hdr3", "tile3_start", "tile3_w0", "tile3_lvl", "tile3_sseg", "seed_end", "blk_words",
-                                  "blk_rec", "tile3_min")]
+                                  "blk_rec")]
 
 
 class UB200Error(RuntimeError):
@@ -66,7 +66,7 @@ EXPORTS = [
     "ub200_mat_info_get", "ub200_mat_node_arrays", "ub200_mat_set_pass_samples", "ub200_place_batch",
     "ub200_samples_upload", "ub200_samples_free", "ub200_place_resident", "ub200_results_download",
     "ub200_results_device_ptr", "ub200_node_scores_download", "ub200_best_set_download", "ub200_mat_set_stream",
-    "ub200_mat_synchronize", "ub200_last_timing", "ub200_results_copy_device",
+    "ub200_mat_synchronize", "ub200_last_timing", "ub200_results_copy_device", "ub200_mat_set_scan_sharing",
 ]
 
 
@@ -84,6 +84,7 @@ def lib():
         L.ub200_mat_info_get.argtypes = [vp, C.POINTER(MatInfo)]
         L.ub200_mat_node_arrays.argtypes = [vp, vp, vp, vp]
         L.ub200_mat_set_pass_samples.argtypes = [vp, u32]
+        L.ub200_mat_set_scan_sharing.argtypes = [vp, u32]
         L.ub200_place_batch.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, u64]
         L.ub200_samples_upload.argtypes = [vp, u32, vp, vp, C.POINTER(vp)]
         L.ub200_samples_free.argtypes = [vp]
@@ -183,7 +184,6 @@ def debug_derive(parent, row_ptr, muts, tie_index=None, target_tiles=64, min_til
             "seed_end": _view(v.seed_end, np.uint32, v.n_seed_segs).copy(),
             "blk_words": _view(v.blk_words, np.uint32, (n + 31) // 32).copy(),
             "blk_rec": _view(v.blk_rec, np.uint32, 4 * ((n + 31) // 32)).copy().reshape(-1, 4),
-            "tile3_min": _view(v.tile3_min, np.int32, T3).copy(),
         })
     lib().ub200_debug_derive_free(h)
     return out
@@ -223,6 +223,9 @@ class Mat:
 
     def set_pass_samples(self, n):
         _check(lib().ub200_mat_set_pass_samples(self.h, n))
+
+    def set_scan_sharing(self, groups_per_scan):
+        _check(lib().ub200_mat_set_scan_sharing(self.h, groups_per_scan))
 
     def set_stream(self, cuda_stream_ptr):
         _check(lib().ub200_mat_set_stream(self.h, cuda_stream_ptr))

@@ -11,7 +11,7 @@
 #include <cstdlib>
 
 #include "score_kernel.cuh"
-#include "score_kernel3.cuh"
+#include "score_kernel4.cuh"
 #include "ub200_internal.h"
 #include "usher_b200.h"
 
@@ -51,7 +51,8 @@ struct ub200_mat {
     // device: k_score3 layout (always resident when the genome fits its 23-bit position field)
     uint32_t* mstream = nullptr;
     ub200::NodeHdr* hdr3 = nullptr;
-    uint32_t *blk_words = nullptr;
+    uint32_t *blk_words = nullptr, *blk_rec = nullptr;
+    uint32_t consumers = 0;     // sample groups per scanner (k_score4 NC); 0 = chosen per pass
     uint32_t *tiekey = nullptr, *tile3_start = nullptr, *tile3_w0 = nullptr, *tile3_lvl = nullptr, *tile3_sseg = nullptr,
              *seed_end = nullptr;
     int32_t* gstack3 = nullptr;
@@ -197,49 +198,69 @@ int ensure_v1(ub200_mat* M) {
     return 0;
 }
 
-// Streaming best-placement kernel (score_kernel3.cuh): one CTA of 16 scanner/consumer warp pairs per SM.
-int launch_score3(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, uint32_t* grid_out,
-                  bool collect = false) {
+// Consumers per scanner (NC) for a pass of `ng` sample groups: the scan of the mutation stream is shared by NC
+// groups, so wide passes want NC = 3 and a single group NC = 1.
+uint32_t pick_consumers(const ub200_mat* M, uint32_t ng) {
+    uint32_t nc = M->consumers;
+    if (const char* e = getenv("UB200_NC")) nc = (uint32_t)atoi(e);
+    if (nc == 0) nc = ng >= 3 ? 3u : ng;
+    return std::max(1u, std::min(nc, std::min(ng, 3u)));
+}
+
+// Streaming best-placement kernel (score_kernel4.cuh): one CTA of scanner + NC consumer warp units per SM.
+template <int NC>
+int launch_score4_nc(ub200_mat* M, ub200_samples* S, const ub200::Score4Params& p, uint32_t grid, bool collect) {
     using namespace ub200;
-    Score3Params p;
-    p.stream = M->mstream; p.hdr = M->hdr3; p.tiekey = M->tiekey;
-    p.tile_start = M->tile3_start; p.tile_w0 = M->tile3_w0; p.tile_lvl = M->tile3_lvl; p.tile_sseg = M->tile3_sseg;
-    p.seed_end = M->seed_end; p.blk_words = M->blk_words;
-    p.n_nodes = M->n; p.n_tiles = M->n_tiles3; p.L = M->L;
-    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap; p.tab = S->tab; p.gbest = S->gbest;
-    p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups;
-    p.part_key = S->part_key; p.part_cnt = S->part_cnt;
-    p.gstack = M->gstack3; p.gstack_levels = M->gstack3_levels;
-    p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
-    p.tile_counter = S->tile_counter;
-    CU(cudaMemsetAsync(S->tile_counter, 0, 64, M->stream));
-    const uint32_t grid = std::max<uint32_t>(ngroups, ((uint32_t)M->num_sms / ngroups) * ngroups);
-    *grid_out = grid;
-    const uint32_t fixed = kLut3Bytes + (uint32_t)kPairs3 * kWarpSmem3;
+    using C = Cfg4<NC>;
     const uint32_t bm_need = (S->bitmap_words * 4u + 127u) & ~127u;
-    const bool smem_bitmap = fixed + bm_need <= kSmemLimit3;
-    const size_t smem = fixed + (smem_bitmap ? bm_need : 0u);
+    const bool smem_bitmap = C::kFixed + bm_need <= kSmemLimit4;
+    const size_t smem = C::kFixed + (smem_bitmap ? bm_need : 0u);
     auto go = [&](auto k) -> int {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kThreads3, smem, M->stream>>>(p);
+        k<<<grid, C::kThreads, smem, M->stream>>>(p);
         return 0;
     };
     int rc;
     if (M->d.narrow3) {
-        if (smem_bitmap) rc = collect ? go(k_score3<true, true, true>) : go(k_score3<true, false, true>);
-        else rc = collect ? go(k_score3<false, true, true>) : go(k_score3<false, false, true>);
+        if (smem_bitmap) rc = collect ? go(k_score4<NC, true, true, true>) : go(k_score4<NC, true, false, true>);
+        else rc = collect ? go(k_score4<NC, false, true, true>) : go(k_score4<NC, false, false, true>);
     } else {
-        if (smem_bitmap) rc = collect ? go(k_score3<true, true, false>) : go(k_score3<true, false, false>);
-        else rc = collect ? go(k_score3<false, true, false>) : go(k_score3<false, false, false>);
+        if (smem_bitmap) rc = collect ? go(k_score4<NC, true, true, false>) : go(k_score4<NC, true, false, false>);
+        else rc = collect ? go(k_score4<NC, false, true, false>) : go(k_score4<NC, false, false, false>);
     }
     if (rc) return rc;
     CU(cudaGetLastError());
     return 0;
 }
 
+// One pass: groups [group0, group0 + ngroups) of the batch, `nc` groups per scanner; bm0 = index of the pass's first
+// union bitmap.  *wpg_out = partial rows per group (CTAs per scan group) for k_reduce.
+int launch_score4(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, uint32_t nc, uint32_t bm0,
+                  uint32_t* wpg_out, bool collect = false) {
+    using namespace ub200;
+    Score4Params p;
+    p.stream = M->mstream; p.hdr = M->hdr3; p.tiekey = M->tiekey;
+    p.tile_start = M->tile3_start; p.tile_w0 = M->tile3_w0; p.tile_lvl = M->tile3_lvl; p.tile_sseg = M->tile3_sseg;
+    p.seed_end = M->seed_end; p.blk_words = M->blk_words; p.blk_rec = reinterpret_cast<const uint4*>(M->blk_rec);
+    p.n_nodes = M->n; p.n_tiles = M->n_tiles3; p.L = M->L;
+    p.bitmap_words = S->bitmap_words; p.bitmap = S->bitmap + (size_t)bm0 * S->bitmap_words; p.tab = S->tab;
+    p.gbest = S->gbest;
+    p.n_samples = S->n_samples; p.group0 = group0; p.ngroups = ngroups; p.nsg = (ngroups + nc - 1) / nc;
+    p.part_key = S->part_key; p.part_cnt = S->part_cnt;
+    p.gstack = M->gstack3; p.gstack_levels = M->gstack3_levels;
+    p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
+    p.tile_counter = S->tile_counter;
+    CU(cudaMemsetAsync(S->tile_counter, 0, 256, M->stream));
+    const uint32_t grid = std::max<uint32_t>(p.nsg, ((uint32_t)M->num_sms / p.nsg) * p.nsg);
+    *wpg_out = grid / p.nsg;
+    if (nc == 1) return launch_score4_nc<1>(M, S, p, grid, collect);
+    if (nc == 2) return launch_score4_nc<2>(M, S, p, grid, collect);
+    return launch_score4_nc<3>(M, S, p, grid, collect);
+}
+
 // Build the per-group position bitmap + position-major cost table + per-sample base count on the device.
 // Part of every place call (it is sample-side work of the hot path), timed as "prep".
-int run_prep(ub200_mat* M, ub200_samples* S) {
+int run_prep(ub200_mat* M, ub200_samples* S, uint32_t pass_groups, uint32_t nc) {
     cudaStream_t st = M->stream;
     int rc = span_begin(M, 0);
     if (rc) return rc;
@@ -251,6 +272,7 @@ int run_prep(ub200_mat* M, ub200_samples* S) {
         pp.calls = S->calls; pp.sample_ptr = S->sample_ptr; pp.call_sample = S->call_sample;
         pp.n_calls = S->n_calls; pp.L = M->L; pp.bitmap_words = S->bitmap_words;
         pp.bitmap = S->bitmap; pp.tab = S->tab; pp.base = S->base;
+        pp.pass_groups = pass_groups; pp.nc = nc; pp.nsg_per_pass = (pass_groups + nc - 1) / nc;
         const uint32_t blocks = (uint32_t)((S->n_calls + 255) / 256);
         ub200::k_prep_scatter<<<blocks, 256, 0, st>>>(pp);
         CU(cudaGetLastError());
@@ -281,7 +303,7 @@ void ub200_mat_destroy(ub200_mat* M) {
     cudaFree(M->anc); cudaFree(M->key_to_node); cudaFree(M->tie_index); cudaFree(M->num_leaves);
     cudaFree(M->gstack);
     cudaFree(M->mstream); cudaFree(M->hdr3); cudaFree(M->tiekey); cudaFree(M->tile3_start); cudaFree(M->tile3_w0);
-    cudaFree(M->tile3_lvl); cudaFree(M->tile3_sseg); cudaFree(M->seed_end); cudaFree(M->blk_words); cudaFree(M->gstack3);
+    cudaFree(M->tile3_lvl); cudaFree(M->tile3_sseg); cudaFree(M->seed_end); cudaFree(M->blk_words); cudaFree(M->blk_rec); cudaFree(M->gstack3);
     if (M->scratch) ub200_samples_free(M->scratch);
     for (auto e : M->ev) cudaEventDestroy(e);
     if (M->own_stream) cudaStreamDestroy(M->own_stream);
@@ -302,7 +324,7 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     M->num_sms = prop.multiProcessorCount;
     M->grid = (uint32_t)M->num_sms * 2u;
     // workers of either kernel (k_score: 2 CTAs x 8 warps per SM, k_score3: 1 CTA x kPairs3 warp pairs)
-    const uint32_t warps3 = (uint32_t)std::max(M->num_sms, 8) * ub200::kPairs3;   // tile workers = warp pairs
+    const uint32_t warps3 = (uint32_t)std::max(M->num_sms, 8) * 16u;   // tile workers = scanner/consumer units (NC = 1)
     const uint32_t total_warps = std::max<uint32_t>(M->grid * ub200::kWarpsPerCta, warps3);
     std::string err;
     const char* mt = getenv("UB200_MIN_TILE");   // test hook: cut small trees into many tiles
@@ -330,11 +352,14 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
         guard(dev_upload(&M->tile3_sseg, d.tile3_sseg.data(), d.tile3_sseg.size(), M->stream));
         guard(dev_upload(&M->seed_end, d.seed_end.data(), d.seed_end.size(), M->stream));
         guard(dev_upload(&M->blk_words, d.blk_words.data(), d.blk_words.size(), M->stream));
+        guard(dev_upload(&M->blk_rec, d.blk_rec.data(), d.blk_rec.size(), M->stream));
         M->device_bytes += d.stream.size() * 4 + d.hdr3.size() * 16 + d.tiekey.size() * 4 +
-                           (d.tile3_start.size() * 4 + d.seed_end.size() + d.blk_words.size()) * 4;
-        if (!rc && d.max_level + 1 > (uint32_t)ub200::kStack3) {
-            M->gstack3_levels = d.max_level + 1 - ub200::kStack3;
-            const size_t bytes = (size_t)warps3 * M->gstack3_levels * 32 * sizeof(int32_t);
+                           (d.tile3_start.size() * 4 + d.seed_end.size() + d.blk_words.size() + d.blk_rec.size()) * 4;
+        // spill rows of the consumers' level stacks: at most 24 consumers per SM (NC = 3), 32 levels in shared memory
+        constexpr uint32_t kMinStack = (uint32_t)ub200::Cfg4<3>::kStack;
+        if (!rc && d.max_level + 1 > kMinStack) {
+            M->gstack3_levels = d.max_level + 1 - kMinStack;
+            const size_t bytes = (size_t)std::max(M->num_sms, 8) * 24u * M->gstack3_levels * 32 * sizeof(int32_t);
             if (bytes > (size_t)16 << 30) {
                 rc = fail(UB200_E_LIMIT, "tree too deep for the spill stack (" + std::to_string(d.max_level) + " levels)");
             } else {
@@ -376,8 +401,15 @@ int ub200_mat_node_arrays(const ub200_mat* M, uint32_t* bfs_index, uint32_t* num
 int ub200_mat_set_pass_samples(ub200_mat* M, uint32_t spp) {
     if (!M) return fail(UB200_E_ARG, "NULL handle");
     if (spp == 0) spp = 32;
-    if (spp % 32 || spp > 256 || (spp & (spp - 1))) return fail(UB200_E_ARG, "samples per pass must be 32, 64, 128 or 256");
+    if (spp % 32 || spp > 768) return fail(UB200_E_ARG, "samples per pass must be a multiple of 32, at most 768");
     M->pass_groups = spp / 32;
+    return UB200_OK;
+}
+
+int ub200_mat_set_scan_sharing(ub200_mat* M, uint32_t nc) {
+    if (!M) return fail(UB200_E_ARG, "NULL handle");
+    if (nc > 3) return fail(UB200_E_ARG, "groups per scan must be 0 (auto), 1, 2 or 3");
+    M->consumers = nc;
     return UB200_OK;
 }
 
@@ -451,14 +483,15 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
         if (!rc) rc = alloc((void**)&S->tab, (size_t)g * M->L * 32);
         if (!rc) rc = alloc((void**)&S->base, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->gbest, (size_t)g * 32 * 4);
-        if (!rc && !S->tile_counter) rc = alloc((void**)&S->tile_counter, 64);
+        if (!rc && !S->tile_counter) rc = alloc((void**)&S->tile_counter, 256);
         if (!rc) rc = alloc((void**)&S->results, (size_t)g * 32 * sizeof(ub200_placement));
         if (!rc) rc = alloc((void**)&S->best_rel, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->sample_ptr, ((size_t)g * 32 + 1) * 8);
         if (!rc) rc = alloc((void**)&S->set_ptr, ((size_t)g * 32 + 1) * 8);
         if (!rc) rc = alloc((void**)&S->set_fill, (size_t)g * 32 * 4);
-        // per-CTA partial bests of one pass: up to 8 groups x (CTAs per group) rows of 32 lanes
-        const size_t part_rows = (size_t)std::max<uint32_t>(M->grid, 8u) + 8u;
+        // per-CTA partial bests of one pass: one row of 32 lanes per CTA and group it serves (up to 3), or per
+        // warp-slice of k_score
+        const size_t part_rows = (size_t)std::max<uint32_t>(M->grid, 8u) * 3u + 32u;
         if (!rc) rc = alloc((void**)&S->part_key, part_rows * 32 * 8);
         if (!rc) rc = alloc((void**)&S->part_cnt, part_rows * 32 * 4);
         if (rc) { S->cap_groups = 0; return rc; }
@@ -512,24 +545,27 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
     const bool smem_bitmap = S->bitmap_words * 4u <= ub200::kMaxSmemBitmapBytes;
     // the streaming kernel packs per-(node,sample) deltas in 10-bit fields and path corrections in int16
     const char* force = getenv("UB200_KERNEL");
-    const bool use_v3 = !(force && force[0] == '1') && M->d.have3 && M->d.max_row <= ub200::kMaxRowV3 &&
-                        S->max_calls <= ub200::kMaxCallsV3;
+    const bool use_v3 = !(force && force[0] == '1') && M->d.have3 && M->d.max_row <= ub200::kMaxRowV4 &&
+                        S->max_calls <= ub200::kMaxCallsV4;
     if (!use_v3 || (flags & UB200_WANT_NODE_SCORES)) { int rc = ensure_v1(M); if (rc) return rc; }
     const uint32_t NG = M->pass_groups;
     M->spans.clear(); M->ev_used = 0;
     M->last = {};
-    { int rc = run_prep(M, S); if (rc) return rc; }
+    // k_score (per-node scores, fallback) indexes one bitmap per group: no shared scans then
+    const uint32_t nc = (use_v3 && !(flags & UB200_WANT_NODE_SCORES)) ? pick_consumers(M, std::min(NG, S->n_groups)) : 1u;
+    const uint32_t nsgpp = (NG + nc - 1) / nc;   // union bitmaps per pass
+    { int rc = run_prep(M, S, NG, nc); if (rc) return rc; }
     M->last.total_launches += 5;
     for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
         const uint32_t ng = std::min(NG, S->n_groups - g0);
         int rc = span_begin(M, 1); if (rc) return rc;
-        uint32_t grid = std::max<uint32_t>(ng, (M->grid / ng) * ng);
-        if (use_v3) rc = launch_score3(M, S, g0, ng, &grid);
+        uint32_t wpg = std::max<uint32_t>(ng, (M->grid / ng) * ng) / ng;
+        if (use_v3) rc = launch_score4(M, S, g0, ng, nc, (g0 / NG) * nsgpp, &wpg);
         else rc = launch_score<ub200::kModeBest>(M, S, g0, ng, smem_bitmap);
         if (rc) return rc;
         rc = span_end(M); if (rc) return rc;
         ub200::ReduceParams rp;
-        rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = grid / ng;   // one partial row per CTA
+        rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = wpg;   // one partial row per CTA and group
         rp.group0 = g0; rp.n_samples = S->n_samples; rp.base = S->base; rp.key_to_node = M->key_to_node;
         rp.tie_index = M->tie_index; rp.num_leaves = M->num_leaves; rp.out = S->results; rp.best_rel = S->best_rel;
         rc = span_begin(M, 2); if (rc) return rc;
@@ -567,8 +603,8 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
         CU(cudaMemsetAsync(S->set_fill, 0, (size_t)S->n_groups * 32 * 4, M->stream));
         for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
             const uint32_t ng = std::min(NG, S->n_groups - g0);
-            uint32_t grid_unused = 0;
-            int rc = use_v3 ? launch_score3(M, S, g0, ng, &grid_unused, true)
+            uint32_t wpg_unused = 0;
+            int rc = use_v3 ? launch_score4(M, S, g0, ng, nc, (g0 / NG) * nsgpp, &wpg_unused, true)
                             : launch_score<ub200::kModeCollect>(M, S, g0, ng, smem_bitmap);
             if (rc) return rc;
             M->last.total_launches++;

@@ -172,41 +172,21 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     }
     d.tile3_w0[T] = (uint32_t)(w / kChunk3);
     d.seed_end.push_back(0);   // never empty
-    // ---- block records + static bounds (tile-local subtree minima of G - nmut)
-    {
-        std::vector<int32_t> sub(n);
-        for (uint32_t i = 0; i < n; i++) sub[i] = d.hdr3[i].g - (int32_t)(d.hdr3[i].nmut_c0 >> 16);
-        std::vector<int32_t> own(sub);
-        d.tile3_min.assign(T, 0);
-        d.blk_rec.assign((size_t)nblk * 4, 0);
-        for (size_t t = 0; t < T; t++) {
-            const uint32_t n0 = d.tile3_start[t], n1 = d.tile3_start[t + 1];
-            // reverse DFS order: a node's subtree minimum is complete before it is folded into its parent;
-            // parents outside the tile are not touched (tile-local bound)
-            for (uint32_t i = n1; i-- > n0;) {
-                const int32_t p = f.parent[i];
-                if (p >= (int32_t)n0) sub[p] = std::min(sub[p], sub[i]);
+    // ---- block records: what the consumer needs of a block that cannot hold an optimum (score_kernel4.cuh)
+    d.blk_rec.assign((size_t)nblk * 4, 0);
+    for (uint32_t b = 0; b < n; b += 32) {
+        const uint32_t e = std::min(n, b + 32);
+        int32_t omin = INT32_MAX;
+        uint32_t open = 0, lv0 = 0;
+        for (uint32_t i = b; i < e; i++) {
+            omin = std::min(omin, d.hdr3[i].g - (int32_t)(d.hdr3[i].nmut_c0 >> 16));
+            if (d.hdr3[i].level_flags & kFlagOpen) {
+                if (!open) lv0 = d.level[i];
+                open |= 1u << (i & 31);
             }
-            int32_t tmin = INT32_MAX;
-            for (uint32_t b = n0; b < n1; b += 32) {
-                const uint32_t e = std::min(n1, b + 32);
-                int32_t omin = INT32_MAX, smin = INT32_MAX;
-                uint32_t open = 0, lv0 = 0;
-                for (uint32_t i = b; i < e; i++) {
-                    omin = std::min(omin, own[i]);
-                    smin = std::min(smin, sub[i]);
-                    if (d.hdr3[i].level_flags & kFlagOpen) {
-                        if (!open) lv0 = d.level[i];
-                        open |= 1u << (i & 31);
-                    }
-                }
-                uint32_t* r = &d.blk_rec[(size_t)(b >> 5) * 4];
-                r[0] = (uint32_t)omin; r[1] = (uint32_t)smin; r[2] = open;
-                r[3] = (lv0 << 14) | d.blk_words[b >> 5];
-                tmin = std::min(tmin, omin);
-            }
-            d.tile3_min[t] = tmin;
         }
+        uint32_t* r = &d.blk_rec[(size_t)(b >> 5) * 4];
+        r[0] = (uint32_t)omin; r[1] = open; r[2] = lv0; r[3] = d.blk_words[b >> 5];
     }
 }
 
@@ -431,7 +411,7 @@ struct ub200_derived_view {
     uint64_t stream_words;
     const uint32_t* stream; const void* hdr3; const uint32_t* tile3_start; const uint32_t* tile3_w0;
     const uint32_t* tile3_lvl; const uint32_t* tile3_sseg; const uint32_t* seed_end; const uint32_t* blk_words;
-    const uint32_t* blk_rec; const int32_t* tile3_min;
+    const uint32_t* blk_rec;
 };
 
 int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32_t min_tile_cost, void** handle,
@@ -458,7 +438,7 @@ int ub200_debug_derive(const ub200_flat_mat* flat, uint32_t target_tiles, uint32
     view->tile3_w0 = d->tile3_w0.data(); view->tile3_lvl = d->tile3_lvl.data();
     view->tile3_sseg = d->tile3_sseg.data(); view->seed_end = d->seed_end.data();
     view->blk_words = d->blk_words.data();
-    view->blk_rec = d->blk_rec.data(); view->tile3_min = d->tile3_min.data();
+    view->blk_rec = d->blk_rec.data();
     *handle = d;
     return UB200_OK;
 }

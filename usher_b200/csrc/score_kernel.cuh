@@ -480,6 +480,9 @@ struct PrepParams {
     uint32_t* bitmap;
     uint32_t* tab;
     int32_t* base;
+    // union bitmaps: groups are scored in passes of `pass_groups`, `nc` consecutive groups of a pass share one scan of
+    // the mutation stream and therefore one bitmap (nc = 1: one bitmap per group)
+    uint32_t pass_groups, nc, nsg_per_pass;
 };
 
 __global__ void k_prep_scatter(const PrepParams p) {
@@ -492,7 +495,8 @@ __global__ void k_prep_scatter(const PrepParams p) {
     if (!c.is_missing && (set & c.ref_nuc) == 0) atomicAdd(p.base + s, 1);
     const uint32_t pos = (uint32_t)c.position;
     if (pos < p.L) {
-        atomicOr(p.bitmap + (size_t)g * p.bitmap_words + (pos >> 5), 1u << (pos & 31u));
+        const uint32_t ub = (g / p.pass_groups) * p.nsg_per_pass + (g % p.pass_groups) / p.nc;
+        atomicOr(p.bitmap + (size_t)ub * p.bitmap_words + (pos >> 5), 1u << (pos & 31u));
         const uint32_t cost = c.is_missing ? 0u : (~set & 15u);
         uint32_t* row = p.tab + ((size_t)g * p.L + pos) * 8u;
         atomicOr(row, 1u << lane);

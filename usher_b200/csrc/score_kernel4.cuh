@@ -1,0 +1,741 @@
+// k_score4 — streaming best-placement kernel on the segment layout (ub200_internal.h, DESIGN.md "Kernels").
+//
+// One persistent launch scores every node of the tree against `nsg` SCAN GROUPS; a scan group is NC consecutive
+// groups of 32 samples that share one pass over the mutation stream.  The unit of work is a tile: a contiguous DFS
+// range of whole 32-node blocks whose mutations are ONE contiguous piece of the stream, [seed segments][block
+// segments].  A CTA holds kUnits UNITS of 1 + NC warps; a unit works on one tile at a time:
+//
+//   scanner warp   pulls the tile's stream through a 4 KB shared-memory ring of 512 B rows (16-byte cp.async per
+//                  lane per row) in STEPS of 4 rows that are aligned to the tile, not to its segments: every word
+//                  is loaded and tested exactly once against the scan group's UNION bitmap (per word: byte offset
+//                  of the bitmap word, LDS, a wrap shift and a funnel shift collecting the hit bits).  The hit
+//                  bits of a step are then handed out segment by segment: masked to the segment's quads,
+//                  compacted with two ballots and copied into one of eight 64-word message slots that all NC
+//                  consumers read (full barrier: 1 arrival, empty barrier: NC arrivals).  A segment = one or more
+//                  messages, the last one flagged.  The scanner needs no sample state.
+//   consumer warp  owns the state of ONE group of 32 samples.  Per block:
+//     rec            16-byte block record fetched a block ahead (min(G - nmut), open-chain mask and level): the 32
+//                    node headers are only read for blocks that can still hold an optimum
+//     C  lane = hit  table row of the position (32 B, L2; two rows per lane in flight).  Rows whose sample mask is
+//                    empty belong to another group of the scan group and are dropped.  Sparse messages apply the
+//                    (hit, sample) pairs straight from the lanes; dense ones (any lane with more than two pairs)
+//                    first EXPAND the pairs into a shared-memory list and then apply them lane = pair, so that a
+//                    position called by many samples does not serialise the warp: packed (dcorr, da, dcommon)
+//                    from a 1024-entry LUT, shared-memory atomics into dnode[node][sample], neg[sample] +=
+//                    min(dcorr, 0)
+//     bound          exact lower bound of every pair of the block:  min(G - nmut) + gmin + neg  against the running
+//                    best; blocks that cannot hold an optimum skip E and F entirely
+//     E  lane = node     non-hit pairs of a sample that can still improve or tie
+//     F  lane = sample   hit pairs, exactly (score, validity, tie key)
+//     G  lane = sample   path corrections of the block's OPEN chain -> stack rows the following blocks read
+//   Seed segments (the rows of the tile's root path, 32 levels per segment) go through the same scanner ->
+//   consumer path and initialise the stack.
+// The correction of the path above a node inside its own block is never materialised: it is
+// stack[level above the block] + sum of dnode over (in-block ancestors & hit nodes of the sample).  All pruning is
+// exact, so results are schedule-independent.
+#pragma once
+#include "score_kernel.cuh"
+
+namespace ub200 {
+
+constexpr uint32_t kRingRows4 = 8;                         // rows of 128 words (512 B)
+constexpr uint32_t kRingWords4 = kRingRows4 * 128;         // 1024 words = 4 KB
+constexpr uint32_t kSlots4 = 8, kSlotCap4 = 64;            // scanner -> consumer messages
+constexpr uint32_t kPairCap4 = 224;                        // expanded (hit, sample) pairs per round
+constexpr uint32_t kLut4Bytes = 4096;
+constexpr uint32_t kMaxRowV4 = 500;      // packed 10-bit delta fields
+constexpr uint32_t kMaxCallsV4 = 16383;  // path corrections are int16 and reach -2 per call
+constexpr uint32_t kSmemLimit4 = 232448; // 227 KB
+constexpr uint32_t kMsgLast4 = 1u << 16, kMsgTile4 = 2u << 16, kMsgEnd4 = 4u << 16;
+
+// Geometry of a CTA for NC consumers per scanner.
+template <int NC>
+struct Cfg4 {
+    static constexpr int kUnits = NC == 1 ? 16 : (NC == 2 ? 10 : 8);
+    static constexpr int kWarps = kUnits * (1 + NC);
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kStack = NC == 3 ? 32 : 40;        // stack levels kept in shared memory (deeper: HBM spill)
+    // unit-shared part (bytes): ring, hit lists, message words, barriers
+    static constexpr uint32_t kORing = 0;                   // u32[1024]
+    static constexpr uint32_t kOList = 4096;                // u32[8][64]
+    static constexpr uint32_t kOMsg = kOList + kSlots4 * kSlotCap4 * 4;   // uint2[8]
+    static constexpr uint32_t kOBars = kOMsg + kSlots4 * 8;               // 8 full + 8 empty mbarriers
+    static constexpr uint32_t kShared = kOBars + 2 * kSlots4 * 8;
+    // per-consumer part
+    static constexpr uint32_t kODnode = 0;                  // i32[32][32] packed deltas
+    static constexpr uint32_t kOStack = 4096;               // i16[kStack][32]
+    static constexpr uint32_t kONeg = kOStack + kStack * 64;   // i32[32]
+    static constexpr uint32_t kOArea = kONeg + 128;         // u32[224]: pair list while hits arrive, header copies
+                                                            // (G, Z, W, Am, Hm) while a block is evaluated
+    static constexpr uint32_t kCons = kOArea + kPairCap4 * 4;
+    static constexpr uint32_t kUnit = (kShared + NC * kCons + 127) & ~127u;
+    static constexpr uint32_t kFixed = kLut4Bytes + kUnits * kUnit;
+};
+constexpr uint32_t kA4G = 0, kA4Z = 32, kA4W = 64, kA4Am = 96, kA4Hm = 128;
+
+struct Score4Params {
+    const uint32_t* stream;
+    const NodeHdr* hdr;           // hdr3
+    const uint32_t* tiekey;
+    const uint32_t* blk_words;    // [blocks] stream words of each 32-node block segment (multiple of 4)
+    const uint4* blk_rec;         // [blocks] x = min(G - nmut), y = open-chain mask, z = level of the first open node
+    const uint32_t* tile_start;   // [T+1]
+    const uint32_t* tile_w0;      // [T+1]
+    const uint32_t* tile_lvl;     // [T]
+    const uint32_t* tile_sseg;    // [T+1]
+    const uint32_t* seed_end;
+    uint32_t n_nodes, n_tiles, L, bitmap_words;
+    const uint32_t* bitmap;       // union bitmaps of this pass's scan groups: [nsg][bitmap_words]
+    const uint32_t* tab;          // [groups][L][8]: mask, ref<<4, nibbles[4], -, -
+    int32_t* gbest;
+    uint32_t n_samples, group0, ngroups, nsg;   // first group / number of groups / scan groups of this pass
+    unsigned long long* part_key;
+    uint32_t* part_cnt;
+    int32_t* gstack;
+    uint32_t gstack_levels;
+    const int32_t* target_rel;
+    uint32_t* set_out;
+    const unsigned long long* set_ptr;
+    uint32_t* set_fill;
+    uint32_t* tile_counter;
+};
+
+__device__ __forceinline__ uint32_t lds32_4(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32_4(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128_4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// wait of the scanner on a slot the consumers still hold: the consumers are the slower side then, so the scanner
+// backs off instead of polling (a polling warp eats issue slots the consumers need)
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(256);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __noinline__ int spill_read4(const int32_t* gstk, uint32_t level, uint32_t s) {
+    return gstk[(size_t)level * 32u + s];
+}
+__device__ __noinline__ void spill_write4(int32_t* gstk, uint32_t level, uint32_t s, int v) {
+    gstk[(size_t)level * 32u + s] = v;
+}
+__device__ __forceinline__ int lut_delta4(uint32_t i) {
+    const uint32_t e = i >> 6, refc = (i >> 4) & 3u, prevc = (i >> 2) & 3u, mutc = i & 3u;
+    const int rm = (mutc != refc), rp = (prevc != refc);
+    const int wm = (e >> mutc) & 1u, wp = (e >> prevc) & 1u;
+    const int dcorr = (wm - wp) - (rm - rp);
+    const int tk = wm ^ 1, t0 = rm ^ 1;
+    const int da = (tk & wp) - (t0 & rp);
+    const int dcom = tk - t0;
+    return dcorr * (1 << 20) + da * (1 << 10) + dcom;
+}
+// bitmap word of a stream word's position: narrow words carry the byte offset at bit 14
+template <bool SMEM_BITMAP, bool NARROW>
+__device__ __forceinline__ uint32_t bitmap_word(const uint32_t* bm_s, const uint32_t* bm_g, uint32_t w) {
+    if (NARROW) {
+        const uint32_t off = w >> 14;
+        return SMEM_BITMAP ? *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bm_s) + off)
+                           : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bm_g) + off));
+    }
+    return SMEM_BITMAP ? bm_s[w >> 14] : __ldg(bm_g + (w >> 14));
+}
+__device__ __forceinline__ int dc_of(int v) { return (v + (1 << 19)) >> 20; }
+__device__ __forceinline__ void unpack_delta4(int v, int& dcorr, int& da, int& dcom) {
+    dcom = (int)((uint32_t)v << 22) >> 22;
+    const int v1 = (v - dcom) >> 10;
+    da = (int)((uint32_t)v1 << 22) >> 22;
+    dcorr = (v1 - da) >> 10;
+}
+
+// COLLECT = false: best placement per sample.  COLLECT = true: second pass that lists every optimal node of each
+// sample (best_j_vec + node_has_unique); the final best score is the bound, so almost every block is pruned.
+template <int NC, bool SMEM_BITMAP, bool COLLECT, bool NARROW>
+__global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Params p) {
+    using C = Cfg4<NC>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // unit / role of this warp; the scanners are spread over the four SM sub-partitions (warp % 4)
+    uint32_t unit, role;   // role 0 = scanner, 1..NC = consumer role-1
+    if (NC == 1) {
+        unit = warp >> 1;
+        role = ((warp & 1u) == ((warp >> 2) & 1u)) ? 0u : 1u;
+    } else if (NC == 2) {
+        unit = warp / 3u;
+        role = warp % 3u;
+    } else {
+        unit = warp >> 2;
+        role = ((warp & 3u) - (unit & 3u)) & 3u;
+    }
+    const uint32_t sg = blockIdx.x % p.nsg;
+    const uint32_t cta_in_sg = blockIdx.x / p.nsg;
+    const uint32_t ctas_per_sg = gridDim.x / p.nsg;
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    constexpr int BIG = 0x3fffffff;
+
+    // ---- shared memory: [bitmap][lut][unit 0 .. unit kUnits-1]
+    uint32_t* bm_s = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t bm_bytes = SMEM_BITMAP ? ((p.bitmap_words * 4u + 127u) & ~127u) : 0u;
+    int* lut = reinterpret_cast<int*>(smem + bm_bytes);
+    uint8_t* ubase = smem + bm_bytes + kLut4Bytes + unit * C::kUnit;
+    uint32_t* mring = reinterpret_cast<uint32_t*>(ubase + C::kORing);
+    uint32_t* list = reinterpret_cast<uint32_t*>(ubase + C::kOList);
+    volatile uint2* msg = reinterpret_cast<volatile uint2*>(ubase + C::kOMsg);
+    const uint32_t mring_a = smem_u32(mring), bars_a = smem_u32(ubase + C::kOBars), list_a = smem_u32(list);
+    constexpr uint32_t kBarFull = 0, kBarEmpty = kSlots4;
+
+    const uint32_t* bm_g = p.bitmap + (size_t)sg * p.bitmap_words;
+    if (SMEM_BITMAP) {
+        const uint4* src = reinterpret_cast<const uint4*>(bm_g);
+        uint4* dst = reinterpret_cast<uint4*>(bm_s);
+        for (uint32_t i = threadIdx.x; i < p.bitmap_words / 4; i += C::kThreads) dst[i] = __ldg(src + i);
+    }
+    for (uint32_t i = threadIdx.x; i < 1024; i += C::kThreads) lut[i] = lut_delta4(i);
+    if (role == 0) {
+        // lanes past a segment's end still index the bitmap with what the ring holds: only ever valid words
+        for (uint32_t i = lane; i < kRingWords4; i += 32) mring[i] = 0u;
+        if (lane == 0) {
+            for (uint32_t i = 0; i < kSlots4; i++) {
+                mbar_init(bars_a + 8 * (kBarFull + i), 1);
+                mbar_init(bars_a + 8 * (kBarEmpty + i), NC);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
+    if (role == 0) {
+        // =====================================================================================================
+        // scanner
+        // =====================================================================================================
+        uint32_t lrow = 0, rows_end = 0;   // next ring row to load, end of the tile's rows
+        uint32_t nmsg = 0;        // messages sent so far; the open one lives in slot nmsg % kSlots4
+        uint32_t fill = 0;        // hit words in the open message
+        auto open_msg = [&]() {   // wait until every consumer has released the slot
+            const uint32_t s = nmsg % kSlots4;
+            mbar_wait_backoff(bars_a + 8 * (kBarEmpty + s), ((nmsg / kSlots4) & 1u) ^ 1u);
+            fill = 0;
+        };
+        auto send_msg = [&](uint32_t flags, uint32_t payload) {
+            const uint32_t s = nmsg % kSlots4;
+            __syncwarp();
+            if (elect_one()) {
+                msg[s].x = fill | flags;
+                msg[s].y = payload;
+                mbar_arrive(bars_a + 8 * (kBarFull + s));
+            }
+            nmsg++;
+        };
+        // ring loader: rows of 128 words (512 B, absolute-aligned), one 16-byte cp.async per lane per row
+        // (LDGSTS, L2 -> shared memory without registers); two counters and cp.async groups are all the
+        // bookkeeping.  Rows below cur_row are dead.
+        auto ring_fill = [&](uint32_t cur_row) {
+            const uint32_t lim_row = min(rows_end, cur_row + kRingRows4);
+            while (lrow < lim_row) {
+                cp_async16(mring_a + (((lrow & (kRingRows4 - 1u)) << 9) + (lane << 4)),
+                           p.stream + ((size_t)lrow << 7) + (lane << 2));
+                lrow++;
+            }
+            cp_async_commit();
+        };
+        // hand the hits of the current step that lie in stream words [off, lim) (multiples of 4, inside the step
+        // starting at word `base`) to the open message; full messages are sent (not flagged last) and reopened
+        auto emit = [&](uint32_t hb_step, uint32_t base, uint32_t off, uint32_t lim) {
+            const uint32_t idx = base + 4u * lane;
+            uint32_t hb = hb_step;                            // bit 4k+j = word j of quad k (row k of the step)
+            if (off != base || lim != base + 512u) {          // quads outside [off, lim) belong to other segments
+                const int lo = (int)(off - idx), hi = (int)(lim - idx);   // multiples of 4
+                const uint32_t k_lo = lo > 0 ? min((uint32_t)(lo + 127) >> 7, 4u) : 0u;
+                const uint32_t k_hi = hi > 0 ? min((uint32_t)(hi + 127) >> 7, 4u) : 0u;
+                hb &= ((1u << (4u * k_hi)) - 1u) & ~((1u << (4u * k_lo)) - 1u);
+            }
+            // compact: lane l's hits follow those of lanes < l.  Exclusive prefix of the per-lane counts:
+            // two ballots when no lane has more than 3 hits (the usual case), else a shuffle scan
+            const uint32_t c = __popc(hb);
+            const uint32_t big = __ballot_sync(FULL, c > 3u);
+            uint32_t excl, remaining;
+            if (big == 0u) {
+                const uint32_t v0 = __ballot_sync(FULL, c & 1u), v1 = __ballot_sync(FULL, c & 2u);
+                if ((v0 | v1) == 0u) return;
+                excl = __popc(v0 & lt_mask) + 2u * __popc(v1 & lt_mask);
+                remaining = __popc(v0) + 2u * __popc(v1);
+            } else {
+                uint32_t incl = c;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
+                    if (lane >= (uint32_t)dlt) incl += v;
+                }
+                remaining = __shfl_sync(FULL, incl, 31);
+                excl = incl - c;
+            }
+            if (remaining <= kSlotCap4 - fill) {
+                // common case: all of these hits fit the open message
+                uint32_t pa = list_a + (((nmsg % kSlots4) * kSlotCap4 + fill + excl) << 2);
+                while (hb) {
+                    uint32_t bit;
+                    asm("bfind.u32 %0, %1;" : "=r"(bit) : "r"(hb));   // highest set bit (FLO)
+                    hb ^= 1u << bit;
+                    const uint32_t wi = idx + ((bit & 12u) << 5) + (bit & 3u);
+                    sts32_4(pa, lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
+                    pa += 4u;
+                }
+                fill += remaining;
+                return;
+            }
+            uint32_t mine = excl;           // index of this lane's next hit among these hits
+            uint32_t done = 0;              // hits already placed in messages
+            while (remaining) {
+                if (fill == kSlotCap4) {
+                    send_msg(0u, 0u);
+                    open_msg();
+                }
+                const uint32_t take = min(kSlotCap4 - fill, remaining);
+                const uint32_t slot_a = (nmsg % kSlots4) * kSlotCap4 + fill;
+                while (hb && mine < done + take) {
+                    const uint32_t bit = __ffs(hb) - 1;
+                    hb &= hb - 1;
+                    const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
+                    list[slot_a + (mine - done)] = lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2));
+                    mine++;
+                }
+                fill += take;
+                remaining -= take;
+                done += take;
+            }
+        };
+
+        // tiles are handed out in DFS order by a per-scan-group counter: balances uneven tiles, and the CTAs of
+        // different scan groups still walk the tree in the same order (one HBM read, the rest from L2).  The next
+        // tile and its metadata are fetched while the last blocks of the current one are scanned.
+        struct TileMeta { uint32_t t, n0, n1, lvl0, sseg, w0, w1; };
+        auto fetch_tile = [&]() -> TileMeta {
+            TileMeta m;
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(p.tile_counter + sg, 1u);
+            m.t = __shfl_sync(FULL, t, 0);
+            const uint32_t tt = min(m.t, p.n_tiles - 1u);
+            m.n0 = p.tile_start[tt]; m.n1 = p.tile_start[tt + 1];
+            m.lvl0 = p.tile_lvl[tt]; m.sseg = p.tile_sseg[tt];
+            m.w0 = p.tile_w0[tt]; m.w1 = p.tile_w0[tt + 1];
+            return m;
+        };
+        TileMeta cur = fetch_tile();
+        for (;;) {
+            open_msg();
+            if (cur.t >= p.n_tiles) {
+                send_msg(kMsgEnd4, 0u);
+                break;
+            }
+            send_msg(kMsgTile4, cur.t);
+            lrow = cur.w0 * (kChunk3 / 128u);
+            rows_end = cur.w1 * (kChunk3 / 128u);
+            ring_fill(lrow);
+            // segments of the tile in stream order: seed segments, then one segment per block
+            const uint32_t nseed = (cur.lvl0 + 31u) >> 5;
+            const uint32_t b0 = cur.n0 >> 5, nb = (cur.n1 - cur.n0 + 31u) >> 5;
+            const uint32_t nseg = nseed + nb;
+            const uint32_t b_fetch = nb > 3u ? nb - 3u : 0u;
+            TileMeta nxt = cur;
+            uint32_t bw = 0;
+            uint32_t off = cur.w0 * kChunk3;
+            uint32_t si = 0;                       // current segment
+            uint32_t seg_end = off;
+            auto next_segment = [&]() {            // end of segment si (stream word offset)
+                if (si < nseed) {
+                    seg_end = p.seed_end[cur.sseg + si] * 4u;
+                } else {
+                    const uint32_t b = si - nseed;
+                    if ((b & 31u) == 0) bw = (b + lane < nb) ? __ldg(p.blk_words + b0 + b + lane) : 0u;
+                    if (b == b_fetch) nxt = fetch_tile();
+                    seg_end = off + __shfl_sync(FULL, bw, b & 31u);
+                }
+            };
+            next_segment();
+            open_msg();
+            for (uint32_t base = off;; base += 512u) {
+                // ---- one step: 4 rows = 16 words per lane, loaded and tested once
+                // everything issued so far has to be there (this step's rows went out one step ago)
+                cp_async_wait<0>();
+                __syncwarp();
+                const uint32_t idx = base + 4u * lane;
+                uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
+                auto row_of = [&](uint32_t k) { return lds128_4(mring_a + (((idx + 128u * k) & (kRingWords4 - 1u)) << 2)); };
+                auto test4 = [&](const uint4& q) {
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.x), 0u, q.x), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.y), 0u, q.y), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.z), 0u, q.z), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.w), 0u, q.w), 1u);
+                };
+                {
+                    const uint4 q0 = row_of(0), q1 = row_of(1), q2 = row_of(2), q3 = row_of(3);
+                    // rows below this step are dead: top the ring up (needed one step from now) while the loads fly
+                    ring_fill(base >> 7);
+                    test4(q0); test4(q1); test4(q2); test4(q3);
+                }
+                const uint32_t hb_step = acc >> 16;                // bit 4k+j = word j of quad k
+                // ---- hand the step's hits out, segment by segment
+                bool tile_done = false;
+                for (;;) {
+                    const uint32_t lim = min(seg_end, base + 512u);
+                    if (lim > off) emit(hb_step, base, off, lim);
+                    off = lim;
+                    if (off == seg_end) {
+                        send_msg(kMsgLast4, 0u);
+                        if (++si == nseg) { tile_done = true; break; }
+                        next_segment();
+                        open_msg();
+                        if (seg_end == off) continue;              // empty segment
+                    }
+                    if (off == base + 512u) break;
+                }
+                if (tile_done) break;
+            }
+            cur = nxt;
+        }
+    } else {
+        // =====================================================================================================
+        // consumer role-1 of the unit: one group of 32 samples
+        // =====================================================================================================
+        const uint32_t cons = role - 1u;
+        const uint32_t lgroup = sg * NC + cons;                  // group within this pass
+        const bool dead = lgroup >= p.ngroups;                   // the last scan group may be short
+        const uint32_t ggroup = p.group0 + lgroup;
+        uint8_t* cbase = ubase + C::kShared + cons * C::kCons;
+        int* dnode = reinterpret_cast<int*>(cbase + C::kODnode);
+        int16_t* stk = reinterpret_cast<int16_t*>(cbase + C::kOStack);
+        int* neg = reinterpret_cast<int*>(cbase + C::kONeg);
+        uint32_t* area = reinterpret_cast<uint32_t*>(cbase + C::kOArea);
+        const uint32_t* tabg = p.tab + (size_t)ggroup * p.L * 8u;
+        int32_t* gstk = p.gstack
+                            ? p.gstack + ((size_t)((blockIdx.x * C::kUnits + unit) * NC + cons) * p.gstack_levels) * 32u
+                            : nullptr;
+        const uint32_t sample = ggroup * 32u + lane;
+        const bool live = !dead && sample < p.n_samples;
+
+        auto stack_read = [&](uint32_t level, uint32_t s) -> int {
+            if (__builtin_expect(level >= (uint32_t)C::kStack, 0)) return spill_read4(gstk, level - C::kStack, s);
+            return stk[level * 32u + s];
+        };
+        auto stack_write = [&](uint32_t level, uint32_t s, int v) {
+            if (__builtin_expect(level >= (uint32_t)C::kStack, 0)) spill_write4(gstk, level - C::kStack, s, v);
+            else stk[level * 32u + s] = (int16_t)v;
+        };
+
+        // per-lane (= sample) running best (COLLECT: the known final best, fixed)
+        int bsc = COLLECT ? (live ? p.target_rel[sample] : (int)0x80000000) : 0x7fffffff;
+        unsigned long long bkey = ~0ull;
+        uint32_t cnt = 0;
+        auto merge = [&](int sc, uint32_t hu, uint32_t node) {
+            if (COLLECT) {
+                if (sc == bsc) {
+                    const uint32_t k = atomicAdd(p.set_fill + sample, 1u);
+                    p.set_out[p.set_ptr[sample] + k] = node | (hu ? 0x80000000u : 0u);
+                }
+                return;
+            }
+            const uint32_t tiekey = __ldg(p.tiekey + node);
+            const unsigned long long key =
+                ((unsigned long long)(uint32_t)(sc + kScoreBias) << 33) | ((unsigned long long)tiekey << 1) | hu;
+            if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
+            else if (sc == bsc) { cnt++; if (key < bkey) bkey = key; }
+        };
+        auto zero_dnode = [&]() {
+#pragma unroll
+            for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(dnode)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
+            neg[lane] = 0;
+        };
+        // ---- C: the hit words of one message
+        // sparse form: lane = hit, the lane walks the samples that call the position
+        auto apply_hit = [&](uint32_t w, const uint4& r0, const uint2& r1) {
+            const uint32_t nl = (w >> 9) & 31u;
+            const uint32_t lo = r0.y | ((w >> 5) & 15u);
+            uint32_t pm = r0.x;
+            while (pm) {
+                const uint32_t s = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
+                const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
+                const int d = lut[(e4 << 6) | lo];
+                atomicAdd(&dnode[nl * 32u + s], d);
+                const int dc = dc_of(d);
+                if (dc < 0) atomicAdd(&neg[s], dc);
+            }
+        };
+        // dense form, first half: lane = hit writes its (hit, sample) pairs, LUT index << 10 | dnode index, into the
+        // pair list at its prefix position (only those of the current round)
+        auto expand_hit = [&](uint32_t w, const uint4& r0, const uint2& r1, uint32_t& idx, uint32_t lo_i, uint32_t hi_i) {
+            const uint32_t nlb = ((w >> 9) & 31u) << 5;
+            const uint32_t lo = r0.y | ((w >> 5) & 15u);
+            uint32_t pm = r0.x;
+            while (pm) {
+                const uint32_t s = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
+                const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
+                if (idx >= lo_i && idx < hi_i) area[idx - lo_i] = (((e4 << 6) | lo) << 10) | nlb | s;
+                idx++;
+            }
+        };
+        auto process = [&](uint32_t slot, uint32_t n) {
+            static_assert(kSlotCap4 == 64, "two hits per lane");
+            const bool h0 = lane < n, h1 = lane + 32u < n;
+            uint32_t w0 = 0, w1 = 0;
+            uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0;
+            uint2 a1 = make_uint2(0, 0), b1 = a1;
+            if (h0) {
+                w0 = list[slot * kSlotCap4 + lane];
+                const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w0) * 8u;
+                a0 = __ldg(reinterpret_cast<const uint4*>(row));
+                a1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+            }
+            if (h1) {
+                w1 = list[slot * kSlotCap4 + 32u + lane];
+                const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w1) * 8u;
+                b0 = __ldg(reinterpret_cast<const uint4*>(row));
+                b1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+            }
+            const uint32_t c = __popc(a0.x) + __popc(b0.x);     // rows of absent hits are zero
+            if (__ballot_sync(FULL, c > 2u) == 0u) {
+                if (a0.x) apply_hit(w0, a0, a1);
+                if (b0.x) apply_hit(w1, b0, b1);
+                return;
+            }
+            uint32_t incl = c;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
+                if (lane >= (uint32_t)dlt) incl += v;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            for (uint32_t r0i = 0; r0i < total; r0i += kPairCap4) {
+                const uint32_t r1i = min(total, r0i + kPairCap4);
+                uint32_t idx = incl - c;
+                if (idx < r1i && incl > r0i) {
+                    expand_hit(w0, a0, a1, idx, r0i, r1i);
+                    expand_hit(w1, b0, b1, idx, r0i, r1i);
+                }
+                __syncwarp();
+                for (uint32_t q = lane; q < r1i - r0i; q += 32u) {
+                    const uint32_t e = area[q];
+                    const int d = lut[e >> 10];
+                    atomicAdd(&dnode[e & 1023u], d);
+                    const int dc = dc_of(d);
+                    if (dc < 0) atomicAdd(&neg[e & 31u], dc);
+                }
+                __syncwarp();
+            }
+        };
+        uint32_t nmsg = 0;
+        // receive the messages of one segment and fold their hits into dnode / neg
+        auto take_segment = [&]() {
+            for (;;) {
+                const uint32_t s = nmsg % kSlots4;
+                mbar_wait_idle(bars_a + 8 * (kBarFull + s), (nmsg / kSlots4) & 1u, p.gbest);
+                const uint32_t m = msg[s].x;
+                if (m & 0xffffu) process(s, m & 0xffffu);
+                __syncwarp();
+                if (elect_one()) mbar_arrive(bars_a + 8 * (kBarEmpty + s));
+                nmsg++;
+                if (m & kMsgLast4) break;
+            }
+            __syncwarp();
+        };
+
+        for (;;) {
+            uint32_t t;
+            {
+                const uint32_t s = nmsg % kSlots4;
+                mbar_wait_long(bars_a + 8 * (kBarFull + s), (nmsg / kSlots4) & 1u);
+                const uint32_t m = msg[s].x;
+                t = msg[s].y;
+                __syncwarp();
+                if (elect_one()) mbar_arrive(bars_a + 8 * (kBarEmpty + s));
+                nmsg++;
+                if (m & kMsgEnd4) break;
+                if (dead || !(m & kMsgTile4)) continue;   // a consumer without a group only releases the slots
+            }
+            const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
+            const uint32_t lvl0 = p.tile_lvl[t];
+            // block records: one 16-byte word per block (same address for every lane), fetched one block ahead
+            const uint4* recp = p.blk_rec + (n0 >> 5);
+            uint4 rnext = __ldg(recp);
+
+            // cross-unit bound of this lane's sample, and the tile-local floor of every stack value
+            const int gb = COLLECT ? bsc : (live ? *(volatile int*)(p.gbest + sample) : 0x7fffffff);
+            int gmin = 0;
+
+            // ================= seed: path corrections of levels 0 .. lvl0-1, 32 levels per segment =============
+            for (uint32_t l0 = 0; l0 < lvl0; l0 += 32u) {
+                zero_dnode();
+                __syncwarp();
+                take_segment();
+                const uint32_t cn = min(32u, lvl0 - l0);
+                int v = l0 ? stack_read(l0 - 1u, lane) : 0;
+                for (uint32_t j = 0; j < cn; j++) {
+                    v += dc_of(dnode[j * 32u + lane]);
+                    stack_write(l0 + j, lane, v);
+                    gmin = min(gmin, v);
+                }
+                __syncwarp();
+            }
+
+            for (uint32_t blk = n0; blk < n1; blk += 32u) {
+                const uint4 rec = rnext;
+                if (blk + 32u < n1) rnext = __ldg(++recp);
+                zero_dnode();
+                __syncwarp();
+
+                // ================= C: the block's hits from the scanner =================
+                take_segment();
+
+                // ================= bound: can any pair of this block still be optimal? =================
+                const int lbase = gmin + neg[lane];
+                const int bound = min(bsc, gb);
+                const uint32_t needs = __ballot_sync(FULL, live && (int)rec.x + lbase <= bound);
+                if (needs) {
+                    // ---- A: headers (lane = node), only for blocks that get here
+                    const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.hdr) + blk + lane);
+                    const bool act = blk + lane < n1;
+                    const uint32_t level = h.z >> kLevelShift, flags = h.z & 0x3fffu;
+                    const bool dense_ok = act && (flags & kFlagValid0);
+                    const int min_g = __reduce_min_sync(FULL, dense_ok ? (int)h.x : BIG);            // signed: G can be < 0
+                    // hit nodes of this lane's sample = non-zero column entries (a pair whose packed delta is zero
+                    // scores exactly like a pair without a hit)
+                    uint32_t hmv = 0;
+#pragma unroll 8
+                    for (uint32_t n = 0; n < 32u; n++) hmv |= (dnode[n * 32u + lane] != 0 ? 1u : 0u) << n;
+                    area[kA4G + lane] = (uint32_t)h.x;
+                    area[kA4Z + lane] = h.z;
+                    area[kA4W + lane] = h.w;
+                    area[kA4Am + lane] = h.y;
+                    area[kA4Hm + lane] = hmv;
+                    __syncwarp();
+                    // correction of the path above node (level, am) for sample s
+                    auto above = [&](uint32_t lvl, uint32_t am, uint32_t hmask, uint32_t s) -> int {
+                        const uint32_t top = lvl - __popc(am);
+                        int v = top ? stack_read(top - 1u, s) : 0;
+                        uint32_t m = am & hmask;
+                        while (m) {
+                            const uint32_t a = __ffs(m) - 1;
+                            m &= m - 1;
+                            v += dc_of(dnode[a * 32u + s]);
+                        }
+                        return v;
+                    };
+                    // ---- E: non-hit pairs (lane = node), one sample at a time
+                    uint32_t need_e = __ballot_sync(FULL, live && min_g < BIG && min_g + lbase <= bound);
+                    while (need_e) {
+                        const uint32_t s = __ffs(need_e) - 1;
+                        need_e &= need_e - 1;
+                        const uint32_t hm_s = area[kA4Hm + s];
+                        const int sc = (int)h.x + above(level, h.y, hm_s, s);
+                        const int bs = __shfl_sync(FULL, bsc, s);
+                        uint32_t cm = __ballot_sync(FULL, dense_ok && !((hm_s >> lane) & 1u) && sc <= bs);
+                        while (cm) {
+                            const uint32_t j = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            const int scj = __shfl_sync(FULL, sc, j);
+                            const uint32_t huj = __shfl_sync(FULL, (flags & kFlagHu0) ? 1u : 0u, j);
+                            if (lane == s) merge(scj, huj, blk + j);
+                        }
+                    }
+                    // ---- F: hit pairs, exact (lane = sample)
+                    if ((needs >> lane) & 1u) {
+                        uint32_t hmw = hmv;
+                        while (hmw) {
+                            const uint32_t n = __ffs(hmw) - 1;
+                            hmw &= hmw - 1;
+                            int dcorr, da, dcom;
+                            unpack_delta4(dnode[n * 32u + lane], dcorr, da, dcom);
+                            const uint32_t z = area[kA4Z + n], w = area[kA4W + n];
+                            const uint32_t fl = z & 0x3fffu;
+                            const int g = (int)area[kA4G + n];
+                            int sc;
+                            bool valid;
+                            uint32_t hu;
+                            if (fl & kFlagRoot) {
+                                sc = g + dcorr; valid = true; hu = 0;
+                            } else {
+                                const bool masked = fl & kFlagMasked;
+                                if (masked) { da = 0; dcom = 0; }
+                                sc = g + above(z >> kLevelShift, area[kA4Am + n], hmv, lane) - da;
+                                const int common = (int)(w & 0xffffu) + dcom;
+                                hu = (masked || (int)(w >> 16) > common) ? 1u : 0u;
+                                valid = (fl & kFlagLeaf) ? common > 0 : (!hu || common > 0);
+                            }
+                            if (valid && sc <= bsc) merge(sc, hu, blk + n);
+                        }
+                    }
+                }
+                __syncwarp();
+
+                // ================= G: stack rows of the open chain (lane = sample) =================
+                uint32_t chain = rec.y;
+                if (chain) {
+                    uint32_t lv = rec.z;
+                    int v = lv ? stack_read(lv - 1u, lane) : 0;
+                    while (chain) {
+                        const uint32_t n = __ffs(chain) - 1;
+                        chain &= chain - 1;
+                        v += dc_of(dnode[n * 32u + lane]);
+                        stack_write(lv, lane, v);
+                        gmin = min(gmin, v);
+                        lv++;
+                    }
+                }
+                __syncwarp();
+            }
+            // publish an improved bound for the other units working on this sample group
+            if (!COLLECT && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
+            __syncwarp();
+        }
+
+        if (!COLLECT) {
+            // park the consumer's result in its own rows for the fold below
+            reinterpret_cast<unsigned long long*>(dnode)[lane] = bkey;
+            neg[lane] = (int)cnt;
+        }
+    }
+
+    if (COLLECT) return;
+    // fold the CTA's units, one partial row per CTA and group: warp c folds consumer c of every unit
+    __syncthreads();
+    if (warp < (uint32_t)NC && sg * NC + warp < p.ngroups) {
+        unsigned long long best = ~0ull;
+        for (int u = 0; u < C::kUnits; u++) {
+            const uint8_t* pb = smem + bm_bytes + kLut4Bytes + u * C::kUnit + C::kShared + warp * C::kCons;
+            best = min(best, reinterpret_cast<const unsigned long long*>(pb + C::kODnode)[lane]);
+        }
+        uint32_t c = 0;
+        for (int u = 0; u < C::kUnits; u++) {
+            const uint8_t* pb = smem + bm_bytes + kLut4Bytes + u * C::kUnit + C::kShared + warp * C::kCons;
+            if ((reinterpret_cast<const unsigned long long*>(pb + C::kODnode)[lane] >> 33) == (best >> 33))
+                c += reinterpret_cast<const uint32_t*>(pb + C::kONeg)[lane];
+        }
+        const size_t o = ((size_t)(sg * NC + warp) * ctas_per_sg + cta_in_sg) * 32u + lane;
+        p.part_key[o] = best;
+        p.part_cnt[o] = c;
+    }
+}
+
+}  // namespace ub200

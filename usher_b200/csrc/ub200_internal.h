@@ -101,14 +101,10 @@ struct Derived {
     std::vector<uint32_t> seed_end;   // end of each seed segment, in 4-word units
     std::vector<uint32_t> blk_words;  // [blocks] stream words of each block segment (row lengths, rounded up to 4)
     // per-block record the k_score4 consumer reads instead of the 32 headers (score_kernel4.cuh):
-    //   x = own_min  : min over the block's nodes of G - nmut            (lower bound term of the exact block bound)
-    //   y = sub_min  : min of the same over the block's nodes AND all their descendants inside the block's tile
-    //                  (static subtree bound: a block whose sub_min + cmin_s exceeds every sample's running best
-    //                  cannot influence any optimum, and neither can any block below it)
-    //   z = open mask: nodes with descendants beyond the block (the chain whose stack rows later blocks read)
-    //   w = level of the first open node << 14 | words of the block segment
+    //   x = min over the block's nodes of G - nmut (the block term of the exact lower bound)
+    //   y = open mask: nodes with descendants beyond the block (the chain whose stack rows later blocks read)
+    //   z = level of the first open node,  w = words of the block segment (= blk_words)
     std::vector<uint32_t> blk_rec;    // [blocks][4]
-    std::vector<int32_t> tile3_min;   // [T3] min own_min over the tile's blocks
     uint64_t seed_words = 0;          // stream words spent on seed segments
 };
 

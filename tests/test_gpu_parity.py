@@ -198,24 +198,32 @@ def test_config5_ambiguity_and_n_runs_vs_reference():
     rt.close(); m.close(); s.close()
 
 
-@pytest.mark.parametrize("nc,pass_samples", [(1, 32), (2, 64), (3, 96), (3, 256), (2, 96), (0, 256), (1, 256)])
-def test_scan_sharing_does_not_change_results(nc, pass_samples, monkeypatch):
-    """Several sample groups sharing one scan of the stream (union bitmap, NC consumers per scanner, foreign hits
-    dropped by the empty sample mask) and the dense pair expansion (N runs over a 4 kb genome: many samples call the
-    same position) against the port: whole optimal sets, 7 groups with a short last one."""
-    monkeypatch.setenv("UB200_MIN_TILE", "512")
+@pytest.fixture(scope="module")
+def sharing_case():
     s = capi.Synth(40_000, 6.0, 4000, capi.Synth.UNIFORM, 901)
     p, r, mu = s.arrays()
     sp, sc, _ = s.samples(200, capi.Synth.AMBIG, 17)
+    pt = port.PortTree(p, r, mu)
+    q = pt.search(sp, sc)
+    pt.close()
+    yield s, sp, sc, q
+    s.close()
+
+
+@pytest.mark.parametrize("nc,pass_samples", [(1, 32), (2, 64), (3, 96), (3, 256), (2, 96), (0, 256), (1, 256)])
+def test_scan_sharing_does_not_change_results(sharing_case, nc, pass_samples, monkeypatch):
+    """Several sample groups sharing one scan of the stream (union bitmap, NC consumers per scanner, foreign hits
+    dropped by the empty sample mask) and the dense (transposed) form of the hit phase (N runs over a 4 kb genome:
+    many samples call the same position) against the port: whole optimal sets, 7 groups with a short last one."""
+    monkeypatch.setenv("UB200_MIN_TILE", "512")
+    s, sp, sc, q = sharing_case
     m = capi.Mat.from_flat_struct(s.flat)
     m.set_pass_samples(pass_samples)
     m.set_scan_sharing(nc)
     got = common.placements_to_dict(m.place_batch(sp, sc, best_set=True))
-    pt = port.PortTree(p, r, mu)
-    q = pt.search(sp, sc)
     for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
         assert np.array_equal(np.asarray(got[k]).astype(np.int64), q[k].astype(np.int64)), (nc, pass_samples, k)
-    pt.close(); m.close(); s.close()
+    m.close()
 
 
 @pytest.mark.parametrize("nc", [1, 3])

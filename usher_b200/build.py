@@ -12,7 +12,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INC = os.path.join(ROOT, "include")
-LIB = os.path.join(PKG, "libusher_b200.so")
+PROFILE = bool(os.environ.get("UB200_PROFILE"))   # developer build with in-kernel cycle counters
+LIB = os.path.join(PKG, "libusher_b200_prof.so" if PROFILE else "libusher_b200.so")
 SYNTH = os.path.join(PKG, "libub200_synth.so")
 USHER = os.path.join(PKG, "usher")   # the drop-in CLI (host C++ over the C ABI)
 # The image exports CXX=/opt/gcc/bin/g++, a wrapper that links libstdc++ statically; a second libstdc++ in a
@@ -43,7 +44,7 @@ def build(force=False, verbose=False):
             _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC", "-shared", "-I", INC, "-I", CSRC,
             "-Xptxas", "-v" if verbose else "-warn-spills", "-o", LIB,
-        ] + srcs
+        ] + (["-DUB200_PROFILE"] if PROFILE else []) + srcs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
@@ -55,7 +56,7 @@ def build(force=False, verbose=False):
     hdir = os.path.join(CSRC, "host")
     hsrc = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir)) if f.endswith(".cpp")]
     hhdr = [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".hpp")]
-    if force or _stale(USHER, hsrc + hhdr + hdrs + [LIB]):
+    if not PROFILE and (force or _stale(USHER, hsrc + hhdr + hdrs + [LIB])):
         subprocess.check_call([HOSTCXX, "-std=c++17", "-O2", "-I", INC, "-I", hdir] + hsrc +
                               ["-o", USHER, "-L", PKG, "-lusher_b200", "-Wl,-rpath,$ORIGIN", "-lz"])
     return LIB, SYNTH

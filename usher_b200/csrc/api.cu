@@ -250,6 +250,7 @@ int launch_score4(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngro
     p.gstack = M->gstack3; p.gstack_levels = M->gstack3_levels;
     p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
     p.tile_counter = S->tile_counter;
+    p.prof = reinterpret_cast<unsigned long long*>(S->tile_counter + 64);   // 16 counters behind the tile counters
     CU(cudaMemsetAsync(S->tile_counter, 0, 256, M->stream));
     const uint32_t grid = std::max<uint32_t>(p.nsg, ((uint32_t)M->num_sms / p.nsg) * p.nsg);
     *wpg_out = grid / p.nsg;
@@ -483,7 +484,10 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
         if (!rc) rc = alloc((void**)&S->tab, (size_t)g * M->L * 32);
         if (!rc) rc = alloc((void**)&S->base, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->gbest, (size_t)g * 32 * 4);
-        if (!rc && !S->tile_counter) rc = alloc((void**)&S->tile_counter, 256);
+        if (!rc && !S->tile_counter) {
+            rc = alloc((void**)&S->tile_counter, 256 + 128);
+            if (!rc) CU(cudaMemset(S->tile_counter, 0, 256 + 128));
+        }
         if (!rc) rc = alloc((void**)&S->results, (size_t)g * 32 * sizeof(ub200_placement));
         if (!rc) rc = alloc((void**)&S->best_rel, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->sample_ptr, ((size_t)g * 32 + 1) * 8);
@@ -639,6 +643,16 @@ int ub200_results_download(ub200_mat* M, ub200_samples* S, ub200_placement* out)
     CU(cudaSetDevice(M->device));
     CU(cudaMemcpyAsync(out, S->results, (size_t)S->n_samples * sizeof(ub200_placement), cudaMemcpyDeviceToHost, M->stream));
     CU(cudaStreamSynchronize(M->stream));
+    return UB200_OK;
+}
+
+// Developer hook (UB200_PROFILE builds): the 16 cycle counters the scoring kernels accumulated since the last call.
+int ub200_debug_prof(ub200_mat* M, ub200_samples* S, unsigned long long* out16) {
+    if (!M || !S || !out16) return fail(UB200_E_ARG, "ub200_debug_prof: NULL argument");
+    CU(cudaSetDevice(M->device));
+    CU(cudaStreamSynchronize(M->stream));
+    CU(cudaMemcpy(out16, S->tile_counter + 64, 128, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(S->tile_counter + 64, 0, 128));
     return UB200_OK;
 }
 

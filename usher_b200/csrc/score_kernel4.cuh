@@ -98,7 +98,19 @@ struct Score4Params {
     const unsigned long long* set_ptr;
     uint32_t* set_fill;
     uint32_t* tile_counter;
+    unsigned long long* prof;     // UB200_PROFILE builds only: cycle counters per role (api.cu ub200_debug_prof)
 };
+
+// Developer instrumentation (compiled in with -DUB200_PROFILE): where the scanner and consumer warps spend their cycles.
+#ifdef UB200_PROFILE
+#define PROF_T0(v) const long long v = clock64()
+#define PROF_ADD(slot, v) pc[slot] += (unsigned long long)(clock64() - (v))
+#define PROF_INC(slot, n) pc[slot] += (n)
+#else
+#define PROF_T0(v)
+#define PROF_ADD(slot, v)
+#define PROF_INC(slot, n)
+#endif
 
 __device__ __forceinline__ uint32_t lds32_4(uint32_t a) {
     uint32_t v;
@@ -122,15 +134,35 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// wait of the scanner on a slot the consumers still hold: the consumers are the slower side then, so the scanner
-// backs off instead of polling (a polling warp eats issue slots the consumers need)
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(256);
-        if (++spins > (1u << 22)) __trap();
+// Waits on another warp.  mbarrier.try_wait does not suspend on this part (measured 21 ns per failed poll with or
+// without a time hint, scripts/ubench/sleep_probe.cu) while nanosleep sleeps what it is told, so a warp that finds its
+// barrier closed backs off exponentially: a waiting warp then costs a handful of issue slots and shared-memory
+// wavefronts per microsecond instead of fifty.
+__device__ __forceinline__ uint32_t mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t cap_ns) {
+    if (mbar_try_wait(bar, parity)) return 0u;
+    uint32_t ns = 32, spins = 0;
+    do {
+        __nanosleep(ns);
+        ns = min(ns * 2u, cap_ns);
+        if (++spins > (1u << 21)) __trap();   // a protocol bug must trap, never hang the GPU
+    } while (!mbar_try_wait(bar, parity));
+    return spins;   // failed polls (instrumentation)
+}
+// one 32-byte table row per lane: a single 256-bit load (one L1 wavefront per row instead of two)
+__device__ __forceinline__ void ldg_row(const uint32_t* row, uint4& r0, uint4& r1) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w), "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w)
+                 : "l"(row));
+}
+// row `lane` of a 32x32 bit matrix in, row `lane` of its transpose out (recursive block transpose, 5 shuffles)
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & (uint32_t)j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
     }
+    return x;
 }
 __device__ __noinline__ int spill_read4(const int32_t* gstk, uint32_t level, uint32_t s) {
     return gstk[(size_t)level * 32u + s];
@@ -148,15 +180,16 @@ __device__ __forceinline__ int lut_delta4(uint32_t i) {
     const int dcom = tk - t0;
     return dcorr * (1 << 20) + da * (1 << 10) + dcom;
 }
-// bitmap word of a stream word's position: narrow words carry the byte offset at bit 14
+// bitmap word of a stream word's position: narrow words carry the byte offset at bit 14.  The shared-memory form
+// is an explicit ld.shared on the 32-bit window address (a generic load here costs a trip through the L1TEX pipe).
 template <bool SMEM_BITMAP, bool NARROW>
-__device__ __forceinline__ uint32_t bitmap_word(const uint32_t* bm_s, const uint32_t* bm_g, uint32_t w) {
+__device__ __forceinline__ uint32_t bitmap_word(uint32_t bm_a, const uint32_t* bm_g, uint32_t w) {
     if (NARROW) {
         const uint32_t off = w >> 14;
-        return SMEM_BITMAP ? *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bm_s) + off)
+        return SMEM_BITMAP ? lds32_4(bm_a + off)
                            : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bm_g) + off));
     }
-    return SMEM_BITMAP ? bm_s[w >> 14] : __ldg(bm_g + (w >> 14));
+    return SMEM_BITMAP ? lds32_4(bm_a + ((w >> 14) << 2)) : __ldg(bm_g + (w >> 14));
 }
 __device__ __forceinline__ int dc_of(int v) { return (v + (1 << 19)) >> 20; }
 __device__ __forceinline__ void unpack_delta4(int v, int& dcorr, int& da, int& dcom) {
@@ -191,6 +224,10 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lt_mask = (1u << lane) - 1u;
     constexpr int BIG = 0x3fffffff;
+#ifdef UB200_PROFILE
+    unsigned long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_start = clock64();
+#endif
 
     // ---- shared memory: [bitmap][lut][unit 0 .. unit kUnits-1]
     uint32_t* bm_s = reinterpret_cast<uint32_t*>(smem);
@@ -201,6 +238,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
     uint32_t* list = reinterpret_cast<uint32_t*>(ubase + C::kOList);
     volatile uint2* msg = reinterpret_cast<volatile uint2*>(ubase + C::kOMsg);
     const uint32_t mring_a = smem_u32(mring), bars_a = smem_u32(ubase + C::kOBars), list_a = smem_u32(list);
+    const uint32_t bm_a = smem_u32(bm_s);
     constexpr uint32_t kBarFull = 0, kBarEmpty = kSlots4;
 
     const uint32_t* bm_g = p.bitmap + (size_t)sg * p.bitmap_words;
@@ -232,7 +270,9 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         uint32_t fill = 0;        // hit words in the open message
         auto open_msg = [&]() {   // wait until every consumer has released the slot
             const uint32_t s = nmsg % kSlots4;
-            mbar_wait_backoff(bars_a + 8 * (kBarEmpty + s), ((nmsg / kSlots4) & 1u) ^ 1u);
+            PROF_T0(tw);
+            const uint32_t polls = mbar_wait_sleep(bars_a + 8 * (kBarEmpty + s), ((nmsg / kSlots4) & 1u) ^ 1u, 512u);
+            PROF_ADD(1, tw); PROF_INC(2, polls); (void)polls;
             fill = 0;
         };
         auto send_msg = [&](uint32_t flags, uint32_t payload) {
@@ -302,26 +342,33 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 fill += remaining;
                 return;
             }
-            uint32_t mine = excl;           // index of this lane's next hit among these hits
-            uint32_t done = 0;              // hits already placed in messages
-            while (remaining) {
-                if (fill == kSlotCap4) {
-                    send_msg(0u, 0u);
-                    open_msg();
-                }
-                const uint32_t take = min(kSlotCap4 - fill, remaining);
-                const uint32_t slot_a = (nmsg % kSlots4) * kSlotCap4 + fill;
-                while (hb && mine < done + take) {
-                    const uint32_t bit = __ffs(hb) - 1;
-                    hb &= hb - 1;
-                    const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
-                    list[slot_a + (mine - done)] = lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2));
-                    mine++;
-                }
-                fill += take;
-                remaining -= take;
-                done += take;
+            // the hits spill over into further messages: reserve every slot they need first (a step holds at most 512
+            // hits = 8 slots), let all lanes copy their hits in ONE pass (hit p of the run goes to slot p / 64, word
+            // p % 64) and then send the full messages; the last one stays open
+            if (fill + remaining > kSlots4 * kSlotCap4) {   // would need a ninth slot: flush the open message
+                send_msg(0u, 0u);
+                open_msg();
             }
+            const uint32_t total = fill + remaining;
+            const uint32_t nslots = (total + kSlotCap4 - 1u) / kSlotCap4;
+            for (uint32_t i = 1; i < nslots; i++) {
+                const uint32_t mi = nmsg + i;
+                mbar_wait_sleep(bars_a + 8 * (kBarEmpty + mi % kSlots4), ((mi / kSlots4) & 1u) ^ 1u, 512u);
+            }
+            uint32_t pidx = fill + excl;
+            while (hb) {
+                const uint32_t bit = __ffs(hb) - 1;
+                hb &= hb - 1;
+                const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
+                const uint32_t slot = (nmsg + (pidx >> 6)) % kSlots4;
+                sts32_4(list_a + ((slot * kSlotCap4 + (pidx & 63u)) << 2), lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
+                pidx++;
+            }
+            for (uint32_t i = 1; i < nslots; i++) {
+                fill = kSlotCap4;
+                send_msg(0u, 0u);
+            }
+            fill = total - (nslots - 1u) * kSlotCap4;
         };
 
         // tiles are handed out in DFS order by a per-scan-group counter: balances uneven tiles, and the CTAs of
@@ -375,16 +422,18 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             for (uint32_t base = off;; base += 512u) {
                 // ---- one step: 4 rows = 16 words per lane, loaded and tested once
                 // everything issued so far has to be there (this step's rows went out one step ago)
+                PROF_T0(tl);
                 cp_async_wait<0>();
                 __syncwarp();
+                PROF_ADD(3, tl);
                 const uint32_t idx = base + 4u * lane;
                 uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
                 auto row_of = [&](uint32_t k) { return lds128_4(mring_a + (((idx + 128u * k) & (kRingWords4 - 1u)) << 2)); };
                 auto test4 = [&](const uint4& q) {
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.x), 0u, q.x), 1u);
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.y), 0u, q.y), 1u);
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.z), 0u, q.z), 1u);
-                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_s, bm_g, q.w), 0u, q.w), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.x), 0u, q.x), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.y), 0u, q.y), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.z), 0u, q.z), 1u);
+                    acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.w), 0u, q.w), 1u);
                 };
                 {
                     const uint4 q0 = row_of(0), q1 = row_of(1), q2 = row_of(2), q3 = row_of(3);
@@ -393,7 +442,10 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                     test4(q0); test4(q1); test4(q2); test4(q3);
                 }
                 const uint32_t hb_step = acc >> 16;                // bit 4k+j = word j of quad k
+                PROF_ADD(4, tl);                                   // load wait + test
+                PROF_INC(5, 1);                                    // steps
                 // ---- hand the step's hits out, segment by segment
+                PROF_T0(te);
                 bool tile_done = false;
                 for (;;) {
                     const uint32_t lim = min(seg_end, base + 512u);
@@ -408,10 +460,15 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                     }
                     if (off == base + 512u) break;
                 }
+                PROF_ADD(6, te);                                   // emission incl. slot waits
                 if (tile_done) break;
             }
             cur = nxt;
         }
+#ifdef UB200_PROFILE
+        pc[0] = (unsigned long long)(clock64() - prof_start);
+        if (lane == 0) for (int i = 0; i < 7; i++) atomicAdd(p.prof + i, pc[i]);
+#endif
     } else {
         // =====================================================================================================
         // consumer role-1 of the unit: one group of 32 samples
@@ -459,14 +516,16 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
             else if (sc == bsc) { cnt++; if (key < bkey) bkey = key; }
         };
+        int negr = 0;   // this lane's (= sample's) share of neg accumulated by the dense form of C
         auto zero_dnode = [&]() {
 #pragma unroll
             for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(dnode)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
             neg[lane] = 0;
+            negr = 0;
         };
-        // ---- C: the hit words of one message
-        // sparse form: lane = hit, the lane walks the samples that call the position
-        auto apply_hit = [&](uint32_t w, const uint4& r0, const uint2& r1) {
+        // ---- C: the hit words of one message, 32 at a time (lane = hit while the table rows are fetched)
+        // sparse form: the lane walks the samples that call its hit's position
+        auto apply_hit = [&](uint32_t w, const uint4& r0, const uint4& r1) {
             const uint32_t nl = (w >> 9) & 31u;
             const uint32_t lo = r0.y | ((w >> 5) & 15u);
             uint32_t pm = r0.x;
@@ -481,78 +540,72 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 if (dc < 0) atomicAdd(&neg[s], dc);
             }
         };
-        // dense form, first half: lane = hit writes its (hit, sample) pairs, LUT index << 10 | dnode index, into the
-        // pair list at its prefix position (only those of the current round)
-        auto expand_hit = [&](uint32_t w, const uint4& r0, const uint2& r1, uint32_t& idx, uint32_t lo_i, uint32_t hi_i) {
-            const uint32_t nlb = ((w >> 9) & 31u) << 5;
-            const uint32_t lo = r0.y | ((w >> 5) & 15u);
-            uint32_t pm = r0.x;
-            while (pm) {
-                const uint32_t s = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint32_t nw = (s & 16u) ? ((s & 8u) ? r1.y : r1.x) : ((s & 8u) ? r0.w : r0.z);
-                const uint32_t e4 = (nw >> ((s & 7u) * 4u)) & 15u;
-                if (idx >= lo_i && idx < hi_i) area[idx - lo_i] = (((e4 << 6) | lo) << 10) | nlb | s;
-                idx++;
+        // dense form (some position is called by more than two samples of the group): the 32 x 32 bit matrix
+        // hit x sample is transposed with 5 shuffles, after which lane = SAMPLE walks its own hits.  The lane owns
+        // column `lane` of dnode, so the updates need no atomics and hit no bank twice, and its share of neg stays
+        // in a register.  The hits' cost nibbles and (node lane, ref/prev/mut) words are staged in `area`.
+        auto dense32 = [&](uint32_t w, const uint4& r0, const uint4& r1, uint32_t t) {
+            area[lane] = r0.z;               // word j of hit h at j * 32 + ((h + 8 j) & 31): conflict-free for the
+            area[32u + ((lane + 8u) & 31u)] = r0.w;     // usual access patterns of the loop below
+            area[64u + ((lane + 16u) & 31u)] = r1.x;
+            area[96u + ((lane + 24u) & 31u)] = r1.y;
+            area[128u + lane] = ((w >> 9) & 31u) | ((r0.y | ((w >> 5) & 15u)) << 5);
+            __syncwarp();
+            const uint32_t j = lane >> 3, sh = (lane & 7u) * 4u;
+            while (t) {
+                const uint32_t h = __ffs(t) - 1;
+                t &= t - 1;
+                const uint32_t info = area[128u + h];
+                const uint32_t e4 = (area[j * 32u + ((h + 8u * j) & 31u)] >> sh) & 15u;
+                const int d = lut[(e4 << 6) | (info >> 5)];
+                dnode[(info & 31u) * 32u + lane] += d;
+                negr += min(dc_of(d), 0);
             }
+            __syncwarp();
+        };
+        // 32 hits: the sparse form costs ~20 issue slots per caller of the busiest hit, the dense one ~12 per hit of
+        // the busiest sample (an N run makes ONE sample own most of 32 position-sorted hits: sparse wins there)
+        auto half = [&](uint32_t w, const uint4& r0, const uint4& r1) {
+            const uint32_t mp = __reduce_max_sync(FULL, (uint32_t)__popc(r0.x));
+            if (mp > 2u) {
+                const uint32_t t = transpose32(r0.x, lane);
+                const uint32_t mt = __reduce_max_sync(FULL, (uint32_t)__popc(t));
+                if (12u * mt + 10u < 20u * mp) {
+                    dense32(w, r0, r1, t);
+                    return;
+                }
+            }
+            if (r0.x) apply_hit(w, r0, r1);
         };
         auto process = [&](uint32_t slot, uint32_t n) {
             static_assert(kSlotCap4 == 64, "two hits per lane");
             const bool h0 = lane < n, h1 = lane + 32u < n;
             uint32_t w0 = 0, w1 = 0;
-            uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0;
-            uint2 a1 = make_uint2(0, 0), b1 = a1;
+            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
             if (h0) {
                 w0 = list[slot * kSlotCap4 + lane];
-                const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w0) * 8u;
-                a0 = __ldg(reinterpret_cast<const uint4*>(row));
-                a1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+                ldg_row(tabg + (size_t)mut3_pos<NARROW>(w0) * 8u, a0, a1);
             }
             if (h1) {
                 w1 = list[slot * kSlotCap4 + 32u + lane];
-                const uint32_t* row = tabg + (size_t)mut3_pos<NARROW>(w1) * 8u;
-                b0 = __ldg(reinterpret_cast<const uint4*>(row));
-                b1 = __ldg(reinterpret_cast<const uint2*>(row + 4));
+                ldg_row(tabg + (size_t)mut3_pos<NARROW>(w1) * 8u, b0, b1);
             }
-            const uint32_t c = __popc(a0.x) + __popc(b0.x);     // rows of absent hits are zero
-            if (__ballot_sync(FULL, c > 2u) == 0u) {
-                if (a0.x) apply_hit(w0, a0, a1);
-                if (b0.x) apply_hit(w1, b0, b1);
-                return;
-            }
-            uint32_t incl = c;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL, incl, dlt);
-                if (lane >= (uint32_t)dlt) incl += v;
-            }
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
-            for (uint32_t r0i = 0; r0i < total; r0i += kPairCap4) {
-                const uint32_t r1i = min(total, r0i + kPairCap4);
-                uint32_t idx = incl - c;
-                if (idx < r1i && incl > r0i) {
-                    expand_hit(w0, a0, a1, idx, r0i, r1i);
-                    expand_hit(w1, b0, b1, idx, r0i, r1i);
-                }
-                __syncwarp();
-                for (uint32_t q = lane; q < r1i - r0i; q += 32u) {
-                    const uint32_t e = area[q];
-                    const int d = lut[e >> 10];
-                    atomicAdd(&dnode[e & 1023u], d);
-                    const int dc = dc_of(d);
-                    if (dc < 0) atomicAdd(&neg[e & 31u], dc);
-                }
-                __syncwarp();
-            }
+            // rows of absent hits are zero; rows of another group's hits have an empty sample mask
+            half(w0, a0, a1);
+            if (n > 32u) half(w1, b0, b1);
         };
         uint32_t nmsg = 0;
         // receive the messages of one segment and fold their hits into dnode / neg
         auto take_segment = [&]() {
             for (;;) {
                 const uint32_t s = nmsg % kSlots4;
-                mbar_wait_idle(bars_a + 8 * (kBarFull + s), (nmsg / kSlots4) & 1u, p.gbest);
+                PROF_T0(tw);
+                const uint32_t polls = mbar_wait_sleep(bars_a + 8 * (kBarFull + s), (nmsg / kSlots4) & 1u, 512u);
+                PROF_ADD(9, tw); PROF_INC(10, polls); (void)polls;
                 const uint32_t m = msg[s].x;
+                PROF_T0(tp);
                 if (m & 0xffffu) process(s, m & 0xffffu);
+                PROF_ADD(11, tp); PROF_INC(12, 1);
                 __syncwarp();
                 if (elect_one()) mbar_arrive(bars_a + 8 * (kBarEmpty + s));
                 nmsg++;
@@ -565,7 +618,9 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             uint32_t t;
             {
                 const uint32_t s = nmsg % kSlots4;
-                mbar_wait_long(bars_a + 8 * (kBarFull + s), (nmsg / kSlots4) & 1u);
+                PROF_T0(tw);
+                const uint32_t polls = mbar_wait_sleep(bars_a + 8 * (kBarFull + s), (nmsg / kSlots4) & 1u, 1024u);
+                PROF_ADD(13, tw); PROF_INC(10, polls); (void)polls;
                 const uint32_t m = msg[s].x;
                 t = msg[s].y;
                 __syncwarp();
@@ -609,10 +664,12 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 take_segment();
 
                 // ================= bound: can any pair of this block still be optimal? =================
-                const int lbase = gmin + neg[lane];
+                const int lbase = gmin + neg[lane] + negr;
                 const int bound = min(bsc, gb);
                 const uint32_t needs = __ballot_sync(FULL, live && (int)rec.x + lbase <= bound);
+                PROF_T0(tn);
                 if (needs) {
+                    PROF_INC(15, 1);
                     // ---- A: headers (lane = node), only for blocks that get here
                     const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.hdr) + blk + lane);
                     const bool act = blk + lane < n1;
@@ -688,6 +745,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                     }
                 }
                 __syncwarp();
+                PROF_ADD(14, tn);
 
                 // ================= G: stack rows of the open chain (lane = sample) =================
                 uint32_t chain = rec.y;
@@ -710,6 +768,10 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             __syncwarp();
         }
 
+#ifdef UB200_PROFILE
+        pc[8] = (unsigned long long)(clock64() - prof_start);
+        if (lane == 0 && !dead) for (int i = 8; i < 16; i++) atomicAdd(p.prof + i, pc[i]);
+#endif
         if (!COLLECT) {
             // park the consumer's result in its own rows for the fold below
             reinterpret_cast<unsigned long long*>(dnode)[lane] = bkey;

@@ -1,6 +1,4 @@
 set -x
 mkdir -p gpurun_out
-for cfg in "c4 0 32 1" "c4 0 96 3" "mid 2 32 1" "c3 1 96 3"; do
-  UB200_PROFILE=1 timeout 300 python scripts/prof_roles.py $cfg >> gpurun_out/i_prof.log 2>&1
-done
-cat gpurun_out/i_prof.log
+ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/m_c4 python scripts/one_launch.py c4 0 32 32 2 1 > gpurun_out/m_c4_ncu.log 2>&1
+tail -n 3 gpurun_out/m_c4_ncu.log

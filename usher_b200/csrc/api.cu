@@ -356,11 +356,11 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
         guard(dev_upload(&M->blk_rec, d.blk_rec.data(), d.blk_rec.size(), M->stream));
         M->device_bytes += d.stream.size() * 4 + d.hdr3.size() * 16 + d.tiekey.size() * 4 +
                            (d.tile3_start.size() * 4 + d.seed_end.size() + d.blk_words.size() + d.blk_rec.size()) * 4;
-        // spill rows of the consumers' level stacks: at most 24 consumers per SM (NC = 3), 32 levels in shared memory
+        // spill rows of the workers' level stacks: at most 32 per SM, the first 32 levels live in shared memory
         constexpr uint32_t kMinStack = (uint32_t)ub200::Cfg4<3>::kStack;
         if (!rc && d.max_level + 1 > kMinStack) {
             M->gstack3_levels = d.max_level + 1 - kMinStack;
-            const size_t bytes = (size_t)std::max(M->num_sms, 8) * 24u * M->gstack3_levels * 32 * sizeof(int32_t);
+            const size_t bytes = (size_t)std::max(M->num_sms, 8) * 32u * M->gstack3_levels * 32 * sizeof(int32_t);
             if (bytes > (size_t)16 << 30) {
                 rc = fail(UB200_E_LIMIT, "tree too deep for the spill stack (" + std::to_string(d.max_level) + " levels)");
             } else {

@@ -89,6 +89,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     const uint32_t pad = pack_mut3(nw, d.L, 0, 0, 0);
     auto conv = [&](uint32_t w, uint32_t lane) { return pack_mut3(nw, w >> 6, lane, (w >> 2) & 3u, w & 3u); };
     const uint32_t pshift = nw ? 16 : 14;
+    const bool pad_steps = !getenv("UB200_NO_STEP_PAD");   // developer switch: measure what the padding buys
     // Every tile's piece of the stream starts on a 1 KB boundary, so the pieces are built independently (one
     // host thread per slice of tiles) and concatenated afterwards.
     struct Piece { std::vector<uint32_t> words; std::vector<uint32_t> seed_end4; uint64_t seed_words = 0; };
@@ -107,6 +108,14 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
                 return px != py ? px < py : x < y;
             });
             while (seg.size() % 4) seg.push_back(pad);
+            // The kernel takes the tile's piece in steps of 512 words (4 rows) counted from the tile's start and
+            // hands the hits of a step out segment by segment.  A segment that starts on a step boundary is padded
+            // up to the next one when that costs at most an eighth of its length: it then spans the fewest possible
+            // steps, every step it touches belongs to it alone, and the segments behind it stay aligned.
+            if (pad_steps && out.size() % 512 == 0) {
+                const size_t padw = (512 - seg.size() % 512) % 512;
+                if (padw && padw * 8 <= seg.size()) seg.resize(seg.size() + padw, pad);
+            }
             size_t s0 = 0;
             while (s0 < seg.size()) {
                 const size_t off = out.size();

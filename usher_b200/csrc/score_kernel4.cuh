@@ -41,7 +41,7 @@ namespace ub200 {
 constexpr uint32_t kRingRows4 = 8;                         // rows of 128 words (512 B)
 constexpr uint32_t kRingWords4 = kRingRows4 * 128;         // 1024 words = 4 KB
 constexpr uint32_t kSlots4 = 8, kSlotCap4 = 64;            // scanner -> consumer messages
-constexpr uint32_t kPairCap4 = 224;                        // expanded (hit, sample) pairs per round
+constexpr uint32_t kAreaWords4 = 192;                      // per-consumer scratch (dense-form staging: 160, header copies: 160)
 constexpr uint32_t kLut4Bytes = 4096;
 constexpr uint32_t kMaxRowV4 = 500;      // packed 10-bit delta fields
 constexpr uint32_t kMaxCallsV4 = 16383;  // path corrections are int16 and reach -2 per call
@@ -67,9 +67,11 @@ struct Cfg4 {
     static constexpr uint32_t kONeg = kOStack + kStack * 64;   // i32[32]
     static constexpr uint32_t kOArea = kONeg + 128;         // u32[224]: pair list while hits arrive, header copies
                                                             // (G, Z, W, Am, Hm) while a block is evaluated
-    static constexpr uint32_t kCons = kOArea + kPairCap4 * 4;
+    static constexpr uint32_t kCons = kOArea + kAreaWords4 * 4;
     static constexpr uint32_t kUnit = (kShared + NC * kCons + 127) & ~127u;
     static constexpr uint32_t kFixed = kLut4Bytes + kUnits * kUnit;
+    // the 3.75 KB position bitmap of a 30 kb genome has to fit beside the units (else every bitmap test goes to L1/L2)
+    static_assert(kFixed + 3840 <= kSmemLimit4, "a 30 kb bitmap no longer fits shared memory");
 };
 constexpr uint32_t kA4G = 0, kA4Z = 32, kA4W = 64, kA4Am = 96, kA4Hm = 128;
 
@@ -299,6 +301,8 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         };
         // hand the hits of the current step that lie in stream words [off, lim) (multiples of 4, inside the step
         // starting at word `base`) to the open message; full messages are sent (not flagged last) and reopened
+        // hit words are stored from the registers they were tested in (q0..q3 = the step's four rows)
+        uint4 q0, q1, q2, q3;
         auto emit = [&](uint32_t hb_step, uint32_t base, uint32_t off, uint32_t lim) {
             const uint32_t idx = base + 4u * lane;
             uint32_t hb = hb_step;                            // bit 4k+j = word j of quad k (row k of the step)
@@ -328,42 +332,32 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 remaining = __shfl_sync(FULL, incl, 31);
                 excl = incl - c;
             }
-            if (remaining <= kSlotCap4 - fill) {
-                // common case: all of these hits fit the open message
-                uint32_t pa = list_a + (((nmsg % kSlots4) * kSlotCap4 + fill + excl) << 2);
-                while (hb) {
-                    uint32_t bit;
-                    asm("bfind.u32 %0, %1;" : "=r"(bit) : "r"(hb));   // highest set bit (FLO)
-                    hb ^= 1u << bit;
-                    const uint32_t wi = idx + ((bit & 12u) << 5) + (bit & 3u);
-                    sts32_4(pa, lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
-                    pa += 4u;
+            // The eight 64-word slots are one circular buffer of 512 words: hit p of this run goes to word
+            // (64 * open slot + fill + p) mod 512.  Hits that spill over into further messages first reserve every
+            // slot they need (a step holds at most 512 hits = 8 slots); the full messages are sent after the copy,
+            // the last one stays open.
+            const bool spans = remaining > kSlotCap4 - fill;
+            uint32_t nslots = 1;
+            if (spans) {
+                if (fill + remaining > kSlots4 * kSlotCap4) {   // would need a ninth slot: flush the open message
+                    send_msg(0u, 0u);
+                    open_msg();
                 }
-                fill += remaining;
-                return;
+                nslots = (fill + remaining + kSlotCap4 - 1u) / kSlotCap4;
+                for (uint32_t i = 1; i < nslots; i++) {
+                    const uint32_t mi = nmsg + i;
+                    mbar_wait_sleep(bars_a + 8 * (kBarEmpty + mi % kSlots4), ((mi / kSlots4) & 1u) ^ 1u, 512u);
+                }
             }
-            // the hits spill over into further messages: reserve every slot they need first (a step holds at most 512
-            // hits = 8 slots), let all lanes copy their hits in ONE pass (hit p of the run goes to slot p / 64, word
-            // p % 64) and then send the full messages; the last one stays open
-            if (fill + remaining > kSlots4 * kSlotCap4) {   // would need a ninth slot: flush the open message
-                send_msg(0u, 0u);
-                open_msg();
-            }
+            uint32_t pi = (nmsg % kSlots4) * kSlotCap4 + fill + excl;
+#define UB200_PUT(bit, val) \
+    if (hb & (1u << (bit))) { sts32_4(list_a + ((pi & (kSlots4 * kSlotCap4 - 1u)) << 2), (val)); pi++; }
+            UB200_PUT(0, q0.x) UB200_PUT(1, q0.y) UB200_PUT(2, q0.z) UB200_PUT(3, q0.w)
+            UB200_PUT(4, q1.x) UB200_PUT(5, q1.y) UB200_PUT(6, q1.z) UB200_PUT(7, q1.w)
+            UB200_PUT(8, q2.x) UB200_PUT(9, q2.y) UB200_PUT(10, q2.z) UB200_PUT(11, q2.w)
+            UB200_PUT(12, q3.x) UB200_PUT(13, q3.y) UB200_PUT(14, q3.z) UB200_PUT(15, q3.w)
+#undef UB200_PUT
             const uint32_t total = fill + remaining;
-            const uint32_t nslots = (total + kSlotCap4 - 1u) / kSlotCap4;
-            for (uint32_t i = 1; i < nslots; i++) {
-                const uint32_t mi = nmsg + i;
-                mbar_wait_sleep(bars_a + 8 * (kBarEmpty + mi % kSlots4), ((mi / kSlots4) & 1u) ^ 1u, 512u);
-            }
-            uint32_t pidx = fill + excl;
-            while (hb) {
-                const uint32_t bit = __ffs(hb) - 1;
-                hb &= hb - 1;
-                const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
-                const uint32_t slot = (nmsg + (pidx >> 6)) % kSlots4;
-                sts32_4(list_a + ((slot * kSlotCap4 + (pidx & 63u)) << 2), lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
-                pidx++;
-            }
             for (uint32_t i = 1; i < nslots; i++) {
                 fill = kSlotCap4;
                 send_msg(0u, 0u);
@@ -435,12 +429,11 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.z), 0u, q.z), 1u);
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.w), 0u, q.w), 1u);
                 };
-                {
-                    const uint4 q0 = row_of(0), q1 = row_of(1), q2 = row_of(2), q3 = row_of(3);
-                    // rows below this step are dead: top the ring up (needed one step from now) while the loads fly
-                    ring_fill(base >> 7);
-                    test4(q0); test4(q1); test4(q2); test4(q3);
-                }
+                q0 = row_of(0); q1 = row_of(1); q2 = row_of(2); q3 = row_of(3);
+                // every row below the NEXT step is dead once these loads are out (hit words are taken from the
+                // registers): top the ring up two steps ahead while the loads fly
+                ring_fill((base >> 7) + 4u);
+                test4(q0); test4(q1); test4(q2); test4(q3);
                 const uint32_t hb_step = acc >> 16;                // bit 4k+j = word j of quad k
                 PROF_ADD(4, tl);                                   // load wait + test
                 PROF_INC(5, 1);                                    // steps

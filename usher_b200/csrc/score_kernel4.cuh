@@ -65,7 +65,7 @@ struct Cfg4 {
     static constexpr uint32_t kODnode = 0;                  // i32[32][32] packed deltas
     static constexpr uint32_t kOStack = 4096;               // i16[kStack][32]
     static constexpr uint32_t kONeg = kOStack + kStack * 64;   // i32[32]
-    static constexpr uint32_t kOArea = kONeg + 128;         // u32[224]: pair list while hits arrive, header copies
+    static constexpr uint32_t kOArea = kONeg + 128;         // u32[192]: dense-form staging while hits arrive, header copies
                                                             // (G, Z, W, Am, Hm) while a block is evaluated
     static constexpr uint32_t kCons = kOArea + kAreaWords4 * 4;
     static constexpr uint32_t kUnit = (kShared + NC * kCons + 127) & ~127u;
@@ -301,8 +301,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         };
         // hand the hits of the current step that lie in stream words [off, lim) (multiples of 4, inside the step
         // starting at word `base`) to the open message; full messages are sent (not flagged last) and reopened
-        // hit words are stored from the registers they were tested in (q0..q3 = the step's four rows)
-        uint4 q0, q1, q2, q3;
+        uint4 q0, q1, q2, q3;   // the current step's four rows (16 words per lane)
         auto emit = [&](uint32_t hb_step, uint32_t base, uint32_t off, uint32_t lim) {
             const uint32_t idx = base + 4u * lane;
             uint32_t hb = hb_step;                            // bit 4k+j = word j of quad k (row k of the step)
@@ -332,32 +331,76 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 remaining = __shfl_sync(FULL, incl, 31);
                 excl = incl - c;
             }
-            // The eight 64-word slots are one circular buffer of 512 words: hit p of this run goes to word
-            // (64 * open slot + fill + p) mod 512.  Hits that spill over into further messages first reserve every
-            // slot they need (a step holds at most 512 hits = 8 slots); the full messages are sent after the copy,
-            // the last one stays open.
-            const bool spans = remaining > kSlotCap4 - fill;
-            uint32_t nslots = 1;
-            if (spans) {
-                if (fill + remaining > kSlots4 * kSlotCap4) {   // would need a ninth slot: flush the open message
-                    send_msg(0u, 0u);
-                    open_msg();
+            if (NC > 1) {
+                // Shared scans see 2-3 times the hits: the hit words are stored straight from the registers they were
+                // tested in (16 predicated stores, no ring re-read, no per-hit loop).  The eight 64-word slots are one
+                // circular buffer of 512 words: hit p of this run goes to word (64 * open slot + fill + p) mod 512.
+                // Hits that spill over into further messages first reserve every slot they need (a step holds at most
+                // 512 hits = 8 slots); the full messages are sent after the copy, the last one stays open.
+                uint32_t nslots = 1;
+                if (remaining > kSlotCap4 - fill) {
+                    if (fill + remaining > kSlots4 * kSlotCap4) {   // would need a ninth slot: flush the open message
+                        send_msg(0u, 0u);
+                        open_msg();
+                    }
+                    nslots = (fill + remaining + kSlotCap4 - 1u) / kSlotCap4;
+                    for (uint32_t i = 1; i < nslots; i++) {
+                        const uint32_t mi = nmsg + i;
+                        mbar_wait_sleep(bars_a + 8 * (kBarEmpty + mi % kSlots4), ((mi / kSlots4) & 1u) ^ 1u, 512u);
+                    }
                 }
-                nslots = (fill + remaining + kSlotCap4 - 1u) / kSlotCap4;
-                for (uint32_t i = 1; i < nslots; i++) {
-                    const uint32_t mi = nmsg + i;
-                    mbar_wait_sleep(bars_a + 8 * (kBarEmpty + mi % kSlots4), ((mi / kSlots4) & 1u) ^ 1u, 512u);
-                }
-            }
-            uint32_t pi = (nmsg % kSlots4) * kSlotCap4 + fill + excl;
+                uint32_t pi = (nmsg % kSlots4) * kSlotCap4 + fill + excl;
 #define UB200_PUT(bit, val) \
     if (hb & (1u << (bit))) { sts32_4(list_a + ((pi & (kSlots4 * kSlotCap4 - 1u)) << 2), (val)); pi++; }
-            UB200_PUT(0, q0.x) UB200_PUT(1, q0.y) UB200_PUT(2, q0.z) UB200_PUT(3, q0.w)
-            UB200_PUT(4, q1.x) UB200_PUT(5, q1.y) UB200_PUT(6, q1.z) UB200_PUT(7, q1.w)
-            UB200_PUT(8, q2.x) UB200_PUT(9, q2.y) UB200_PUT(10, q2.z) UB200_PUT(11, q2.w)
-            UB200_PUT(12, q3.x) UB200_PUT(13, q3.y) UB200_PUT(14, q3.z) UB200_PUT(15, q3.w)
+                UB200_PUT(0, q0.x) UB200_PUT(1, q0.y) UB200_PUT(2, q0.z) UB200_PUT(3, q0.w)
+                UB200_PUT(4, q1.x) UB200_PUT(5, q1.y) UB200_PUT(6, q1.z) UB200_PUT(7, q1.w)
+                UB200_PUT(8, q2.x) UB200_PUT(9, q2.y) UB200_PUT(10, q2.z) UB200_PUT(11, q2.w)
+                UB200_PUT(12, q3.x) UB200_PUT(13, q3.y) UB200_PUT(14, q3.z) UB200_PUT(15, q3.w)
 #undef UB200_PUT
+                const uint32_t total = fill + remaining;
+                for (uint32_t i = 1; i < nslots; i++) {
+                    fill = kSlotCap4;
+                    send_msg(0u, 0u);
+                }
+                fill = total - (nslots - 1u) * kSlotCap4;
+                return;
+            }
+            if (remaining <= kSlotCap4 - fill) {
+                // common case: all of these hits fit the open message
+                uint32_t pa = list_a + (((nmsg % kSlots4) * kSlotCap4 + fill + excl) << 2);
+                while (hb) {
+                    uint32_t bit;
+                    asm("bfind.u32 %0, %1;" : "=r"(bit) : "r"(hb));   // highest set bit (FLO)
+                    hb ^= 1u << bit;
+                    const uint32_t wi = idx + ((bit & 12u) << 5) + (bit & 3u);
+                    sts32_4(pa, lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
+                    pa += 4u;
+                }
+                fill += remaining;
+                return;
+            }
+            // the hits spill over into further messages: reserve every slot they need first (a step holds at most 512
+            // hits = 8 slots), let all lanes copy their hits in ONE pass (hit p of the run goes to slot p / 64, word
+            // p % 64) and then send the full messages; the last one stays open
+            if (fill + remaining > kSlots4 * kSlotCap4) {   // would need a ninth slot: flush the open message
+                send_msg(0u, 0u);
+                open_msg();
+            }
             const uint32_t total = fill + remaining;
+            const uint32_t nslots = (total + kSlotCap4 - 1u) / kSlotCap4;
+            for (uint32_t i = 1; i < nslots; i++) {
+                const uint32_t mi = nmsg + i;
+                mbar_wait_sleep(bars_a + 8 * (kBarEmpty + mi % kSlots4), ((mi / kSlots4) & 1u) ^ 1u, 512u);
+            }
+            uint32_t pidx = fill + excl;
+            while (hb) {
+                const uint32_t bit = __ffs(hb) - 1;
+                hb &= hb - 1;
+                const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
+                const uint32_t slot = (nmsg + (pidx >> 6)) % kSlots4;
+                sts32_4(list_a + ((slot * kSlotCap4 + (pidx & 63u)) << 2), lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
+                pidx++;
+            }
             for (uint32_t i = 1; i < nslots; i++) {
                 fill = kSlotCap4;
                 send_msg(0u, 0u);
@@ -430,9 +473,9 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.w), 0u, q.w), 1u);
                 };
                 q0 = row_of(0); q1 = row_of(1); q2 = row_of(2); q3 = row_of(3);
-                // every row below the NEXT step is dead once these loads are out (hit words are taken from the
-                // registers): top the ring up two steps ahead while the loads fly
-                ring_fill((base >> 7) + 4u);
+                // rows below this step are dead: top the ring up (needed one step from now) while the loads fly.
+                // With shared scans the hit words are taken from the registers, so this step's rows are dead too.
+                ring_fill((base >> 7) + (NC > 1 ? 4u : 0u));
                 test4(q0); test4(q1); test4(q2); test4(q3);
                 const uint32_t hb_step = acc >> 16;                // bit 4k+j = word j of quad k
                 PROF_ADD(4, tl);                                   // load wait + test

@@ -197,7 +197,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("UB200_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
     ap.add_argument("--samples-per-rank", type=int, default=1280)
-    ap.add_argument("--pass-samples", type=int, default=32)
+    ap.add_argument("--pass-samples", type=int, default=32, help="samples per scoring launch")
+    ap.add_argument("--scan-sharing", type=int, default=0, help="sample groups per scan of the stream (0 = from the pass width)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--family", default=None, choices=sorted(FAMILIES), help="sample family (default: the workload's)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs' records (extra)")
@@ -241,6 +242,7 @@ def main():
     mat = capi.Mat.from_flat_struct(synth.flat, device=local_rank)
     t_create = time.time() - t
     mat.set_pass_samples(args.pass_samples)
+    mat.set_scan_sharing(args.scan_sharing)
     # a real (non-default) stream shared by torch, NCCL and the library: CUDA events recorded through torch then see
     # the library's kernels (handle 0 would make the library fall back to its own stream)
     stream = torch.cuda.Stream(device=dev)
@@ -360,7 +362,7 @@ def main():
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": "ub200::k_score3<smem bitmap, best, narrow words>", "peak_source": peak_src,
+        "traffic": traffic, "kernel": "ub200::k_score4<groups per scan, smem bitmap, best, narrow words>", "peak_source": peak_src,
         "bytes_per_launch": int(mat.info.algorithmic_bytes), "launches": int(score_launches),
         "us_per_launch": 1000.0 * score_ms / max(score_launches, 1),
         "share_of_step": score_ms / (ev0.elapsed_time(ev1)) if ms_total > 0 else None,
@@ -368,20 +370,21 @@ def main():
     }
 
     # ------------------------------------------------------------------ the other BASELINE configs (rank 0, N=1)
-    def time_family(m, syn, family, n_samples, pass_samples, reps, seed):
+    def time_family(m, syn, family, n_samples, pass_samples, reps, seed, sharing=0, flags=0):
         """placements/s, us per launch and roofline fraction of `reps` resident-batch place calls (CUDA events of the
-        library, same stream) for one (tree, sample family, pass width)."""
+        library, same stream) for one (tree, sample family, pass width, groups per scan)."""
         m.set_pass_samples(pass_samples)
+        m.set_scan_sharing(sharing)
         spx, scx, _ = syn.samples(n_samples, family, seed)
         S = m.upload(spx, scx)
         for _ in range(2):
-            S.place(0, sync=True)
+            S.place(flags, sync=True)
         ms = sc_ms = 0.0
         nl = by = 0
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            S.place(0, sync=False)
+            S.place(flags, sync=False)
             e1.record()
             tmx = m.timing()
             ms += e0.elapsed_time(e1); sc_ms += tmx.score_ms; nl += tmx.score_launches; by += tmx.score_bytes
@@ -389,7 +392,8 @@ def main():
         calls_mean = float(np.diff(spx.astype(np.int64)).mean())
         gbs = (by / 1e9) / (sc_ms / 1000.0)
         return {"placements_per_s": n_samples * reps / (ms / 1000.0), "us_per_launch": 1000.0 * sc_ms / nl,
-                "samples_per_launch": pass_samples, "samples": n_samples, "launches": int(nl),
+                "samples_per_launch": pass_samples, "groups_per_scan": sharing or "auto", "samples": n_samples,
+                "launches": int(nl), "optimal_sets": bool(flags & 2),
                 "achieved_gbs": gbs, "frac": gbs / peak, "mean_calls_per_sample": calls_mean,
                 "family": FAMILY_NAME[family]}, (spx, scx)
 
@@ -401,9 +405,18 @@ def main():
             for name, family in (("c4_snv40", 0), ("c4_leaf", 1), ("c5_ambig", 2)):
                 if family == fam or nodes != 10_000_000:
                     continue
-                extra[name], extra_samples[family] = time_family(mat, synth, family, 256, 32, 3, 4242 + family)
+                extra[name], extra_samples[family] = time_family(mat, synth, family, 256, 32, 3, 4242 + family, 1)
                 log(f"[bench] extra {name}: {extra[name]}")
+            # the headline family at other operating points: three groups sharing one scan of the stream (the best
+            # pass width for throughput), and with the optimal-set pass (best_j_vec / node_has_unique) included
+            wname = f"{wl}_{FAMILY_NAME[fam]}"
+            extra[wname + "_96_per_launch_shared_scan"], _ = time_family(mat, synth, fam, 1152, 96, 3, 4260, 3)
+            extra[wname + "_32_per_launch"], _ = time_family(mat, synth, fam, 256, 32, 3, 4261, 1)
+            extra[wname + "_with_optimal_sets"], _ = time_family(mat, synth, fam, 256, 32, 3, 4262, 1, flags=2)
+            for k in (wname + "_96_per_launch_shared_scan", wname + "_32_per_launch", wname + "_with_optimal_sets"):
+                log(f"[bench] extra {k}: {extra[k]}")
             mat.set_pass_samples(args.pass_samples)
+            mat.set_scan_sharing(args.scan_sharing)
             if wl != "c3":
                 n3, mu3, L3, shape3, seed3, fam3 = WORKLOADS["c3"]
                 syn3 = capi.Synth(n3, mu3, L3, shape3, seed3)
@@ -463,7 +476,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": wl, "nodes": nodes, "mutations": int(synth.m), "genome_len": L,
                        "sample_family": FAMILY_NAME[fam], "samples_per_rank_per_step": B,
-                       "samples_per_launch": args.pass_samples, "parallelism": f"samples sharded x{world}, 1 allgather/step",
+                       "samples_per_launch": args.pass_samples,
+                       "groups_per_scan": args.scan_sharing or ("auto: min(3, groups per launch)"), "parallelism": f"samples sharded x{world}, 1 allgather/step",
                        "l2": "inputs (%.2f GB MAT) exceed the 126 MB L2; no flush needed" % (mat.info.algorithmic_bytes / 1e9)},
             "e2e": {"value": e2e_value, "unit": "placements/s", "h2d_bytes_per_step": int(h2d / args.steps),
                     "d2h_bytes_per_step": int(d2h / args.steps)},

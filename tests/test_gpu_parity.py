@@ -243,3 +243,33 @@ def test_tiny_blocks_many_segments_per_step(nc, monkeypatch):
     for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
         assert np.array_equal(np.asarray(got[k]).astype(np.int64), q[k].astype(np.int64)), (nc, k)
     pt.close(); m.close(); s.close()
+
+
+@pytest.mark.parametrize("n_calls", [16_300, 17_500])
+def test_many_calls_near_the_int16_stack_limit(n_calls):
+    """A sample that carries every mutation of a deep chain: its path corrections fall by 2 per call and reach
+    -2 * calls.  Up to 16383 calls they fit the streaming kernel's int16 stack rows; longer call lists must switch to
+    the first-generation kernel — both against the port."""
+    parent, row_ptr, muts, refg = small_synth.random_mat(4242, 500, 400_000, 300.0, p_masked=0.0, shape="chain")
+    lvl = np.zeros(len(parent), np.int64)
+    for i in range(1, len(parent)):
+        lvl[i] = lvl[parent[i]] + 1
+    deep = int(np.argmax(lvl))
+    g = small_synth.genotype(parent, row_ptr, muts, deep)
+    sites = sorted(p for p, nuc in g.items() if nuc != refg[p])
+    assert len(sites) >= n_calls, len(sites)
+    calls = np.zeros(n_calls + 3, capi.MUT_DTYPE)
+    for i, p in enumerate(sites[:n_calls]):
+        calls[i] = (p, int(refg[p]), int(refg[p]), g[p], 0)
+    # a second, short sample in the same group
+    short = [p for p in sites[n_calls - 50:n_calls - 47]]
+    for i, p in enumerate(short):
+        calls[n_calls + i] = (p, int(refg[p]), int(refg[p]), g[p], 0)
+    s_ptr = np.array([0, n_calls, n_calls + 3], np.uint64)
+    m = capi.Mat(parent, row_ptr, muts)
+    got = common.placements_to_dict(m.place_batch(s_ptr, calls, best_set=True))
+    pt = port.PortTree(parent, row_ptr, muts)
+    q = pt.search(s_ptr, calls)
+    for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
+        assert np.array_equal(np.asarray(got[k]).astype(np.int64), q[k].astype(np.int64)), (n_calls, k)
+    pt.close(); m.close()

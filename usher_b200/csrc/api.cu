@@ -101,7 +101,7 @@ struct ub200_samples {
     uint32_t* set_out = nullptr;
     unsigned long long* set_ptr = nullptr;
     uint32_t* set_fill = nullptr;
-    uint64_t set_total = 0;
+    uint64_t set_total = 0, set_cap = 0;
     bool have_results = false, have_node_scores = false, have_set = false;
     float prep_ms = 0.f;
     uint64_t max_calls = 0;    // longest call list in the batch
@@ -134,13 +134,24 @@ int span_end(ub200_mat* M) {
     return 0;
 }
 
+// exclusive prefix of num_best over the batch (one block: per-thread chunks, then a scan of the chunk sums)
 __global__ void k_prefix_numbest(const ub200_placement* r, uint32_t n, unsigned long long* ptr) {
-    // single thread: n is the batch size (<= a few 100k); runs once per BEST_SET request
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long acc = 0;
-        for (uint32_t i = 0; i < n; i++) { ptr[i] = acc; acc += r[i].num_best; }
-        ptr[n] = acc;
+    __shared__ unsigned long long part[1024];
+    const uint32_t t = threadIdx.x, per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+    unsigned long long acc = 0;
+    for (uint32_t i = lo; i < hi; i++) acc += r[i].num_best;
+    part[t] = acc;
+    __syncthreads();
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+        const unsigned long long v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
     }
+    acc = t ? part[t - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) { ptr[i] = acc; acc += r[i].num_best; }
+    if (t == blockDim.x - 1) ptr[n] = part[t];
 }
 
 template <int MODE>
@@ -184,16 +195,27 @@ int ensure_v1(ub200_mat* M) {
     guard(dev_upload(&M->tile_start, d.tile_start.data(), d.tile_start.size(), M->stream));
     guard(dev_upload(&M->anc_ptr, d.anc_ptr.data(), d.anc_ptr.size(), M->stream));
     guard(dev_upload(&M->anc, d.anc.data(), d.anc.size(), M->stream));
-    if (rc) return rc;
-    M->device_bytes += d.mutw.size() * 4 + d.hdr.size() * 16 + d.row32.size() * 4 + d.tile_start.size() * 4 +
-                       d.anc_ptr.size() * 4 + d.anc.size() * 4;
+    auto drop_v1 = [&]() {   // a failed upload must not leave half a layout behind (the next call starts over)
+        cudaFree(M->mutw); cudaFree(M->hdr); cudaFree(M->row32); cudaFree(M->tile_start); cudaFree(M->anc_ptr);
+        cudaFree(M->anc); cudaFree(M->gstack);
+        M->mutw = nullptr; M->hdr = nullptr; M->row32 = M->tile_start = M->anc_ptr = M->anc = nullptr; M->gstack = nullptr;
+        M->gstack_levels = 0;
+    };
+    if (rc) { drop_v1(); return rc; }
+    uint64_t v1_bytes = d.mutw.size() * 4 + d.hdr.size() * 16 + d.row32.size() * 4 + d.tile_start.size() * 4 +
+                        d.anc_ptr.size() * 4 + d.anc.size() * 4;
     if (d.max_level + 1 > (uint32_t)ub200::kStackDepth) {
         M->gstack_levels = d.max_level + 1 - ub200::kStackDepth;
         const size_t bytes = (size_t)M->grid * ub200::kWarpsPerCta * M->gstack_levels * 32 * sizeof(int32_t);
-        CU(cudaMalloc((void**)&M->gstack, bytes));
-        M->device_bytes += bytes;
+        cudaError_t e = cudaMalloc((void**)&M->gstack, bytes);
+        if (e != cudaSuccess) { drop_v1(); return fail((int)e, std::string("cudaMalloc spill stack: ") + cudaGetErrorString(e)); }
+        v1_bytes += bytes;
     }
-    CU(cudaStreamSynchronize(M->stream));
+    {
+        cudaError_t e = cudaStreamSynchronize(M->stream);
+        if (e != cudaSuccess) { drop_v1(); return fail((int)e, std::string("upload: ") + cudaGetErrorString(e)); }
+    }
+    M->device_bytes += v1_bytes;
     M->v1_resident = true;
     return 0;
 }
@@ -336,7 +358,13 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
     M->n = d.n; M->m = d.m; M->L = d.L; M->n_tiles = (uint32_t)d.tile_start.size() - 1;
     rc = 0;
     auto guard = [&](int r) { if (r && !rc) rc = r; };
-    CU(cudaStreamCreateWithFlags(&M->own_stream, cudaStreamNonBlocking));
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&M->own_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            ub200_mat_destroy(M);
+            return fail((int)e, std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(e));
+        }
+    }
     M->stream = M->own_stream;
     guard(dev_upload(&M->key_to_node, d.key_to_node.data(), d.key_to_node.size(), M->stream));
     guard(dev_upload(&M->tie_index, d.tie_index.data(), d.tie_index.size(), M->stream));
@@ -543,8 +571,19 @@ int ub200_results_copy_device(ub200_mat* M, ub200_samples* S, void* dst_dev) {
     return UB200_OK;
 }
 
+static int place_resident_impl(ub200_mat* M, ub200_samples* S, uint32_t flags, int sync);
+
 int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int sync) {
     if (!M || !S || S->mat != M) return fail(UB200_E_ARG, "ub200_place_resident: bad handles");
+    const int rc = place_resident_impl(M, S, flags, sync);
+    if (rc) {   // a failed call leaves no half-recorded timing spans behind (ub200_last_timing would read them)
+        M->spans.clear(); M->ev_used = 0; M->last = {};
+        S->have_results = S->have_node_scores = S->have_set = false;
+    }
+    return rc;
+}
+
+static int place_resident_impl(ub200_mat* M, ub200_samples* S, uint32_t flags, int sync) {
     CU(cudaSetDevice(M->device));
     const bool smem_bitmap = S->bitmap_words * 4u <= ub200::kMaxSmemBitmapBytes;
     // the streaming kernel packs per-(node,sample) deltas in 10-bit fields and path corrections in int16
@@ -596,13 +635,19 @@ int ub200_place_resident(ub200_mat* M, ub200_samples* S, uint32_t flags, int syn
         S->have_node_scores = true;
     }
     if (flags & UB200_WANT_BEST_SET) {
-        k_prefix_numbest<<<1, 1, 0, M->stream>>>(S->results, S->n_samples, S->set_ptr);
+        k_prefix_numbest<<<1, 1024, 0, M->stream>>>(S->results, S->n_samples, S->set_ptr);
         CU(cudaGetLastError());
         unsigned long long total = 0;
         CU(cudaMemcpyAsync(&total, S->set_ptr + S->n_samples, 8, cudaMemcpyDeviceToHost, M->stream));
         CU(cudaStreamSynchronize(M->stream));
-        cudaFree(S->set_out); S->set_out = nullptr;
-        CU(cudaMalloc((void**)&S->set_out, std::max<size_t>((size_t)total, 1) * 4));
+        // the size of the optimal sets is only known now: this request synchronises the stream (documented in the
+        // header); the buffer is kept and only ever grows
+        if (total > S->set_cap || !S->set_out) {
+            cudaFree(S->set_out); S->set_out = nullptr; S->set_cap = 0;
+            const size_t cap = std::max<size_t>((size_t)total + (size_t)total / 4, 1024);
+            CU(cudaMalloc((void**)&S->set_out, cap * 4));
+            S->set_cap = cap;
+        }
         S->set_total = total;
         CU(cudaMemsetAsync(S->set_fill, 0, (size_t)S->n_groups * 32 * 4, M->stream));
         for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
@@ -696,7 +741,12 @@ int ub200_place_batch(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_p
     // sub-batches bounded by the resident table size
     const size_t per_group = (size_t)M->L * 32;
     uint32_t max_groups = (uint32_t)std::min<size_t>(1u << 16, std::max<size_t>(1, ((size_t)4 << 30) / std::max<size_t>(per_group, 1)));
-    const uint32_t step = max_groups * 32;
+    uint32_t step = max_groups * 32;
+    if (flags & UB200_WANT_NODE_SCORES) {
+        // per-node scores are n_nodes * 4 bytes per sample on the device: keep a sub-batch's block under ~2 GB
+        const uint64_t fit = ((uint64_t)2 << 30) / ((uint64_t)M->n * 4u);
+        step = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(step, fit / 32 * 32));
+    }
     uint64_t set_off = 0;
     bool overflow = false;
     if (best_set_ptr) best_set_ptr[0] = 0;

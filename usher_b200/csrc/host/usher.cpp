@@ -98,18 +98,19 @@ int main(int argc, char** argv) {
     MAT::Tree T;
     Timer timer;
     bool from_newick = false;
-    if (!din.empty()) {
-        timer.Start();
-        fprintf(stderr, "Loading existing mutation-annotated tree object from file %s\n", din.c_str());
-        T = MAT::load_mutation_annotated_tree(din);
-        fprintf(stderr, "Completed in %ld msec \n\n", timer.Stop());
-    } else if (!tree_fn.empty()) {
+    // the reference takes the tree + VCF build path when both -t and -i are given (src/usher.cpp:130)
+    if (!tree_fn.empty()) {
         fprintf(stderr, "Loading input tree.\n");
         timer.Start();
         T = MAT::create_tree_from_newick(tree_fn);
         if (!T.root) { fprintf(stderr, "ERROR: Empty tree.\n"); return 1; }
         fprintf(stderr, "Completed in %ld msec \n\n", timer.Stop());
         from_newick = true;
+    } else if (!din.empty()) {
+        timer.Start();
+        fprintf(stderr, "Loading existing mutation-annotated tree object from file %s\n", din.c_str());
+        T = MAT::load_mutation_annotated_tree(din);
+        fprintf(stderr, "Completed in %ld msec \n\n", timer.Stop());
     } else {
         fprintf(stderr, "Error! No input tree or assignment file provided!\n");
         return 1;

@@ -159,6 +159,22 @@ int ub200_mat_synchronize(ub200_mat* mat);
 /* CUDA-event timings of the last place call on this handle (valid after it completed). */
 int ub200_last_timing(ub200_mat* mat, ub200_timing* out);
 
+/* ---- several GPUs of one box (replaces the one tbb::parallel_for over nodes of src/usher_common.cpp:389-414 by
+ * "samples sharded over devices"; BASELINE configs 4/5).  The tree is derived once and replicated on `n_devices`
+ * devices (0 = every visible device; `devices` = their ordinals or NULL for 0..n-1), one host thread per device.
+ * ub200_multi_place_batch has the contract of ub200_place_batch: the batch is cut into contiguous shards of whole
+ * 32-sample groups, every device scores its shard against its replica, and each writes its records straight into
+ * the caller's host arrays (results are identical to a single-device call: placements do not depend on how samples
+ * are grouped).  ub200_multi_mat() exposes replica i for the tunables above. */
+typedef struct ub200_multi ub200_multi;
+int ub200_multi_create(const ub200_flat_mat* flat, int n_devices, const int* devices, ub200_multi** out);
+void ub200_multi_destroy(ub200_multi* multi);
+int ub200_multi_size(const ub200_multi* multi);
+ub200_mat* ub200_multi_mat(ub200_multi* multi, int i);
+int ub200_multi_place_batch(ub200_multi* multi, uint32_t n_samples, const uint64_t* sample_ptr,
+                            const ub200_mutation* sample_calls, uint32_t flags, ub200_placement* out,
+                            int32_t* node_scores, uint32_t* best_set, uint64_t* best_set_ptr, uint64_t best_set_cap);
+
 #ifdef __cplusplus
 }
 #endif

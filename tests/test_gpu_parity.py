@@ -273,3 +273,24 @@ def test_many_calls_near_the_int16_stack_limit(n_calls):
     for k in ("score", "best_dfs", "best_j", "num_best", "has_unique", "best_set", "best_set_unique"):
         assert np.array_equal(np.asarray(got[k]).astype(np.int64), q[k].astype(np.int64)), (n_calls, k)
     pt.close(); m.close()
+
+
+def test_multi_device_shards_equal_single_device():
+    """ub200_multi_place_batch: the batch cut into contiguous shards over several replicas (here two replicas on the
+    same GPU, so that the shard / gather code runs on a one-GPU box too; every visible GPU when there are more) gives
+    the records and optimal sets of a single-device call."""
+    s = capi.Synth(60_000, 8.0, 8000, capi.Synth.UNIFORM, 515)
+    sp, sc, _ = s.samples(333, capi.Synth.AMBIG, 21)
+    one = capi.Mat.from_flat_struct(s.flat)
+    a = one.place_batch(sp, sc, best_set=True)
+    ndev = capi.lib().ub200_device_count()
+    for devices in ([0, 0], list(range(ndev)) + [0]):
+        mm = capi.MultiMat(s.flat, devices=devices)
+        assert mm.size == len(devices)
+        mm.set_pass_samples(96)
+        b = mm.place_batch(sp, sc, best_set=True)
+        assert np.array_equal(a["placements"], b["placements"])
+        assert np.array_equal(a["best_set_ptr"], b["best_set_ptr"]) and np.array_equal(a["best_set"], b["best_set"])
+        assert np.array_equal(a["best_set_unique"], b["best_set_unique"])
+        mm.close()
+    one.close(); s.close()

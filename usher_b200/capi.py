@@ -67,6 +67,7 @@ EXPORTS = [
     "ub200_samples_upload", "ub200_samples_free", "ub200_place_resident", "ub200_results_download",
     "ub200_results_device_ptr", "ub200_node_scores_download", "ub200_best_set_download", "ub200_mat_set_stream",
     "ub200_mat_synchronize", "ub200_last_timing", "ub200_results_copy_device", "ub200_mat_set_scan_sharing",
+    "ub200_multi_create", "ub200_multi_destroy", "ub200_multi_size", "ub200_multi_mat", "ub200_multi_place_batch",
 ]
 
 
@@ -98,6 +99,13 @@ def lib():
         L.ub200_mat_set_stream.argtypes = [vp, vp]
         L.ub200_mat_synchronize.argtypes = [vp]
         L.ub200_last_timing.argtypes = [vp, C.POINTER(Timing)]
+        L.ub200_multi_create.argtypes = [C.POINTER(FlatMat), C.c_int, vp, C.POINTER(vp)]
+        L.ub200_multi_destroy.argtypes = [vp]
+        L.ub200_multi_destroy.restype = None
+        L.ub200_multi_size.argtypes = [vp]
+        L.ub200_multi_mat.argtypes = [vp, C.c_int]
+        L.ub200_multi_mat.restype = vp
+        L.ub200_multi_place_batch.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, u64]
         L.ub200_debug_derive.argtypes = [C.POINTER(FlatMat), u32, u32, C.POINTER(vp), C.POINTER(DerivedView),
                                          C.c_char_p, C.c_size_t]
         L.ub200_debug_derive_free.argtypes = [vp]
@@ -269,6 +277,53 @@ class Mat:
 
     def upload(self, s_ptr, calls):
         return Samples(self, s_ptr, calls)
+
+
+class MultiMat:
+    """One replica of a tree per GPU of this box (ub200_multi); place_batch shards the samples over the replicas."""
+
+    def __init__(self, flat, n_devices=0, devices=None):
+        self._flat = flat
+        self.h = C.c_void_p()
+        ids = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        _check(lib().ub200_multi_create(C.byref(flat), len(ids) if ids is not None else n_devices, _p(ids), C.byref(self.h)))
+        self.size = lib().ub200_multi_size(self.h)
+        self.n = flat.n_nodes
+
+    def set_pass_samples(self, n, sharing=0):
+        for i in range(self.size):
+            m = lib().ub200_multi_mat(self.h, i)
+            _check(lib().ub200_mat_set_pass_samples(m, n))
+            _check(lib().ub200_mat_set_scan_sharing(m, sharing))
+
+    def place_batch(self, s_ptr, calls, best_set=False):
+        s_ptr = np.ascontiguousarray(s_ptr, dtype=np.uint64)
+        calls = np.ascontiguousarray(calls, dtype=MUT_DTYPE)
+        B = len(s_ptr) - 1
+        out = np.zeros(B, PLACEMENT_DTYPE)
+        bptr = np.zeros(B + 1, np.uint64) if best_set else None
+        cap = max(1024, 4 * B)
+        while True:
+            bset = np.zeros(cap, np.uint32) if best_set else None
+            rc = lib().ub200_multi_place_batch(self.h, B, _p(s_ptr), _p(calls), WANT_BEST_SET if best_set else 0, _p(out),
+                                               None, _p(bset), _p(bptr), cap if best_set else 0)
+            if rc == E_CAPACITY:
+                cap = int(bptr[B]) + 16
+                continue
+            _check(rc)
+            break
+        res = {"placements": out}
+        if best_set:
+            res["best_set_ptr"] = bptr
+            raw = bset[: int(bptr[B])]
+            res["best_set"] = raw & np.uint32(0x7FFFFFFF)
+            res["best_set_unique"] = (raw >> np.uint32(31)).astype(np.uint8)
+        return res
+
+    def close(self):
+        if self.h:
+            lib().ub200_multi_destroy(self.h)
+            self.h = None
 
 
 class Samples:

@@ -5,7 +5,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cstdlib>
@@ -44,8 +46,12 @@ int dev_upload(T** dst, const T* src, size_t count, cudaStream_t st) {
 }  // namespace
 
 struct ub200_mat {
+    // host copies of the derived arrays: the small ones stay, the streamed ones are freed after upload.  Replicas of
+    // one tree on several devices (ub200_multi) share one derivation.
+    std::shared_ptr<ub200::Derived> dp;
+    ub200::Derived& d;
+    explicit ub200_mat(std::shared_ptr<ub200::Derived> p) : dp(std::move(p)), d(*dp) {}
     int device = 0;
-    ub200::Derived d;           // host copies of the small derived arrays (big ones are freed after upload)
     uint32_t n = 0, n_tiles = 0, L = 0;
     uint64_t m = 0;
     // device: k_score3 layout (always resident when the genome fits its 23-bit position field)
@@ -333,30 +339,42 @@ void ub200_mat_destroy(ub200_mat* M) {
     delete M;
 }
 
-int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
-    if (!flat || !out) return fail(UB200_E_ARG, "ub200_mat_create: NULL argument");
-    *out = nullptr;
-    int ndev = ub200_device_count();
-    if (ndev <= 0) return fail(UB200_E_NO_DEVICE, "ub200_mat_create: no CUDA device (there is no CPU path)");
-    if (device < 0 || device >= ndev) return fail(UB200_E_ARG, "ub200_mat_create: bad device ordinal");
-    CU(cudaSetDevice(device));
+// Tile workers of the scoring kernels on a device (k_score: 2 CTAs x 8 warps per SM, k_score4: 16 units per SM)
+static int device_workers(int device, int* num_sms, uint32_t* workers) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    auto* M = new ub200_mat();
-    M->device = device;
-    M->num_sms = prop.multiProcessorCount;
-    M->grid = (uint32_t)M->num_sms * 2u;
-    // workers of either kernel (k_score: 2 CTAs x 8 warps per SM, k_score3: 1 CTA x kPairs3 warp pairs)
-    const uint32_t warps3 = (uint32_t)std::max(M->num_sms, 8) * 16u;   // tile workers = scanner/consumer units (NC = 1)
-    const uint32_t total_warps = std::max<uint32_t>(M->grid * ub200::kWarpsPerCta, warps3);
+    *num_sms = prop.multiProcessorCount;
+    const uint32_t warps3 = (uint32_t)std::max(*num_sms, 8) * 16u;
+    *workers = std::max<uint32_t>((uint32_t)*num_sms * 2u * ub200::kWarpsPerCta, warps3);
+    return 0;
+}
+
+static int derive_for(const ub200_flat_mat* flat, uint32_t workers, std::shared_ptr<ub200::Derived>& out) {
+    auto d = std::make_shared<ub200::Derived>();
     std::string err;
     const char* mt = getenv("UB200_MIN_TILE");   // test hook: cut small trees into many tiles
     const char* tw = getenv("UB200_TILES_PER_WORKER");
-    int rc = ub200::derive(*flat, total_warps * (tw ? (uint32_t)atoi(tw) : 3u), M->d, err, mt ? (uint32_t)atoi(mt) : 0u);
-    if (rc != UB200_OK) { delete M; return fail(rc, err); }
+    int rc = ub200::derive(*flat, workers * (tw ? (uint32_t)atoi(tw) : 3u), *d, err, mt ? (uint32_t)atoi(mt) : 0u);
+    if (rc != UB200_OK) return fail(rc, err);
+    out = d;
+    return UB200_OK;
+}
+
+// Stage a derived tree on one device.  The streamed host arrays (d.stream, d.hdr3) are left alone: the caller frees them
+// once every replica is resident.
+static int mat_upload(std::shared_ptr<ub200::Derived> dp, int device, ub200_mat** out) {
+    *out = nullptr;
+    CU(cudaSetDevice(device));
+    int num_sms = 0;
+    uint32_t workers = 0;
+    { int rc = device_workers(device, &num_sms, &workers); if (rc) return rc; }
+    auto* M = new ub200_mat(std::move(dp));
+    M->device = device;
+    M->num_sms = num_sms;
+    M->grid = (uint32_t)M->num_sms * 2u;
     auto& d = M->d;
     M->n = d.n; M->m = d.m; M->L = d.L; M->n_tiles = (uint32_t)d.tile_start.size() - 1;
-    rc = 0;
+    int rc = 0;
     auto guard = [&](int r) { if (r && !rc) rc = r; };
     {
         cudaError_t e = cudaStreamCreateWithFlags(&M->own_stream, cudaStreamNonBlocking);
@@ -384,11 +402,11 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
         guard(dev_upload(&M->blk_rec, d.blk_rec.data(), d.blk_rec.size(), M->stream));
         M->device_bytes += d.stream.size() * 4 + d.hdr3.size() * 16 + d.tiekey.size() * 4 +
                            (d.tile3_start.size() * 4 + d.seed_end.size() + d.blk_words.size() + d.blk_rec.size()) * 4;
-        // spill rows of the workers' level stacks: at most 32 per SM, the first 32 levels live in shared memory
+        // spill rows of the consumers' level stacks: at most 24 consumers per SM (NC = 3), 32 levels in shared memory
         constexpr uint32_t kMinStack = (uint32_t)ub200::Cfg4<3>::kStack;
         if (!rc && d.max_level + 1 > kMinStack) {
             M->gstack3_levels = d.max_level + 1 - kMinStack;
-            const size_t bytes = (size_t)std::max(M->num_sms, 8) * 32u * M->gstack3_levels * 32 * sizeof(int32_t);
+            const size_t bytes = (size_t)std::max(M->num_sms, 8) * 24u * M->gstack3_levels * 32 * sizeof(int32_t);
             if (bytes > (size_t)16 << 30) {
                 rc = fail(UB200_E_LIMIT, "tree too deep for the spill stack (" + std::to_string(d.max_level) + " levels)");
             } else {
@@ -403,10 +421,30 @@ int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
         if (e != cudaSuccess) rc = fail((int)e, std::string("upload: ") + cudaGetErrorString(e));
     }
     if (rc) { ub200_mat_destroy(M); return rc; }
-    // host copies of the streamed arrays are no longer needed (the k_score layout stays for ensure_v1)
+    *out = M;
+    return UB200_OK;
+}
+
+static void drop_streamed_host_arrays(ub200::Derived& d) {
     std::vector<uint32_t>().swap(d.stream);
     std::vector<ub200::NodeHdr>().swap(d.hdr3);
-    *out = M;
+}
+
+int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {
+    if (!flat || !out) return fail(UB200_E_ARG, "ub200_mat_create: NULL argument");
+    *out = nullptr;
+    int ndev = ub200_device_count();
+    if (ndev <= 0) return fail(UB200_E_NO_DEVICE, "ub200_mat_create: no CUDA device (there is no CPU path)");
+    if (device < 0 || device >= ndev) return fail(UB200_E_ARG, "ub200_mat_create: bad device ordinal");
+    int num_sms = 0;
+    uint32_t workers = 0;
+    { int rc = device_workers(device, &num_sms, &workers); if (rc) return rc; }
+    std::shared_ptr<ub200::Derived> dp;
+    { int rc = derive_for(flat, workers, dp); if (rc) return rc; }
+    int rc = mat_upload(dp, device, out);
+    if (rc) return rc;
+    // host copies of the streamed arrays are no longer needed (the k_score layout stays for ensure_v1)
+    drop_streamed_host_arrays(*dp);
     return UB200_OK;
 }
 
@@ -791,6 +829,124 @@ int ub200_place_batch(ub200_mat* M, uint32_t n_samples, const uint64_t* sample_p
     acc.prep_ms = prep; acc.score_ms = sc; acc.reduce_ms = rd;
     M->last = acc;
     M->spans.clear();
+    return UB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Several GPUs of one box: one replica of the tree per device (derived once, uploaded by one host thread per device),
+// the samples of a batch cut into contiguous shards, one host thread per device driving ub200_place_batch, and the
+// results written by each device straight into the caller's host arrays (a device -> host copy per shard).  The
+// caller lives on the host (the usher binary writes files), so there is no device-side gather: an NCCL allgather
+// would only add a device copy before the same D2H.  Multi-PROCESS runs (bench.py under torchrun) gather the
+// device-resident records with one ncclAllGather instead.
+struct ub200_multi {
+    std::vector<ub200_mat*> mats;
+};
+
+void ub200_multi_destroy(ub200_multi* X) {
+    if (!X) return;
+    for (auto* m : X->mats) ub200_mat_destroy(m);
+    delete X;
+}
+
+int ub200_multi_create(const ub200_flat_mat* flat, int n_devices, const int* devices, ub200_multi** out) {
+    if (!flat || !out) return fail(UB200_E_ARG, "ub200_multi_create: NULL argument");
+    *out = nullptr;
+    const int ndev = ub200_device_count();
+    if (ndev <= 0) return fail(UB200_E_NO_DEVICE, "ub200_multi_create: no CUDA device (there is no CPU path)");
+    if (n_devices <= 0) n_devices = ndev;
+    std::vector<int> ids(n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        ids[i] = devices ? devices[i] : i;
+        if (ids[i] < 0 || ids[i] >= ndev) return fail(UB200_E_ARG, "ub200_multi_create: bad device ordinal");
+    }
+    int num_sms = 0;
+    uint32_t workers = 0;
+    { int rc = device_workers(ids[0], &num_sms, &workers); if (rc) return rc; }
+    std::shared_ptr<ub200::Derived> dp;
+    { int rc = derive_for(flat, workers, dp); if (rc) return rc; }
+    auto* X = new ub200_multi();
+    X->mats.assign(n_devices, nullptr);
+    std::vector<int> rcs(n_devices, 0);
+    std::vector<std::string> errs(n_devices);
+    std::vector<std::thread> pool;
+    for (int i = 0; i < n_devices; i++)
+        pool.emplace_back([&, i]() {
+            rcs[i] = mat_upload(dp, ids[i], &X->mats[i]);
+            if (rcs[i]) errs[i] = g_err;   // the message lives in the worker thread
+        });
+    for (auto& t : pool) t.join();
+    drop_streamed_host_arrays(*dp);
+    for (int i = 0; i < n_devices; i++)
+        if (rcs[i]) {
+            const int rc = rcs[i];
+            const std::string e = "device " + std::to_string(ids[i]) + ": " + errs[i];
+            ub200_multi_destroy(X);
+            return fail(rc, e);
+        }
+    *out = X;
+    return UB200_OK;
+}
+
+int ub200_multi_size(const ub200_multi* X) { return X ? (int)X->mats.size() : 0; }
+ub200_mat* ub200_multi_mat(ub200_multi* X, int i) { return (X && i >= 0 && i < (int)X->mats.size()) ? X->mats[i] : nullptr; }
+
+int ub200_multi_place_batch(ub200_multi* X, uint32_t n_samples, const uint64_t* sample_ptr, const ub200_mutation* calls,
+                            uint32_t flags, ub200_placement* out, int32_t* node_scores, uint32_t* best_set,
+                            uint64_t* best_set_ptr, uint64_t best_set_cap) {
+    if (!X || X->mats.empty() || !out || !sample_ptr) return fail(UB200_E_ARG, "ub200_multi_place_batch: NULL argument");
+    if ((flags & UB200_WANT_NODE_SCORES) && !node_scores) return fail(UB200_E_ARG, "node_scores is NULL");
+    if ((flags & UB200_WANT_BEST_SET) && !best_set_ptr) return fail(UB200_E_ARG, "best_set_ptr is NULL");
+    const uint32_t nd = (uint32_t)X->mats.size();
+    if (nd == 1 || n_samples < 64)
+        return ub200_place_batch(X->mats[0], n_samples, sample_ptr, calls, flags, out, node_scores, best_set, best_set_ptr,
+                                 best_set_cap);
+    // contiguous shards of whole 32-sample groups
+    const uint32_t per = ((n_samples + nd - 1) / nd + 31u) / 32u * 32u;
+    struct Shard { uint32_t s0 = 0, ns = 0; int rc = 0; std::string err; std::vector<uint32_t> set; std::vector<uint64_t> ptr; };
+    std::vector<Shard> sh(nd);
+    std::vector<std::thread> pool;
+    for (uint32_t i = 0; i < nd; i++) {
+        sh[i].s0 = std::min(n_samples, i * per);
+        sh[i].ns = std::min(per, n_samples - sh[i].s0);
+        if (!sh[i].ns) continue;
+        pool.emplace_back([&, i]() {
+            Shard& h = sh[i];
+            std::vector<uint64_t> ptr(h.ns + 1);
+            for (uint32_t k = 0; k <= h.ns; k++) ptr[k] = sample_ptr[h.s0 + k] - sample_ptr[h.s0];
+            const ub200_mutation* c = calls ? calls + sample_ptr[h.s0] : nullptr;
+            int32_t* ns_out = node_scores ? node_scores + (size_t)h.s0 * X->mats[i]->n : nullptr;
+            if (flags & UB200_WANT_BEST_SET) {
+                h.ptr.assign(h.ns + 1, 0);
+                h.set.assign(std::max<size_t>(1024, 4 * (size_t)h.ns), 0);
+                for (;;) {
+                    h.rc = ub200_place_batch(X->mats[i], h.ns, ptr.data(), c, flags, out + h.s0, ns_out, h.set.data(),
+                                             h.ptr.data(), h.set.size());
+                    if (h.rc == UB200_E_CAPACITY) { h.set.assign(h.ptr[h.ns] + 16, 0); continue; }
+                    break;
+                }
+            } else {
+                h.rc = ub200_place_batch(X->mats[i], h.ns, ptr.data(), c, flags, out + h.s0, ns_out, nullptr, nullptr, 0);
+            }
+            if (h.rc) h.err = g_err;
+        });
+    }
+    for (auto& t : pool) t.join();
+    for (uint32_t i = 0; i < nd; i++)
+        if (sh[i].rc) return fail(sh[i].rc, "device " + std::to_string(X->mats[i]->device) + ": " + sh[i].err);
+    if (flags & UB200_WANT_BEST_SET) {
+        uint64_t off = 0;
+        best_set_ptr[0] = 0;
+        for (uint32_t i = 0; i < nd; i++) {
+            if (!sh[i].ns) continue;
+            for (uint32_t k = 1; k <= sh[i].ns; k++) best_set_ptr[sh[i].s0 + k] = off + sh[i].ptr[k];
+            off += sh[i].ptr[sh[i].ns];
+        }
+        const uint64_t total = best_set_ptr[n_samples];
+        if (total > best_set_cap || !best_set) return fail(UB200_E_CAPACITY, "best_set capacity too small: need " + std::to_string(total));
+        for (uint32_t i = 0; i < nd; i++)
+            if (sh[i].ns) memcpy(best_set + best_set_ptr[sh[i].s0], sh[i].set.data(), (size_t)sh[i].ptr[sh[i].ns] * 4);
+    }
     return UB200_OK;
 }
 

@@ -32,7 +32,7 @@ const Opt kOpts[] = {
     {"no-add", 'n', false, "Do not add new samples to the tree"},
     {"detailed-clades", 'D', false, "In clades.txt, write a histogram of annotated clades and counts across all equally parsimonious placements"},
     {"threads", 'T', true, "Accepted for compatibility (the search runs on the GPU)"},
-    {"device", 0, true, "CUDA device ordinal [DEFAULT 0]"},
+    {"device", 0, true, "CUDA device ordinal [DEFAULT: every visible GPU for frozen-tree batches (-n, -p, the -s/-S pre-pass), GPU 0 otherwise]"},
     {"dump-flat", 0, true, "(diagnostic) write the loaded tree and VCF samples as text and exit; needs no GPU"},
     {"resave", 0, true, "(diagnostic) write the loaded tree back as protobuf and exit; needs no GPU"},
     {"version", 0, false, "Print version number"},
@@ -53,7 +53,7 @@ int main(int argc, char** argv) {
          no_add = false, detailed = false;
     uint32_t max_trees = 1, max_unc = 1000000, max_pars = 1000000;
     size_t sub_k = 0, sub_K = 0;
-    int device = 0;
+    int device = -1;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i], val;
         const Opt* hit = nullptr;

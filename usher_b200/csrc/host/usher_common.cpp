@@ -44,18 +44,25 @@ void flatten(const MAT::Tree& T, Flat& f) {
 }
 
 struct DeviceTree {
-    ub200_mat* mat = nullptr;
+    ub200_multi* multi = nullptr;   // one replica per GPU in use (frozen-tree batches use every visible GPU)
+    ub200_mat* mat = nullptr;       // replica 0: the sequential search and the per-node dump
     Flat flat;
-    ~DeviceTree() { if (mat) ub200_mat_destroy(mat); }
-    void build(const MAT::Tree& T, int device) {
-        if (mat) { ub200_mat_destroy(mat); mat = nullptr; }
+    ~DeviceTree() { if (multi) ub200_multi_destroy(multi); }
+    // device >= 0: that GPU only; device < 0: every visible GPU when `all_devices`, else GPU 0
+    void build(const MAT::Tree& T, int device, bool all_devices) {
+        if (multi) { ub200_multi_destroy(multi); multi = nullptr; mat = nullptr; }
         flatten(T, flat);
         ub200_flat_mat v{(uint32_t)flat.parent.size(), flat.muts.size(), flat.parent.data(), flat.row_ptr.data(),
                          flat.muts.data(), nullptr};
-        if (ub200_mat_create(&v, device, &mat) != UB200_OK) {
+        const int one = device < 0 ? 0 : device;
+        const bool every = device < 0 && all_devices;
+        if (ub200_multi_create(&v, every ? 0 : 1, every ? nullptr : &one, &multi) != UB200_OK) {
             fprintf(stderr, "ERROR: %s\n", ub200_last_error());
             exit(1);
         }
+        mat = ub200_multi_mat(multi, 0);
+        // wide passes share one scan of the tree between three sample groups
+        for (int i = 0; i < ub200_multi_size(multi); i++) ub200_mat_set_pass_samples(ub200_multi_mat(multi, i), 96);
     }
 };
 
@@ -197,7 +204,7 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
             fprintf(f, "%s\n", MAT::get_newick_string(*T, true, true, retain_original_branch_len).c_str());
             fclose(f);
         }
-        dev.build(*T, device);
+        dev.build(*T, device, frozen || ((sort1 || sort2) && missing_samples.size() > 64));
 
         // one batched launch set scores every sample against the current tree (sort pre-pass :187-301, and the
         // whole search when the tree is frozen)
@@ -210,7 +217,7 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
             for (auto& s : missing_samples) { sample_calls(s, calls); sp.push_back(calls.size()); }
             best_set.assign(std::max<size_t>(16, 4 * missing_samples.size()), 0);
             for (;;) {
-                int rc = ub200_place_batch(dev.mat, (uint32_t)missing_samples.size(), sp.data(), calls.data(),
+                int rc = ub200_multi_place_batch(dev.multi, (uint32_t)missing_samples.size(), sp.data(), calls.data(),
                                            want_set ? UB200_WANT_BEST_SET : 0, batch.data(), nullptr,
                                            want_set ? best_set.data() : nullptr, want_set ? set_ptr.data() : nullptr,
                                            best_set.size());
@@ -240,6 +247,8 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
         const std::string stats_fn = outdir + "/placement_stats.tsv";
         FILE* stats = fopen(stats_fn.c_str(), "w");
         bool tree_dirty = false;
+        std::vector<int32_t> pps_scores;   // -p: per-node scores of samples indexes[pps_first .. pps_first + pps_count)
+        size_t pps_first = 0, pps_count = 0;
         for (size_t idx = 0; idx < indexes.size(); idx++) {
             timer.Start();
             const size_t s = indexes[idx];
@@ -263,7 +272,7 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
                 res = batch[s];
                 opt.assign(best_set.begin() + set_ptr[s], best_set.begin() + set_ptr[s + 1]);
             } else {
-                if (tree_dirty) { dev.build(*T, device); tree_dirty = false; }
+                if (tree_dirty) { dev.build(*T, device, false); tree_dirty = false; }
                 std::vector<ub200_mutation> calls;
                 sample_calls(missing_samples[s], calls);
                 uint64_t sp[2] = {0, calls.size()}, bp[2] = {0, 0};
@@ -278,13 +287,21 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
                 opt.resize(bp[1]);
             }
             if (print_parsimony_scores) {
-                std::vector<ub200_mutation> calls;
-                sample_calls(missing_samples[s], calls);
-                uint64_t sp[2] = {0, calls.size()};
-                node_scores.resize(dev.flat.dfs.size());
-                ub200_placement tmp;
-                if (ub200_place_batch(dev.mat, 1, sp, calls.data(), UB200_WANT_NODE_SCORES, &tmp, node_scores.data(),
-                                      nullptr, nullptr, 0) != UB200_OK) die_cuda();
+                // per-node scores of the next samples in ONE batched call (as many as fit ~1 GB of host memory),
+                // sharded over the GPUs in use; the tree is frozen in this mode
+                const size_t n_nodes = dev.flat.dfs.size();
+                if (idx < pps_first || idx >= pps_first + pps_count) {
+                    pps_first = idx;
+                    pps_count = std::min<size_t>(indexes.size() - idx, std::max<size_t>(1, ((size_t)1 << 28) / std::max<size_t>(n_nodes, 1)));
+                    std::vector<uint64_t> sp{0};
+                    std::vector<ub200_mutation> calls;
+                    for (size_t k = 0; k < pps_count; k++) { sample_calls(missing_samples[indexes[idx + k]], calls); sp.push_back(calls.size()); }
+                    pps_scores.resize(pps_count * n_nodes);
+                    std::vector<ub200_placement> tmp(pps_count);
+                    if (ub200_multi_place_batch(dev.multi, (uint32_t)pps_count, sp.data(), calls.data(), UB200_WANT_NODE_SCORES,
+                                                tmp.data(), pps_scores.data(), nullptr, nullptr, 0) != UB200_OK) die_cuda();
+                }
+                node_scores.assign(pps_scores.begin() + (idx - pps_first) * n_nodes, pps_scores.begin() + (idx - pps_first + 1) * n_nodes);
             }
             const int best_set_difference = res.score;
             size_t num_best = res.num_best;

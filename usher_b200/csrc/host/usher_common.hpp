@@ -12,4 +12,4 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
                  bool print_uncondensed_tree, bool print_parsimony_scores, bool retain_original_branch_len,
                  bool no_add, bool detailed_clades, size_t print_subtrees_size, size_t print_subtrees_single,
                  std::vector<Missing_Sample>& missing_samples, std::vector<std::string>& low_confidence_samples,
-                 MAT::Tree* loaded_MAT, int device = 0);
+                 MAT::Tree* loaded_MAT, int device = -1);

@@ -130,6 +130,13 @@ class RefTree:
             self.h, outdir.encode(), threads, int(print_parsimony_scores), int(no_add)
         )
 
+    def usher_common2(self, outdir, threads=1, no_add=False, sort1=False, sort2=False, sort3=False, reverse=False,
+                      max_uncertainty=1000000, max_parsimony=1000000, uncondensed=False):
+        f = lib().usher_ref_usher_common2
+        f.argtypes = [C.c_void_p, C.c_char_p] + [C.c_int] * 6 + [C.c_uint32, C.c_uint32, C.c_int]
+        return f(self.h, outdir.encode(), threads, int(no_add), int(sort1), int(sort2), int(sort3), int(reverse),
+                 max_uncertainty, max_parsimony, int(uncondensed))
+
     def search_strided(self, calls, stride, offset=0, threads=1, seed_best=-1):
         """Seconds the reference's two-pass search of one sample takes over every `stride`-th BFS node.  With
         seed_best >= 0 the running best starts from the (known) true best score: see usher_ref_search_strided2."""

@@ -205,6 +205,19 @@ int usher_ref_usher_common(void* hv, const char* outdir, int threads, int print_
                         /*print_subtrees_size*/ 0, /*print_subtrees_single*/ 0, h->samples, low_conf, &h->T);
 }
 
+// Same with the sort pre-pass (-s / -S / -A, -r) and the thresholds (-e max_uncertainty, -E max_parsimony) exposed
+// (src/usher.cpp:44-107 -> src/usher_common.cpp:7-21).
+int usher_ref_usher_common2(void* hv, const char* outdir, int threads, int no_add, int sort1, int sort2, int sort3,
+                            int reverse_sort, uint32_t max_uncertainty, uint32_t max_parsimony, int uncondensed) {
+    auto* h = (RefTree*)hv;
+    std::vector<std::string> low_conf;
+    return usher_common("", outdir, (uint32_t)(threads < 1 ? 1 : threads), max_uncertainty, max_parsimony,
+                        sort1 != 0, sort2 != 0, sort3 != 0, reverse_sort != 0, /*collapse_tree*/ false,
+                        /*collapse_output_tree*/ false, /*print_uncondensed_tree*/ uncondensed != 0,
+                        /*print_parsimony_scores*/ false, /*retain_original_branch_len*/ false, no_add != 0,
+                        /*detailed_clades*/ false, 0, 0, h->samples, low_conf, &h->T);
+}
+
 // Frozen-tree search of every sample against every node, with the reference's loop
 // (src/usher_common.cpp:342-449).  mode 0: two-pass search (pass 1 with early exit, pass 2 over the optimal
 // set) exactly as the default CLI; mode 1: single pass with compute_parsimony_scores=true (-p semantics),

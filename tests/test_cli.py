@@ -132,3 +132,28 @@ def test_fitch_sankoff_known_answer(usher):
                            "/root/reference/scripts/testBranchLen2.vcf", "--dump-flat", d + "/f.txt"], stderr=subprocess.DEVNULL)
     nwk = [l for l in open(d + "/f.txt") if l.startswith("NEWICK\t")][0].split("\t")[1].strip()
     assert nwk == "((a:0,(b:0,(c:0,d:1)node_4:1)node_3:2,((e:0,f:1)node_6:3,g:0)node_5:4)node_2:5,h:0)node_1:0;"
+
+
+HOST_RUNS = {
+    "default": [], "sort1": ["-s"], "sort2": ["-S"], "sort1_reverse": ["-s", "-r"], "sort3": ["-A"],
+    "max_uncertainty_2": ["-e", "2"], "max_parsimony_3": ["-E", "3"], "no_add": ["-n"], "uncondensed": ["-u"],
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("run", sorted(HOST_RUNS))
+def test_ambiguous_samples_host_outputs_match_reference(usher, run):
+    """The host layer around the kernels (imputed mutations of ambiguous / N calls, excess lists, child vs sibling
+    grafts, duplicated genotypes, sort pre-pass orders, -e / -E thresholds, --no-add, uncondensed output) against
+    files the reference's own usher_common() wrote for 14 new samples with IUPAC codes and N runs on the config-1
+    MAT (oracle/make_golden_host.py): byte for byte."""
+    g = common.load(os.path.join(common.GOLDEN, "hostgold.npz"))
+    d = tempfile.mkdtemp()
+    r = subprocess.run([usher, "-i", PB, "-v", os.path.join(common.GOLDEN, "hostgold_samples.vcf"), "-d", d] + HOST_RUNS[run],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for f in ("placement_stats.tsv", "mutation-paths.txt", "final-tree.nh", "uncondensed-final-tree.nh"):
+        key = f"{run}__{f}"
+        if key in g.files:
+            assert open(os.path.join(d, f)).read() == str(g[key]), (run, f)
+    assert f"The parsimony score for this tree is: {int(g[run + '__parsimony'])}" in r.stderr or run == "no_add"

@@ -237,7 +237,7 @@ uint32_t pick_consumers(const ub200_mat* M, uint32_t ng) {
 
 // Streaming best-placement kernel (score_kernel4.cuh): one CTA of scanner + NC consumer warp units per SM.
 template <int NC>
-int launch_score4_nc(ub200_mat* M, ub200_samples* S, const ub200::Score4Params& p, uint32_t grid, bool collect) {
+int launch_score4_nc(ub200_mat* M, ub200_samples* S, const ub200::Score4Params& p, uint32_t grid, int mode) {
     using namespace ub200;
     using C = Cfg4<NC>;
     const uint32_t bm_need = (S->bitmap_words * 4u + 127u) & ~127u;
@@ -249,12 +249,19 @@ int launch_score4_nc(ub200_mat* M, ub200_samples* S, const ub200::Score4Params& 
         return 0;
     };
     int rc;
-    if (M->d.narrow3) {
-        if (smem_bitmap) rc = collect ? go(k_score4<NC, true, true, true>) : go(k_score4<NC, true, false, true>);
-        else rc = collect ? go(k_score4<NC, false, true, true>) : go(k_score4<NC, false, false, true>);
+    if (mode == kMode4NodeScores) {
+        if constexpr (NC == 1) {
+            if (M->d.narrow3) rc = smem_bitmap ? go(k_score4<1, true, kMode4NodeScores, true>) : go(k_score4<1, false, kMode4NodeScores, true>);
+            else rc = smem_bitmap ? go(k_score4<1, true, kMode4NodeScores, false>) : go(k_score4<1, false, kMode4NodeScores, false>);
+        } else {
+            return fail(UB200_E_ARG, "per-node scores run one sample group per scan");
+        }
+    } else if (M->d.narrow3) {
+        if (smem_bitmap) rc = mode ? go(k_score4<NC, true, kMode4Collect, true>) : go(k_score4<NC, true, kMode4Best, true>);
+        else rc = mode ? go(k_score4<NC, false, kMode4Collect, true>) : go(k_score4<NC, false, kMode4Best, true>);
     } else {
-        if (smem_bitmap) rc = collect ? go(k_score4<NC, true, true, false>) : go(k_score4<NC, true, false, false>);
-        else rc = collect ? go(k_score4<NC, false, true, false>) : go(k_score4<NC, false, false, false>);
+        if (smem_bitmap) rc = mode ? go(k_score4<NC, true, kMode4Collect, false>) : go(k_score4<NC, true, kMode4Best, false>);
+        else rc = mode ? go(k_score4<NC, false, kMode4Collect, false>) : go(k_score4<NC, false, kMode4Best, false>);
     }
     if (rc) return rc;
     CU(cudaGetLastError());
@@ -264,7 +271,7 @@ int launch_score4_nc(ub200_mat* M, ub200_samples* S, const ub200::Score4Params& 
 // One pass: groups [group0, group0 + ngroups) of the batch, `nc` groups per scanner; bm0 = index of the pass's first
 // union bitmap.  *wpg_out = partial rows per group (CTAs per scan group) for k_reduce.
 int launch_score4(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, uint32_t nc, uint32_t bm0,
-                  uint32_t* wpg_out, bool collect = false) {
+                  uint32_t* wpg_out, int mode = 0) {
     using namespace ub200;
     Score4Params p;
     p.stream = M->mstream; p.hdr = M->hdr3; p.tiekey = M->tiekey;
@@ -277,14 +284,15 @@ int launch_score4(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngro
     p.part_key = S->part_key; p.part_cnt = S->part_cnt;
     p.gstack = M->gstack3; p.gstack_levels = M->gstack3_levels;
     p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
+    p.base = S->base; p.node_scores = S->node_scores;
     p.tile_counter = S->tile_counter;
     p.prof = reinterpret_cast<unsigned long long*>(S->tile_counter + 64);   // 16 counters behind the tile counters
     CU(cudaMemsetAsync(S->tile_counter, 0, 256, M->stream));
     const uint32_t grid = std::max<uint32_t>(p.nsg, ((uint32_t)M->num_sms / p.nsg) * p.nsg);
     *wpg_out = grid / p.nsg;
-    if (nc == 1) return launch_score4_nc<1>(M, S, p, grid, collect);
-    if (nc == 2) return launch_score4_nc<2>(M, S, p, grid, collect);
-    return launch_score4_nc<3>(M, S, p, grid, collect);
+    if (nc == 1) return launch_score4_nc<1>(M, S, p, grid, mode);
+    if (nc == 2) return launch_score4_nc<2>(M, S, p, grid, mode);
+    return launch_score4_nc<3>(M, S, p, grid, mode);
 }
 
 // Build the per-group position bitmap + position-major cost table + per-sample base count on the device.
@@ -628,7 +636,7 @@ static int place_resident_impl(ub200_mat* M, ub200_samples* S, uint32_t flags, i
     const char* force = getenv("UB200_KERNEL");
     const bool use_v3 = !(force && force[0] == '1') && M->d.have3 && M->d.max_row <= ub200::kMaxRowV4 &&
                         S->max_calls <= ub200::kMaxCallsV4;
-    if (!use_v3 || (flags & UB200_WANT_NODE_SCORES)) { int rc = ensure_v1(M); if (rc) return rc; }
+    if (!use_v3) { int rc = ensure_v1(M); if (rc) return rc; }   // the first-generation layout, only when it is needed
     const uint32_t NG = M->pass_groups;
     M->spans.clear(); M->ev_used = 0;
     M->last = {};
@@ -667,7 +675,10 @@ static int place_resident_impl(ub200_mat* M, ub200_samples* S, uint32_t flags, i
         }
         for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
             const uint32_t ng = std::min(NG, S->n_groups - g0);
-            int rc = launch_score<ub200::kModeNodeScores>(M, S, g0, ng, smem_bitmap); if (rc) return rc;
+            uint32_t wpg_unused = 0;
+            int rc = use_v3 ? launch_score4(M, S, g0, ng, 1, (g0 / NG) * nsgpp, &wpg_unused, ub200::kMode4NodeScores)
+                            : launch_score<ub200::kModeNodeScores>(M, S, g0, ng, smem_bitmap);
+            if (rc) return rc;
             M->last.total_launches++;
         }
         S->have_node_scores = true;
@@ -691,7 +702,7 @@ static int place_resident_impl(ub200_mat* M, ub200_samples* S, uint32_t flags, i
         for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
             const uint32_t ng = std::min(NG, S->n_groups - g0);
             uint32_t wpg_unused = 0;
-            int rc = use_v3 ? launch_score4(M, S, g0, ng, nc, (g0 / NG) * nsgpp, &wpg_unused, true)
+            int rc = use_v3 ? launch_score4(M, S, g0, ng, nc, (g0 / NG) * nsgpp, &wpg_unused, ub200::kMode4Collect)
                             : launch_score<ub200::kModeCollect>(M, S, g0, ng, smem_bitmap);
             if (rc) return rc;
             M->last.total_launches++;

@@ -99,6 +99,8 @@ struct Score4Params {
     uint32_t* set_out;
     const unsigned long long* set_ptr;
     uint32_t* set_fill;
+    const int32_t* base;          // MODE 2: per sample, the calls that already disagree with the bare reference
+    int32_t* node_scores;         // MODE 2: [n_samples][n_nodes]
     uint32_t* tile_counter;
     unsigned long long* prof;     // UB200_PROFILE builds only: cycle counters per role (api.cu ub200_debug_prof)
 };
@@ -201,11 +203,15 @@ __device__ __forceinline__ void unpack_delta4(int v, int& dcorr, int& da, int& d
     dcorr = (v1 - da) >> 10;
 }
 
-// COLLECT = false: best placement per sample.  COLLECT = true: second pass that lists every optimal node of each
-// sample (best_j_vec + node_has_unique); the final best score is the bound, so almost every block is pruned.
-template <int NC, bool SMEM_BITMAP, bool COLLECT, bool NARROW>
+// MODE 0: best placement per sample.  MODE 1 (collect): second pass that lists every optimal node of each sample
+// (best_j_vec + node_has_unique); the final best score is the bound, so almost every block is pruned.  MODE 2: the
+// reported score of EVERY node (`-p`, src/usher_common.cpp:557-578: score + 1 on invalid nodes): every block is
+// evaluated, non-hit pairs are written lane = node (coalesced), hit pairs one by one.
+constexpr int kMode4Best = 0, kMode4Collect = 1, kMode4NodeScores = 2;
+template <int NC, bool SMEM_BITMAP, int MODE, bool NARROW>
 __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Params p) {
     using C = Cfg4<NC>;
+    constexpr bool COLLECT = MODE == kMode4Collect, SCORES = MODE == kMode4NodeScores;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     // unit / role of this warp; the scanners are spread over the four SM sub-partitions (warp % 4)
@@ -702,7 +708,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 // ================= bound: can any pair of this block still be optimal? =================
                 const int lbase = gmin + neg[lane] + negr;
                 const int bound = min(bsc, gb);
-                const uint32_t needs = __ballot_sync(FULL, live && (int)rec.x + lbase <= bound);
+                const uint32_t needs = __ballot_sync(FULL, live && (SCORES || (int)rec.x + lbase <= bound));
                 PROF_T0(tn);
                 if (needs) {
                     PROF_INC(15, 1);
@@ -736,12 +742,18 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                         return v;
                     };
                     // ---- E: non-hit pairs (lane = node), one sample at a time
-                    uint32_t need_e = __ballot_sync(FULL, live && min_g < BIG && min_g + lbase <= bound);
+                    uint32_t need_e = __ballot_sync(FULL, live && (SCORES || (min_g < BIG && min_g + lbase <= bound)));
                     while (need_e) {
                         const uint32_t s = __ffs(need_e) - 1;
                         need_e &= need_e - 1;
                         const uint32_t hm_s = area[kA4Hm + s];
                         const int sc = (int)h.x + above(level, h.y, hm_s, s);
+                        if (SCORES) {
+                            const uint32_t gs = ggroup * 32u + s;
+                            if (act && !((hm_s >> lane) & 1u))
+                                p.node_scores[(size_t)gs * p.n_nodes + blk + lane] = p.base[gs] + sc + ((flags & kFlagValid0) ? 0 : 1);
+                            continue;
+                        }
                         const int bs = __shfl_sync(FULL, bsc, s);
                         uint32_t cm = __ballot_sync(FULL, dense_ok && !((hm_s >> lane) & 1u) && sc <= bs);
                         while (cm) {
@@ -776,7 +788,8 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                                 hu = (masked || (int)(w >> 16) > common) ? 1u : 0u;
                                 valid = (fl & kFlagLeaf) ? common > 0 : (!hu || common > 0);
                             }
-                            if (valid && sc <= bsc) merge(sc, hu, blk + n);
+                            if (SCORES) p.node_scores[(size_t)sample * p.n_nodes + blk + n] = p.base[sample] + sc + (valid ? 0 : 1);
+                            else if (valid && sc <= bsc) merge(sc, hu, blk + n);
                         }
                     }
                 }
@@ -800,7 +813,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 __syncwarp();
             }
             // publish an improved bound for the other units working on this sample group
-            if (!COLLECT && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
+            if (MODE == kMode4Best && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
             __syncwarp();
         }
 
@@ -808,14 +821,14 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         pc[8] = (unsigned long long)(clock64() - prof_start);
         if (lane == 0 && !dead) for (int i = 8; i < 16; i++) atomicAdd(p.prof + i, pc[i]);
 #endif
-        if (!COLLECT) {
+        if (MODE == kMode4Best) {
             // park the consumer's result in its own rows for the fold below
             reinterpret_cast<unsigned long long*>(dnode)[lane] = bkey;
             neg[lane] = (int)cnt;
         }
     }
 
-    if (COLLECT) return;
+    if (MODE != kMode4Best) return;
     // fold the CTA's units, one partial row per CTA and group: warp c folds consumer c of every unit
     __syncthreads();
     if (warp < (uint32_t)NC && sg * NC + warp < p.ngroups) {

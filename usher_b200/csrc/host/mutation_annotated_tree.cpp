@@ -808,6 +808,7 @@ void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Samp
         exit(1);
     }
     std::istringstream in(raw);
+    int8_t stale_mut_nuc = 0;   // see the genotype loop below
     bool header = false;
     std::vector<std::string> ids;
     std::vector<size_t> cols;
@@ -838,6 +839,11 @@ void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Samp
             for (size_t k = 0; k < cols.size(); k++) {
                 const std::string& gt = w[cols[k]];
                 Mutation m;
+                // The reference leaves Mutation::mut_nuc uninitialised here (src/mutation_annotated_tree.cpp:2246) and
+                // tests it for ambiguity even when the genotype is 0 (:2271); the object reuses the stack slot of the
+                // previous iteration, so num_ambiguous (the -A sort key) counts the PREVIOUS genotype's allele for
+                // reference calls.  Reproduced, since the sample order decides the final tree.
+                m.mut_nuc = stale_mut_nuc;
                 m.chrom = w[0];
                 m.position = std::stoi(w[1]);
                 m.ref_nuc = get_nuc_id(w[3][0]);
@@ -858,6 +864,7 @@ void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Samp
                 }
                 if (add) missing_samples[k].mutations.push_back(m);
                 if (m.mut_nuc & (m.mut_nuc - 1)) missing_samples[k].num_ambiguous++;
+                stale_mut_nuc = m.mut_nuc;
             }
         }
     }

@@ -214,3 +214,19 @@ def test_random_trees_segment_model_vs_port(seed):
         a, b = int(q["best_set_ptr"][i]), int(q["best_set_ptr"][i + 1])
         assert [x for x, _ in r["optimal"]] == q["best_set"][a:b].tolist()
     pt.close()
+
+
+def test_derivation_does_not_depend_on_the_host_thread_count(monkeypatch):
+    """The derivation runs on host threads (chunks of the node range: checks, tie-break ranks, path states, tile
+    pieces): every derived array is identical for 1, 3 and 7 threads, on trees with masked rows and reversions."""
+    import small_synth
+    for seed, n, L, mu, shape in ((11, 900, 300, 4.0, "uniform"), (12, 2500, 60, 2.0, "chain"), (13, 1, 10, 1.0, "uniform")):
+        parent, row_ptr, muts, _ = small_synth.random_mat(seed, n, L, mu, shape=shape)
+        outs = []
+        for nt in (1, 3, 7):
+            monkeypatch.setenv("UB200_HOST_THREADS", str(nt))
+            outs.append(capi.debug_derive(parent, row_ptr, muts, target_tiles=16, min_tile_cost=64))
+        for o in outs[1:]:
+            assert sorted(o) == sorted(outs[0])
+            for k, v in outs[0].items():
+                assert np.array_equal(np.asarray(v), np.asarray(o[k])), (seed, k)

@@ -434,7 +434,7 @@ static int mat_upload(std::shared_ptr<ub200::Derived> dp, int device, ub200_mat*
 }
 
 static void drop_streamed_host_arrays(ub200::Derived& d) {
-    std::vector<uint32_t>().swap(d.stream);
+    ub200::StreamVec().swap(d.stream);
     std::vector<ub200::NodeHdr>().swap(d.hdr3);
 }
 

@@ -18,11 +18,44 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 
 #include "ub200_internal.h"
 
 namespace ub200 {
+
+namespace {
+struct PhaseTimer {
+    bool on = getenv("UB200_DERIVE_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[derive] %-28s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+// Host threads for the derivation: contiguous chunks of [0, n), one chunk per thread (results are independent of the
+// thread count: every chunk writes its own slice, and the reductions are order-free min / max / sum / first error).
+unsigned host_threads(uint64_t work) {
+    unsigned t = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char* e = getenv("UB200_HOST_THREADS")) return (unsigned)std::max(1, atoi(e));   // tests force the split
+    return work < (1u << 18) ? 1u : t;
+}
+template <class F>
+void parallel_chunks(uint32_t n, unsigned nthr, F body) {   // body(chunk, lo, hi)
+    if (nthr <= 1) { body(0u, 0u, n); return; }
+    std::vector<std::thread> pool;
+    for (unsigned c = 0; c < nthr; c++) {
+        const uint32_t lo = (uint32_t)((uint64_t)n * c / nthr), hi = (uint32_t)((uint64_t)n * (c + 1) / nthr);
+        pool.emplace_back([=, &body]() { body(c, lo, hi); });
+    }
+    for (auto& th : pool) th.join();
+}
+}  // namespace
 
 // The k_score3 layout (ub200_internal.h), built from the arrays derive() has already filled.
 static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min_tile_cost, Derived& d) {
@@ -31,6 +64,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     if (!d.have3) return;
     d.narrow3 = d.L <= kMaxPos3Narrow && !getenv("UB200_WIDE_WORDS");   // env: test hook for the wide form
     const uint32_t nblk = (n + 31) / 32;
+    PhaseTimer pt;
     // subtree ends (DFS pre-order: subtree of i = [i, send[i])), words on the root path above each node
     std::vector<uint32_t> send(n);
     for (uint32_t i = 0; i < n; i++) send[i] = i + 1;
@@ -54,6 +88,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
             h.level_flags = (d.level[i] << kLevelShift) | flags | (open ? kFlagOpen : 0u);
         }
     }
+    pt.lap("  3: subtree ends, headers");
     // tiles: whole blocks, roughly equal cost; the seed stream must stay a small fraction of the tree
     const uint64_t node_cost = 4;
     const uint64_t total = d.m + node_cost * n;
@@ -79,6 +114,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         if (seed <= std::max<uint64_t>(d.m / 8, 1u << 16) || d.tile3_start.size() <= 2) break;
         per += per / 2;
     }
+    pt.lap("  3: tile boundaries");
     const size_t T = d.tile3_start.size() - 1;
     d.tile3_w0.assign(T + 1, 0);
     d.tile3_lvl.assign(T, 0);
@@ -164,23 +200,32 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         worker();
         for (auto& th : pool) th.join();
     }
+    pt.lap("  3: tile pieces (threads)");
     uint64_t total_words = 0;
     for (size_t t = 0; t < T; t++) total_words += pieces[t].words.size();
     d.stream.resize(total_words);
     d.seed_words = 0;
     uint64_t w = 0;
+    std::vector<uint64_t> piece_off(T + 1, 0);
     for (size_t t = 0; t < T; t++) {
         Piece& pc = pieces[t];
+        piece_off[t] = w;
         d.tile3_w0[t] = (uint32_t)(w / kChunk3);
         for (uint32_t e4 : pc.seed_end4) d.seed_end.push_back((uint32_t)(w / 4) + e4);
         d.tile3_sseg[t + 1] = (uint32_t)d.seed_end.size();
         d.seed_words += pc.seed_words;
-        std::memcpy(d.stream.data() + w, pc.words.data(), pc.words.size() * sizeof(uint32_t));
         w += pc.words.size();
-        std::vector<uint32_t>().swap(pc.words);
     }
+    parallel_chunks((uint32_t)T, host_threads(total_words), [&](unsigned, uint32_t lo, uint32_t hi) {
+        for (uint32_t t = lo; t < hi; t++) {
+            Piece& pc = pieces[t];
+            std::memcpy(d.stream.data() + piece_off[t], pc.words.data(), pc.words.size() * sizeof(uint32_t));
+            std::vector<uint32_t>().swap(pc.words);
+        }
+    });
     d.tile3_w0[T] = (uint32_t)(w / kChunk3);
     d.seed_end.push_back(0);   // never empty
+    pt.lap("  3: concatenate");
     // ---- block records: what the consumer needs of a block that cannot hold an optimum (score_kernel4.cuh)
     d.blk_rec.assign((size_t)nblk * 4, 0);
     for (uint32_t b = 0; b < n; b += 32) {
@@ -210,6 +255,7 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
         err = "flat MAT: row_ptr does not span [0, n_mutations]";
         return UB200_E_ARG;
     }
+    PhaseTimer pt;
     d.n = n;
     // ---- topology checks: DFS pre-order <=> parent[i] lies on the root path of node i-1
     d.level.assign(n, 0);
@@ -234,6 +280,7 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
         }
     }
     d.max_level = *std::max_element(d.level.begin(), d.level.end());
+    pt.lap("topology checks");
     // ---- leaves, leaf counts (reverse sweep), BFS index
     std::vector<uint32_t> nchild(n + 1, 0);
     for (uint32_t i = 1; i < n; i++) nchild[f.parent[i] + 1]++;
@@ -259,118 +306,205 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
             for (uint32_t k = off[u]; k < off[u + 1]; k++) q[tail++] = kids[k];
         }
     }
+    pt.lap("leaves + BFS index");
     // ---- tie-break order: preferred = more leaves, then larger j  -> tiekey 0 is the most preferred
     {
         std::vector<uint64_t> keys(n);
         for (uint32_t i = 0; i < n; i++) keys[i] = ((uint64_t)d.num_leaves[i] << 32) | d.tie_index[i];
         std::vector<uint32_t> ord(n);
         std::iota(ord.begin(), ord.end(), 0u);
-        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
-            return keys[a] != keys[b] ? keys[a] > keys[b] : a < b;
-        });
+        auto before = [&](uint32_t a, uint32_t b) { return keys[a] != keys[b] ? keys[a] > keys[b] : a < b; };
+        // sorted runs by thread, then pairwise merges (a strict total order: the result does not depend on the split)
+        const unsigned nt = host_threads(n);
+        std::vector<uint32_t> cut(nt + 1);
+        for (unsigned c = 0; c <= nt; c++) cut[c] = (uint32_t)((uint64_t)n * c / nt);
+        parallel_chunks(n, nt, [&](unsigned, uint32_t lo, uint32_t hi) { std::sort(ord.begin() + lo, ord.begin() + hi, before); });
+        for (unsigned w = 1; w < nt; w *= 2) {
+            std::vector<std::thread> pool;
+            for (unsigned c = 0; c + w < nt; c += 2 * w)
+                pool.emplace_back([&, c]() {
+                    std::inplace_merge(ord.begin() + cut[c], ord.begin() + cut[c + w], ord.begin() + cut[std::min(nt, c + 2 * w)], before);
+                });
+            for (auto& th : pool) th.join();
+        }
         d.tiekey.resize(n);
         d.key_to_node = ord;
         for (uint32_t r = 0; r < n; r++) d.tiekey[ord[r]] = r;
     }
-    // ---- mutation checks, genome extent
+    pt.lap("tie-break rank (sort)");
+    // ---- mutation checks, genome extent (chunks of nodes in parallel; the first error in node order is reported)
     int64_t maxpos = 0;
     uint64_t kept = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        if (f.row_ptr[i + 1] < f.row_ptr[i]) { err = "flat MAT: row_ptr not monotone"; return UB200_E_ARG; }
-        int32_t last = INT32_MIN;
-        uint64_t row_kept = 0;
-        for (uint64_t k = f.row_ptr[i]; k < f.row_ptr[i + 1]; k++) {
-            const ub200_mutation& m = f.mutations[k];
-            if (m.position < last) {
-                err = "flat MAT: row " + std::to_string(i) + " is not position-sorted";
-                return UB200_E_POSITION;
+    std::vector<uint32_t> row_kept_of(n);
+    {
+        const unsigned nt = host_threads(f.n_mutations + n);
+        struct Part { int64_t maxpos = 0; uint64_t kept = 0; uint32_t max_row = 0; int rc = 0; std::string err; };
+        std::vector<Part> part(nt);
+        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            Part& P = part[c];
+            auto bad = [&](int rc, std::string msg) { P.rc = rc; P.err = std::move(msg); };
+            for (uint32_t i = lo; i < hi && !P.rc; i++) {
+                if (f.row_ptr[i + 1] < f.row_ptr[i]) { bad(UB200_E_ARG, "flat MAT: row_ptr not monotone"); break; }
+                int32_t last = INT32_MIN;
+                uint64_t row_kept = 0;
+                for (uint64_t k = f.row_ptr[i]; k < f.row_ptr[i + 1]; k++) {
+                    const ub200_mutation& m = f.mutations[k];
+                    if (m.position < last) { bad(UB200_E_POSITION, "flat MAT: row " + std::to_string(i) + " is not position-sorted"); break; }
+                    if (m.position >= 0 && m.position == last) {
+                        bad(UB200_E_POSITION, "flat MAT: row " + std::to_string(i) + " repeats position " + std::to_string(last));
+                        break;
+                    }
+                    last = m.position;
+                    if (m.position < 0) continue;
+                    if ((uint32_t)m.position > kMaxPos) { bad(UB200_E_POSITION, "flat MAT: position >= 2^26-1"); break; }
+                    if (nuc_code(m.mut_nuc) < 0 || nuc_code(m.ref_nuc) < 0) {
+                        bad(UB200_E_NOT_ONE_HOT, "flat MAT: node " + std::to_string(i) + " position " + std::to_string(m.position) +
+                                                     " has a non-one-hot ref/mut nucleotide");
+                        break;
+                    }
+                    P.maxpos = std::max<int64_t>(P.maxpos, m.position);
+                    row_kept++;
+                }
+                if (P.rc) break;
+                P.max_row = std::max<uint32_t>(P.max_row, (uint32_t)row_kept);
+                if (row_kept > kMaxRow) { bad(UB200_E_LIMIT, "flat MAT: a branch with more than 65534 mutations"); break; }
+                row_kept_of[i] = (uint32_t)row_kept;
+                P.kept += row_kept;
             }
-            if (m.position >= 0 && m.position == last) {
-                err = "flat MAT: row " + std::to_string(i) + " repeats position " + std::to_string(last);
-                return UB200_E_POSITION;
-            }
-            last = m.position;
-            if (m.position < 0) continue;
-            if ((uint32_t)m.position > kMaxPos) { err = "flat MAT: position >= 2^26-1"; return UB200_E_POSITION; }
-            if (nuc_code(m.mut_nuc) < 0 || nuc_code(m.ref_nuc) < 0) {
-                err = "flat MAT: node " + std::to_string(i) + " position " + std::to_string(m.position) +
-                      " has a non-one-hot ref/mut nucleotide";
-                return UB200_E_NOT_ONE_HOT;
-            }
-            maxpos = std::max<int64_t>(maxpos, m.position);
-            row_kept++;
+        });
+        for (auto& P : part) {
+            if (P.rc) { err = P.err; return P.rc; }
+            maxpos = std::max(maxpos, P.maxpos);
+            kept += P.kept;
+            d.max_row = std::max(d.max_row, P.max_row);
         }
-        d.max_row = std::max<uint32_t>(d.max_row, (uint32_t)row_kept);
-        if (row_kept > kMaxRow) { err = "flat MAT: a branch with more than 65534 mutations"; return UB200_E_LIMIT; }
-        kept += row_kept;
     }
     if (kept >= (1ull << 32) - kMutChunk) { err = "flat MAT: more than 2^32 mutations"; return UB200_E_LIMIT; }
     d.m = kept;
     d.L = (uint32_t)maxpos + 1;
     d.ref_of.assign(d.L, 0);
     d.root_init_extra = (int32_t)(f.row_ptr[1] - f.row_ptr[0]);
-
-    // ---- one DFS with a live state array
-    d.row32.assign((size_t)n + 1, 0);
-    d.mutw.assign(((kept + kMutChunk - 1) / kMutChunk + 1) * kMutChunk, 0);
-    d.hdr.assign(((size_t)n + kHdrChunk - 1) / kHdrChunk * kHdrChunk + kHdrChunk, NodeHdr{0, 0, 0, 0});
-    std::vector<uint8_t> state(d.L, 0);  // 0 = never mutated on the current path, else one-hot
-    std::vector<int32_t> dref(n, 0);
-    struct Undo { uint32_t node; uint32_t pos; uint8_t old; };
-    std::vector<Undo> undo;
-    std::vector<uint32_t> path;
-    uint64_t w = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        while (!path.empty() && (int32_t)path.back() != f.parent[i]) {
-            uint32_t top = path.back();
-            path.pop_back();
-            while (!undo.empty() && undo.back().node == top) {
-                state[undo.back().pos] = undo.back().old;
-                undo.pop_back();
-            }
-        }
-        const bool is_root = (i == 0);
-        const bool leaf = nchild[i + 1] == 0;
-        bool masked = false;
-        int32_t dd = 0, a0 = 0;
-        uint32_t c0 = 0, nm = 0;
-        d.row32[i] = (uint32_t)w;
-        for (uint64_t k = f.row_ptr[i]; k < f.row_ptr[i + 1]; k++) {
+    // reference allele per position: any writer wins (relaxed byte stores; all writers agree on a consistent tree),
+    // then every mutation is checked against what was kept, so an inconsistent tree fails whoever won
+    parallel_chunks(n, host_threads(f.n_mutations), [&](unsigned, uint32_t lo, uint32_t hi) {
+        for (uint64_t k = f.row_ptr[lo]; k < f.row_ptr[hi]; k++) {
             const ub200_mutation& m = f.mutations[k];
-            if (m.position < 0) { masked = true; continue; }
-            const uint32_t pos = (uint32_t)m.position;
-            if (d.ref_of[pos] == 0) d.ref_of[pos] = m.ref_nuc;
-            else if (d.ref_of[pos] != m.ref_nuc) {
-                err = "flat MAT: tree mutations disagree on the reference allele at position " + std::to_string(pos);
+            if (m.position >= 0 && __atomic_load_n(&d.ref_of[m.position], __ATOMIC_RELAXED) == 0)
+                __atomic_store_n(&d.ref_of[m.position], m.ref_nuc, __ATOMIC_RELAXED);
+        }
+    });
+    {
+        const unsigned nt = host_threads(f.n_mutations);
+        std::vector<int64_t> bad_pos(nt, -1);
+        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            for (uint64_t k = f.row_ptr[lo]; k < f.row_ptr[hi]; k++) {
+                const ub200_mutation& m = f.mutations[k];
+                if (m.position >= 0 && d.ref_of[m.position] != m.ref_nuc) { bad_pos[c] = m.position; break; }
+            }
+        });
+        for (int64_t bp : bad_pos)
+            if (bp >= 0) {
+                err = "flat MAT: tree mutations disagree on the reference allele at position " + std::to_string(bp);
                 return UB200_E_ARG;
             }
-            const uint8_t prev = state[pos] ? state[pos] : m.ref_nuc;
-            const int rp = prev != m.ref_nuc, rm = m.mut_nuc != m.ref_nuc;
-            dd += rm - rp;
-            if (!rm) { c0++; a0 += rp; }   // LOOP 1 for an absent position: common iff back to ref (:244-259)
-            d.mutw[w++] = pack_mut(pos, (uint32_t)nuc_code(m.ref_nuc), (uint32_t)nuc_code(prev),
-                                   (uint32_t)nuc_code(m.mut_nuc));
-            undo.push_back({i, pos, state[pos]});
-            state[pos] = m.mut_nuc;
-            nm++;
-        }
-        const int32_t dpar = is_root ? 0 : dref[f.parent[i]];
-        dref[i] = dpar + dd;
-        if (masked || is_root) { a0 = 0; c0 = 0; }  // masked: LOOP 1 breaks before taking anything (:197-200)
-        const bool hu0 = masked || (nm > c0);
-        const bool valid0 = is_root || (leaf ? c0 > 0 : (!hu0 || c0 > 0));
-        NodeHdr h;
-        h.g = is_root ? dref[i] : dpar - a0;
-        h.tiekey = d.tiekey[i];
-        const uint32_t plane = (!is_root && (uint32_t)f.parent[i] >= (i & ~31u)) ? 1u + ((uint32_t)f.parent[i] & 31u) : 0u;
-        h.level_flags = (d.level[i] << kLevelShift) | (plane << 8) | (leaf ? kFlagLeaf : 0) | (masked ? kFlagMasked : 0) |
-                        (is_root ? kFlagRoot : 0) | (valid0 ? kFlagValid0 : 0) | ((hu0 && !is_root) ? kFlagHu0 : 0);
-        h.nmut_c0 = (nm << 16) | c0;
-        d.hdr[i] = h;
-        path.push_back(i);
     }
-    d.row32[n] = (uint32_t)w;
 
+    pt.lap("mutation checks");
+    // ---- path states: one DFS with a live state array per chunk of the node range.  A chunk starts from the state of
+    // its first node's root path (rebuilt by walking that path root-first); every node writes only its own rows.
+    d.row32.assign((size_t)n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) d.row32[i + 1] = d.row32[i] + row_kept_of[i];
+    std::vector<uint32_t>().swap(row_kept_of);
+    d.mutw.assign(((kept + kMutChunk - 1) / kMutChunk + 1) * kMutChunk, 0);
+    d.hdr.assign(((size_t)n + kHdrChunk - 1) / kHdrChunk * kHdrChunk + kHdrChunk, NodeHdr{0, 0, 0, 0});
+    std::vector<int32_t> dref(n, 0);
+    {
+        const unsigned nt = host_threads(kept + n);
+        // chunk boundaries by mutation count
+        std::vector<uint32_t> cut(nt + 1, n);
+        cut[0] = 0;
+        for (unsigned c = 1; c < nt; c++)
+            cut[c] = (uint32_t)(std::lower_bound(d.row32.begin(), d.row32.begin() + n, (uint32_t)(kept * c / nt)) - d.row32.begin());
+        for (unsigned c = 1; c <= nt; c++) cut[c] = std::max(cut[c], cut[c - 1]);
+        auto chunk = [&](unsigned c) {
+            const uint32_t lo = cut[c], hi = cut[c + 1];
+            if (lo >= hi) return;
+            std::vector<uint8_t> state(d.L, 0);  // 0 = never mutated on the current path, else one-hot
+            struct Undo { uint32_t node; uint32_t pos; uint8_t old; };
+            std::vector<Undo> undo;
+            std::vector<uint32_t> path;
+            std::vector<int32_t> dref_anc;       // Dref of the ancestors of `lo`, by level
+            // root path of the chunk's first node, root first
+            for (int32_t a = lo ? f.parent[lo] : -1; a >= 0; a = f.parent[a]) path.push_back((uint32_t)a);
+            std::reverse(path.begin(), path.end());
+            for (uint32_t a : path) {
+                int32_t dd = 0;
+                for (uint64_t k = f.row_ptr[a]; k < f.row_ptr[a + 1]; k++) {
+                    const ub200_mutation& m = f.mutations[k];
+                    if (m.position < 0) continue;
+                    const uint32_t pos = (uint32_t)m.position;
+                    const uint8_t prev = state[pos] ? state[pos] : m.ref_nuc;
+                    dd += (m.mut_nuc != m.ref_nuc) - (prev != m.ref_nuc);
+                    undo.push_back({a, pos, state[pos]});
+                    state[pos] = m.mut_nuc;
+                }
+                dref_anc.push_back((dref_anc.empty() ? 0 : dref_anc.back()) + dd);
+            }
+            for (uint32_t i = lo; i < hi; i++) {
+                while (!path.empty() && (int32_t)path.back() != f.parent[i]) {
+                    uint32_t top = path.back();
+                    path.pop_back();
+                    while (!undo.empty() && undo.back().node == top) {
+                        state[undo.back().pos] = undo.back().old;
+                        undo.pop_back();
+                    }
+                }
+                const bool is_root = (i == 0);
+                const bool leaf = nchild[i + 1] == 0;
+                bool masked = false;
+                int32_t dd = 0, a0 = 0;
+                uint32_t c0 = 0, nm = 0;
+                uint64_t w = d.row32[i];
+                for (uint64_t k = f.row_ptr[i]; k < f.row_ptr[i + 1]; k++) {
+                    const ub200_mutation& m = f.mutations[k];
+                    if (m.position < 0) { masked = true; continue; }
+                    const uint32_t pos = (uint32_t)m.position;
+                    const uint8_t prev = state[pos] ? state[pos] : m.ref_nuc;
+                    const int rp = prev != m.ref_nuc, rm = m.mut_nuc != m.ref_nuc;
+                    dd += rm - rp;
+                    if (!rm) { c0++; a0 += rp; }   // LOOP 1 for an absent position: common iff back to ref (:244-259)
+                    d.mutw[w++] = pack_mut(pos, (uint32_t)nuc_code(m.ref_nuc), (uint32_t)nuc_code(prev),
+                                           (uint32_t)nuc_code(m.mut_nuc));
+                    undo.push_back({i, pos, state[pos]});
+                    state[pos] = m.mut_nuc;
+                    nm++;
+                }
+                const int32_t par = f.parent[i];
+                const int32_t dpar = is_root ? 0 : ((uint32_t)par >= lo ? dref[par] : dref_anc[d.level[par]]);
+                dref[i] = dpar + dd;
+                if (masked || is_root) { a0 = 0; c0 = 0; }  // masked: LOOP 1 breaks before taking anything (:197-200)
+                const bool hu0 = masked || (nm > c0);
+                const bool valid0 = is_root || (leaf ? c0 > 0 : (!hu0 || c0 > 0));
+                NodeHdr h;
+                h.g = is_root ? dref[i] : dpar - a0;
+                h.tiekey = d.tiekey[i];
+                const uint32_t plane = (!is_root && (uint32_t)par >= (i & ~31u)) ? 1u + ((uint32_t)par & 31u) : 0u;
+                h.level_flags = (d.level[i] << kLevelShift) | (plane << 8) | (leaf ? kFlagLeaf : 0) | (masked ? kFlagMasked : 0) |
+                                (is_root ? kFlagRoot : 0) | (valid0 ? kFlagValid0 : 0) | ((hu0 && !is_root) ? kFlagHu0 : 0);
+                h.nmut_c0 = (nm << 16) | c0;
+                d.hdr[i] = h;
+                path.push_back(i);
+            }
+        };
+        if (nt <= 1) chunk(0);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned c = 0; c < nt; c++) pool.emplace_back(chunk, c);
+            for (auto& th : pool) th.join();
+        }
+    }
+
+    pt.lap("path-state DFS");
     // ---- tiles: contiguous DFS ranges of roughly equal cost (mutations + per-node overhead)
     {
         const uint64_t node_cost = 4;
@@ -399,7 +533,9 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
             d.anc_ptr[t + 1] = (uint32_t)d.anc.size();
         }
     }
+    pt.lap("k_score tiles");
     derive3(f, target_tiles, min_tile_cost, d);
+    pt.lap("segment layout (derive3)");
     if (d.have3 && d.stream.size() / 4 >= (1ull << 32)) { err = "flat MAT: stream longer than 2^34 words"; return UB200_E_LIMIT; }
     return UB200_OK;
 }

@@ -2,7 +2,9 @@
 // C-ABI glue (api.cu).  See DESIGN.md "Data layout in HBM".
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "usher_b200.h"
@@ -71,6 +73,16 @@ UB200_HD inline uint32_t mut3_pos(uint32_t w) { return ((w >> (NARROW ? 16 : 14)
 constexpr uint32_t kFlagOpen = 32u;    // internal node with a descendant beyond its 32-node block
 constexpr uint32_t kChunk3 = 256;      // stream words per bulk copy (1 KB); tiles start on chunk boundaries
 
+// std::vector that leaves new elements uninitialised (resize() of the 1.3 GB stream must not write zeros first)
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+using StreamVec = std::vector<uint32_t, NoInitAlloc<uint32_t>>;
+
 struct Derived {
     uint32_t n = 0;
     uint64_t m = 0;          // unmasked mutations kept on the device
@@ -92,7 +104,7 @@ struct Derived {
     // a block segment the rows of one aligned 32-node block; every segment starts on a 4-word boundary.
     bool have3 = false;               // false: genome too long for the 23-bit position field
     bool narrow3 = false;             // stream words in the narrow form
-    std::vector<uint32_t> stream;     // padded to kChunk3
+    StreamVec stream;                 // padded to kChunk3
     std::vector<NodeHdr> hdr3;        // padded like hdr
     std::vector<uint32_t> tile3_start;// [T3+1] first node of each tile (multiple of 32)
     std::vector<uint32_t> tile3_w0;   // [T3+1] first stream chunk of each tile (tile t ends where t+1 starts)

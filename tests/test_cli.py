@@ -157,3 +157,29 @@ def test_ambiguous_samples_host_outputs_match_reference(usher, run):
         if key in g.files:
             assert open(os.path.join(d, f)).read() == str(g[key]), (run, f)
     assert f"The parsimony score for this tree is: {int(g[run + '__parsimony'])}" in r.stderr or run == "no_add"
+
+
+def test_flat_loader_round_trip_is_byte_identical(usher):
+    """N1: parsimony.proto -> flat SoA -> parsimony.proto without Node objects reproduces the file byte for byte
+    (plain and gzip-compressed), i.e. the flat loader sees the same nodes, names, rows and condensed sets."""
+    d = tempfile.mkdtemp()
+    subprocess.check_call([usher, "-i", PB, "--flat-resave", d + "/f.pb"], stderr=subprocess.DEVNULL)
+    assert open(d + "/f.pb", "rb").read() == open(PB, "rb").read()
+    subprocess.check_call([usher, "-i", PB, "--flat-resave", d + "/f.pb.gz"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([usher, "-i", d + "/f.pb.gz", "--flat-resave", d + "/g.pb"], stderr=subprocess.DEVNULL)
+    assert open(d + "/g.pb", "rb").read() == open(PB, "rb").read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vcf,key", [(VCF, "noadd_placement_stats"), (os.path.join(common.GOLDEN, "hostgold_samples.vcf"), None)])
+def test_flat_placement_equals_no_add_run(usher, vcf, key):
+    """N1 end to end: pb -> flat SoA -> GPU -> records (no Node objects) gives the scores and numbers of optimal
+    placements of the reference's --no-add run."""
+    d = tempfile.mkdtemp()
+    r = subprocess.run([usher, "-i", PB, "-v", vcf, "-d", d, "--place-flat"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = [l.split("\t")[:3] for l in open(d + "/flat-placements.tsv").read().splitlines() if not l.startswith("#")]
+    exp_txt = str(common.load(os.path.join(common.GOLDEN, "config1.npz"))[key]) if key else \
+        str(common.load(os.path.join(common.GOLDEN, "hostgold.npz"))["no_add__placement_stats.tsv"])
+    exp = [l.split("\t")[:3] for l in exp_txt.splitlines() if l]
+    assert got == exp

@@ -1,6 +1,7 @@
 // See mutation_annotated_tree.hpp.  Behaviour follows reference src/mutation_annotated_tree.cpp (line ranges
 // cited per function); the code is an independent implementation.
 #include "mutation_annotated_tree.hpp"
+#include "flat_mat.hpp"
 
 #include <zlib.h>
 
@@ -11,6 +12,7 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <sstream>
 
 #include "usher_graph.hpp"
@@ -657,6 +659,221 @@ void save_mutation_annotated_tree(const Tree& tree, const std::string& filename)
     }
 }
 
+// ---------------------------------------------------------------- flat loader / saver (flat_mat.hpp)
+bool load_flat_mutation_annotated_tree(const std::string& filename, FlatTree& t, std::string& err) {
+    std::string raw;
+    if (!read_all(filename, raw)) { err = "could not read " + filename; return false; }
+    pb::Reader top(raw.data(), raw.size());
+    pb::Reader nwk(nullptr, 0);
+    std::vector<pb::Reader> lists, conds, metas;
+    while (top.more()) {
+        const uint64_t tag = top.varint();
+        const uint32_t field = (uint32_t)(tag >> 3), wt = (uint32_t)(tag & 7);
+        if (wt == 2 && field >= 1 && field <= 4) {
+            pb::Reader r = top.sub();
+            if (field == 1) nwk = r;
+            else if (field == 2) lists.push_back(r);
+            else if (field == 3) conds.push_back(r);
+            else metas.push_back(r);
+        } else {
+            top.skip(wt);
+        }
+    }
+    if (!top.ok) { err = filename + " is not a valid parsimony.proto message"; return false; }
+    // ---- newick -> parent[] / names[]: the reference's tokeniser (split at ',', '(' opens an internal node, the
+    // text before the first ':' or ')' names the leaf, ')' closes), nodes numbered as they are created
+    t = FlatTree();
+    {
+        const char* p = (const char*)nwk.p;
+        const char* end = (const char*)nwk.end;
+        std::vector<int32_t> stack;
+        size_t internal = 0;
+        while (p < end) {
+            const char* q = p;
+            while (q < end && *q != ',') q++;
+            size_t opens = 0, closes = 0;
+            std::string leaf;
+            bool stop = false;
+            for (const char* c = p; c < q; c++) {
+                if (*c == '(') opens++;
+                else if (*c == ')') { closes++; stop = true; }
+                else if (*c == ':') stop = true;
+                else if (!stop) leaf += *c;
+            }
+            for (size_t j = 0; j < opens; j++) {
+                t.parent.push_back(stack.empty() ? -1 : stack.back());
+                t.names.push_back("node_" + std::to_string(++internal));
+                stack.push_back((int32_t)t.parent.size() - 1);
+            }
+            if (stack.empty()) { err = "incorrect Newick format"; return false; }
+            t.parent.push_back(stack.back());
+            t.names.push_back(leaf);
+            for (size_t j = 0; j < closes; j++) {
+                if (stack.empty()) { err = "incorrect Newick format"; return false; }
+                stack.pop_back();
+            }
+            p = q + 1;
+        }
+        if (!stack.empty()) { err = "incorrect Newick format"; return false; }
+    }
+    const size_t n = t.parent.size();
+    if (lists.size() < n) { err = "protobuf holds " + std::to_string(lists.size()) + " mutation lists for " + std::to_string(n) + " nodes"; return false; }
+    t.n_children.assign(n, 0);
+    for (size_t i = 1; i < n; i++) t.n_children[t.parent[i]]++;
+    // ---- mutation lists -> CSR rows
+    t.row_ptr.assign(n + 1, 0);
+    bool chrom_set = false;
+    for (size_t i = 0; i < n; i++) {
+        pb::Reader l = lists[i];
+        const size_t row0 = t.muts.size();
+        while (l.more()) {
+            const uint64_t tag = l.varint();
+            if (!((tag >> 3) == 1 && (tag & 7) == 2)) { l.skip((uint32_t)(tag & 7)); continue; }
+            pb::Reader mr = l.sub();
+            int32_t pos = 0, refn = 0, parn = 0;
+            int8_t mut = 0;
+            const char* chrom_p = nullptr;
+            size_t chrom_n = 0;
+            while (mr.more()) {
+                const uint64_t t2 = mr.varint();
+                const uint32_t f2 = (uint32_t)(t2 >> 3), w2 = (uint32_t)(t2 & 7);
+                if (f2 == 1 && w2 == 0) pos = (int32_t)mr.varint();
+                else if (f2 == 2 && w2 == 0) refn = (int32_t)mr.varint();
+                else if (f2 == 3 && w2 == 0) parn = (int32_t)mr.varint();
+                else if (f2 == 4 && w2 == 0) mut |= (int8_t)(1 << (int)mr.varint());
+                else if (f2 == 4 && w2 == 2) { pb::Reader pk = mr.sub(); while (pk.more()) mut |= (int8_t)(1 << (int)pk.varint()); }
+                else if (f2 == 5 && w2 == 2) { pb::Reader s = mr.sub(); chrom_p = (const char*)s.p; chrom_n = (size_t)(s.end - s.p); }
+                else mr.skip(w2);
+            }
+            if (!l.ok || !mr.ok) { err = "malformed mutation list of node " + std::to_string(i); return false; }
+            if (chrom_n || chrom_set) {
+                if (!chrom_set) { t.chrom.assign(chrom_p ? chrom_p : "", chrom_n); chrom_set = true; }
+                else if (t.chrom.size() != chrom_n || (chrom_n && memcmp(t.chrom.data(), chrom_p, chrom_n) != 0)) {
+                    err = "the tree names more than one chromosome: not representable in the flat form";
+                    return false;
+                }
+            }
+            ub200_mutation m;
+            m.position = pos;
+            m.is_missing = 0;
+            if (pos >= 0) {
+                m.ref_nuc = (uint8_t)(1 << refn);
+                m.par_nuc = (uint8_t)(1 << parn);
+                m.mut_nuc = (uint8_t)mut;
+                if (m.mut_nuc == m.par_nuc) continue;   // :580: entries that change nothing are dropped
+            } else {
+                m.ref_nuc = m.par_nuc = m.mut_nuc = 0;
+            }
+            t.muts.push_back(m);
+        }
+        // rows are stored position-sorted (Node::add_mutation keeps them so; masked entries first)
+        if (!std::is_sorted(t.muts.begin() + row0, t.muts.end(),
+                            [](const ub200_mutation& a, const ub200_mutation& b) { return a.position < b.position; }))
+            std::stable_sort(t.muts.begin() + row0, t.muts.end(),
+                             [](const ub200_mutation& a, const ub200_mutation& b) { return a.position < b.position; });
+        t.row_ptr[i + 1] = t.muts.size();
+    }
+    t.have_metadata = !metas.empty();
+    t.annotations.assign(n, {});
+    for (size_t i = 0; i < n && i < metas.size(); i++) {
+        pb::Reader m = metas[i];
+        while (m.more()) {
+            const uint64_t tag = m.varint();
+            if ((tag >> 3) == 1 && (tag & 7) == 2) {
+                pb::Reader s = m.sub();
+                t.annotations[i].emplace_back((const char*)s.p, (size_t)(s.end - s.p));
+            } else m.skip((uint32_t)(tag & 7));
+        }
+    }
+    for (auto c : conds) {
+        std::string name;
+        std::vector<std::string> members;
+        while (c.more()) {
+            const uint64_t tag = c.varint();
+            if ((tag & 7) != 2) { c.skip((uint32_t)(tag & 7)); continue; }
+            pb::Reader s = c.sub();
+            if ((tag >> 3) == 1) name.assign((const char*)s.p, (size_t)(s.end - s.p));
+            else if ((tag >> 3) == 2) members.emplace_back((const char*)s.p, (size_t)(s.end - s.p));
+        }
+        t.condensed.emplace_back(std::move(name), std::move(members));
+    }
+    return true;
+}
+
+bool save_flat_mutation_annotated_tree(const FlatTree& t, const std::string& filename, std::string& err) {
+    const size_t n = t.parent.size();
+    std::string out;
+    // ---- newick: leaves by name, no internal names, branch length = number of mutations (as save_mutation_annotated_tree)
+    {
+        std::string nwk;
+        auto len_of = [&](size_t i) {
+            std::ostringstream ss;
+            ss << ':' << static_cast<float>(t.row_ptr[i + 1] - t.row_ptr[i]);
+            return ss.str();
+        };
+        // children lists in DFS order
+        std::vector<uint32_t> first(n + 1, 0), kids(n ? n - 1 : 0);
+        for (size_t i = 1; i < n; i++) first[t.parent[i] + 1]++;
+        for (size_t i = 0; i < n; i++) first[i + 1] += first[i];
+        { std::vector<uint32_t> fill(first.begin(), first.end() - 1); for (size_t i = 1; i < n; i++) kids[fill[t.parent[i]]++] = (uint32_t)i; }
+        struct Frame { uint32_t node; uint32_t next; };
+        std::vector<Frame> st;
+        if (n) st.push_back({0, 0});
+        while (!st.empty()) {
+            Frame& f = st.back();
+            const uint32_t u = f.node, nk = first[u + 1] - first[u];
+            if (nk == 0) { nwk += t.names[u]; nwk += len_of(u); st.pop_back(); continue; }
+            if (f.next == 0) nwk += '(';
+            if (f.next < nk) {
+                if (f.next) nwk += ',';
+                const uint32_t c = kids[first[u] + f.next++];
+                st.push_back({c, 0});
+                continue;
+            }
+            nwk += ')';
+            nwk += len_of(u);
+            st.pop_back();
+        }
+        nwk += ';';
+        pb::put_bytes(out, 1, nwk);
+    }
+    auto code = [](uint8_t one_hot) { return (int32_t)(31 - __builtin_clz((unsigned)one_hot)); };
+    for (size_t i = 0; i < n; i++) {
+        std::string list;
+        for (uint64_t k = t.row_ptr[i]; k < t.row_ptr[i + 1]; k++) {
+            const ub200_mutation& m = t.muts[k];
+            std::string mm;
+            pb::put_i32(mm, 1, m.position);
+            if (m.position < 0) {
+                pb::put_i32(mm, 2, -1);
+                pb::put_i32(mm, 3, -1);
+            } else {
+                pb::put_i32(mm, 2, code(m.ref_nuc));
+                pb::put_i32(mm, 3, code(m.par_nuc));
+                std::string packed;
+                for (int b = 0; b < 4; b++) if (m.mut_nuc & (1 << b)) pb::put_varint(packed, (uint64_t)b);
+                if (!packed.empty()) pb::put_bytes(mm, 4, packed);
+            }
+            if (!t.chrom.empty()) pb::put_bytes(mm, 5, t.chrom);
+            pb::put_bytes(list, 1, mm);
+        }
+        pb::put_bytes(out, 2, list);
+    }
+    for (auto& c : t.condensed) {
+        std::string cc;
+        pb::put_bytes(cc, 1, c.first);
+        for (auto& l : c.second) pb::put_bytes(cc, 2, l);
+        pb::put_bytes(out, 3, cc);
+    }
+    for (size_t i = 0; i < n; i++) {
+        std::string meta;
+        if (i < t.annotations.size()) for (auto& a : t.annotations[i]) pb::put_bytes(meta, 1, a);
+        pb::put_bytes(out, 4, meta);
+    }
+    if (!write_all(filename, out)) { err = "could not write " + filename; return false; }
+    return true;
+}
+
 // ---------------------------------------------------------------- outputs / inputs around the placement
 void get_sample_mutation_paths(Tree* T, const std::vector<std::string>& samples, const std::string& filename) {
     FILE* f = fopen(filename.c_str(), "w");   // reference :1991-2050
@@ -801,6 +1018,12 @@ void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Samp
         build_mat_from_vcf(T, vcf_filename, missing_samples);
         return;
     }
+    read_vcf_samples(vcf_filename, [T](const std::string& name) { return T->get_node(name) || T->condensed_leaves.count(name); },
+                     missing_samples);
+}
+
+void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(const std::string&)>& in_tree,
+                      std::vector<Missing_Sample>& missing_samples) {
     fprintf(stderr, "Loading VCF file\n");   // reference :2180-2278
     std::string raw;
     if (!read_all(vcf_filename, raw)) {
@@ -820,7 +1043,7 @@ void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Samp
             if (w[1] == "POS") {
                 for (size_t j = 9; j < w.size(); j++) {
                     ids.push_back(w[j]);
-                    if (!T->get_node(w[j]) && !T->condensed_leaves.count(w[j])) {
+                    if (!in_tree(w[j])) {
                         missing_samples.emplace_back(Missing_Sample(w[j]));
                         cols.push_back(j);
                     } else {

@@ -4,6 +4,7 @@
 // (SURVEY.md §2 #4-#7, §9); matUtils/matOptimize-only helpers are out of scope.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -105,6 +106,9 @@ void save_mutation_annotated_tree(const Tree& tree, const std::string& filename)
 
 void get_sample_mutation_paths(Tree* T, const std::vector<std::string>& samples, const std::string& filename);
 // placement mode only (create_new_mat == false): fills Missing_Sample::mutations in VCF row order
+// placement-mode VCF reader on a membership predicate (the flat path has no Tree): samples already in the tree are skipped
+void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(const std::string&)>& in_tree,
+                      std::vector<Missing_Sample>& missing_samples);
 void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Sample>& missing_samples,
               bool create_new_mat);
 

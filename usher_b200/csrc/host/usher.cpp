@@ -3,8 +3,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
+#include "flat_mat.hpp"
+#include "usher_b200.h"
 #include "usher_common.hpp"
 
 namespace {
@@ -32,6 +35,8 @@ const Opt kOpts[] = {
     {"no-add", 'n', false, "Do not add new samples to the tree"},
     {"detailed-clades", 'D', false, "In clades.txt, write a histogram of annotated clades and counts across all equally parsimonious placements"},
     {"threads", 'T', true, "Accepted for compatibility (the search runs on the GPU)"},
+    {"flat-resave", 0, true, "Load the -i protobuf straight into the flat SoA (no Node objects) and write it back to this file"},
+    {"place-flat", 0, false, "Frozen-tree placement of the VCF's new samples on the -i protobuf loaded straight into the flat SoA (no Node objects); writes flat-placements.tsv"},
     {"device", 0, true, "CUDA device ordinal [DEFAULT: every visible GPU for frozen-tree batches (-n, -p, the -s/-S pre-pass), GPU 0 otherwise]"},
     {"dump-flat", 0, true, "(diagnostic) write the loaded tree and VCF samples as text and exit; needs no GPU"},
     {"resave", 0, true, "(diagnostic) write the loaded tree back as protobuf and exit; needs no GPU"},
@@ -48,7 +53,8 @@ void usage() {
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string vcf, tree_fn, outdir = ".", din, dout, dump_flat, resave;
+    std::string vcf, tree_fn, outdir = ".", din, dout, dump_flat, resave, flat_resave;
+    bool place_flat = false;
     bool s1 = false, s2 = false, s3 = false, rev = false, ct = false, cot = false, unc = false, pps = false, keep = false,
          no_add = false, detailed = false;
     uint32_t max_trees = 1, max_unc = 1000000, max_pars = 1000000;
@@ -91,8 +97,64 @@ int main(int argc, char** argv) {
         else if (n == "detailed-clades") detailed = true; else if (n == "threads") {}
         else if (n == "device") device = std::stoi(val);
         else if (n == "dump-flat") dump_flat = val; else if (n == "resave") resave = val;
+        else if (n == "flat-resave") flat_resave = val; else if (n == "place-flat") place_flat = true;
         else if (n == "version") { printf("UShER usher_b200 (placement build)\n"); return 0; }
         else if (n == "help") { usage(); return 0; }
+    }
+    if (!flat_resave.empty() || place_flat) {
+        // ---- N1: protobuf -> flat SoA -> GPU, no MAT::Node objects anywhere
+        if (din.empty()) { fprintf(stderr, "--flat-resave / --place-flat need --load-mutation-annotated-tree\n"); return 1; }
+        MAT::FlatTree ft;
+        std::string err;
+        Timer tm;
+        tm.Start();
+        if (!MAT::load_flat_mutation_annotated_tree(din, ft, err)) { fprintf(stderr, "ERROR: %s\n", err.c_str()); return 1; }
+        fprintf(stderr, "Loaded %zu nodes, %zu mutations straight into the flat form in %ld msec\n", ft.parent.size(), ft.muts.size(), tm.Stop());
+        if (!flat_resave.empty()) {
+            if (!MAT::save_flat_mutation_annotated_tree(ft, flat_resave, err)) { fprintf(stderr, "ERROR: %s\n", err.c_str()); return 1; }
+            if (!place_flat) return 0;
+        }
+        if (vcf.empty()) { fprintf(stderr, "the option '--vcf' is required but missing\n"); return 1; }
+        std::unordered_set<std::string> known(ft.names.begin(), ft.names.end());
+        for (auto& c : ft.condensed) for (auto& m : c.second) known.insert(m);
+        std::vector<Missing_Sample> missing;
+        MAT::read_vcf_samples(vcf, [&](const std::string& nm) { return known.count(nm) != 0; }, missing);
+        fprintf(stderr, "Found %zu missing samples.\n", missing.size());
+        std::vector<uint64_t> sp{0};
+        std::vector<ub200_mutation> calls;
+        for (auto& s : missing) {
+            for (auto& m : s.mutations)
+                calls.push_back({m.position, (uint8_t)m.ref_nuc, (uint8_t)m.ref_nuc, (uint8_t)m.mut_nuc, (uint8_t)m.is_missing});
+            sp.push_back(calls.size());
+        }
+        ub200_flat_mat v = ft.view();
+        ub200_multi* multi = nullptr;
+        const int one = device < 0 ? 0 : device;
+        tm.Start();
+        if (ub200_multi_create(&v, device < 0 ? 0 : 1, device < 0 ? nullptr : &one, &multi) != UB200_OK) {
+            fprintf(stderr, "ERROR: %s\n", ub200_last_error());
+            return 1;
+        }
+        for (int i = 0; i < ub200_multi_size(multi); i++) ub200_mat_set_pass_samples(ub200_multi_mat(multi, i), 96);
+        fprintf(stderr, "Tree resident on %d GPU(s) in %ld msec\n", ub200_multi_size(multi), tm.Stop());
+        std::vector<ub200_placement> res(missing.size());
+        tm.Start();
+        if (!missing.empty() && ub200_multi_place_batch(multi, (uint32_t)missing.size(), sp.data(), calls.data(), 0, res.data(),
+                                                        nullptr, nullptr, nullptr, 0) != UB200_OK) {
+            fprintf(stderr, "ERROR: %s\n", ub200_last_error());
+            return 1;
+        }
+        fprintf(stderr, "Placed %zu samples in %ld msec\n", missing.size(), tm.Stop());
+        const std::string fn = outdir + "/flat-placements.tsv";
+        FILE* f = fopen(fn.c_str(), "w");
+        if (!f) { fprintf(stderr, "ERROR: cannot write %s\n", fn.c_str()); return 1; }
+        fprintf(f, "#Sample\tParsimony score\tNumber of parsimony-optimal placements\tBest node\tSibling (1) or child (0)\n");
+        for (size_t i = 0; i < missing.size(); i++)
+            fprintf(f, "%s\t%d\t%u\t%s\t%u\n", missing[i].name.c_str(), res[i].score, res[i].num_best,
+                    ft.names[res[i].best_node].c_str(), res[i].has_unique);
+        fclose(f);
+        ub200_multi_destroy(multi);
+        return 0;
     }
     if (vcf.empty() && resave.empty()) { fprintf(stderr, "the option '--vcf' is required but missing\n"); usage(); return 1; }
     MAT::Tree T;

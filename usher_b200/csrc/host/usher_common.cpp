@@ -73,10 +73,15 @@ void sample_calls(const Missing_Sample& s, std::vector<ub200_mutation>& out) {
 
 // What mapper2_body leaves in excess_mutations / imputed_mutations for ONE node with compute_vecs == true
 // (reference src/usher_mapper.cpp:190-445), recomputed on the host for the chosen node(s) only.
-void placement_vectors(MAT::Node* node, const std::vector<MAT::Mutation>& S, std::vector<MAT::Mutation>& excess,
-                       std::vector<MAT::Mutation>& imputed) {
+// Also returns what the call leaves in set_difference / has_unique and whether it would fold the node into the best
+// state (:448-455): the sequential search uses it to score the few nodes an earlier graft created or changed.
+struct NodeEval { int set_difference = 0; bool has_unique = false; bool valid = false; };
+NodeEval placement_vectors(MAT::Node* node, const std::vector<MAT::Mutation>& S, std::vector<MAT::Mutation>& excess,
+                           std::vector<MAT::Mutation>& imputed) {
     excess.clear();
     imputed.clear();
+    NodeEval ev;
+    int node_num_mut = 0, num_common_mut = 0;
     std::vector<MAT::Mutation> anc;
     std::unordered_set<int> seen;
     auto take = [&](const MAT::Mutation& m1, bool to_excess) {
@@ -89,19 +94,23 @@ void placement_vectors(MAT::Node* node, const std::vector<MAT::Mutation>& S, std
     if (!node->is_root()) {
         size_t start = 0;
         for (auto& m1 : node->mutations) {
-            if (m1.is_masked()) break;
+            node_num_mut++;
+            if (m1.is_masked()) { ev.has_unique = true; break; }
             bool found = false, found_pos = false;
             for (size_t k = start; k < S.size(); k++) {
                 const auto& m2 = S[k];
                 start = k;
                 if (m1.position == m2.position) {
                     found_pos = true;
-                    if (m2.is_missing) found = true;
-                    else if (m2.mut_nuc & m1.mut_nuc) { take(m1, true); found = true; break; }
+                    if (m2.is_missing) { found = true; num_common_mut++; }
+                    else if (m2.mut_nuc & m1.mut_nuc) { take(m1, true); found = true; num_common_mut++; break; }
                 }
                 if (m1.position < m2.position) break;
             }
-            if (!found && !found_pos && m1.mut_nuc == m1.ref_nuc) take(m1, true);
+            if (!found) {
+                if (!found_pos && m1.mut_nuc == m1.ref_nuc) { take(m1, true); num_common_mut++; }
+                else ev.has_unique = true;
+            }
         }
     } else {
         for (auto& m : node->mutations) { anc.push_back(m); seen.insert(m.position); }
@@ -134,7 +143,7 @@ void placement_vectors(MAT::Node* node, const std::vector<MAT::Mutation>& S, std
             if (has_ref) m.mut_nuc = m1.ref_nuc;
             else for (int b = 0; b < 4; b++) if (m1.mut_nuc & (1 << b)) { m.mut_nuc = (int8_t)(1 << b); break; }
             if (amb) imputed.push_back(m);
-            if (m.mut_nuc != m.par_nuc) excess.push_back(m);
+            if (m.mut_nuc != m.par_nuc) { excess.push_back(m); ev.set_difference++; }
         }
     }
     for (auto& m1 : anc) {   // LOOP 3: back-mutations to the reference allele
@@ -150,7 +159,24 @@ void placement_vectors(MAT::Node* node, const std::vector<MAT::Mutation>& S, std
         MAT::Mutation m;
         m.chrom = m1.chrom; m.position = m1.position; m.ref_nuc = m1.ref_nuc; m.par_nuc = m1.mut_nuc; m.mut_nuc = m1.ref_nuc;
         excess.push_back(m);
+        ev.set_difference++;
     }
+    const bool leaf = node->is_leaf();
+    ev.valid = node->is_root() || (ev.has_unique && !leaf && num_common_mut > 0 && node_num_mut != num_common_mut) ||
+               (leaf && num_common_mut > 0) || (!ev.has_unique && !leaf && node_num_mut == num_common_mut);
+    return ev;
+}
+
+// a before b in Tree::breadth_first_expansion() (level order, children in stored order)
+bool bfs_before(const MAT::Node* a, const MAT::Node* b) {
+    if (a->level != b->level) return a->level < b->level;
+    while (a->parent != b->parent) { a = a->parent; b = b->parent; }
+    if (!a->parent) return false;
+    for (auto c : a->parent->children) {
+        if (c == a) return true;
+        if (c == b) return false;
+    }
+    return false;
 }
 
 void die_cuda() {
@@ -226,6 +252,49 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
                 break;
             }
         };
+        // ---- sequential mode, batched.  The reference re-searches the whole tree after every graft.
+        // A graft creates at most two nodes (the new leaf, and a new internal node when the branch is split) and changes
+        // the mutation list of at most one existing node (the split branch); the score and validity of every other node
+        // are untouched (its root path carries the same mutations), only tie-break data moves.  So the GPU scores ALL
+        // the remaining samples against one frozen tree version in one batched call (whole optimal sets), and per sample
+        // the host re-scores the few nodes created or changed since the freeze (placement_vectors = mapper2_body for one
+        // node) and redoes the tie-break on the live tree.  After kRefreeze grafts the tree is flattened again.
+        const size_t kRefreeze = getenv("UB200_REFREEZE") ? (size_t)atoi(getenv("UB200_REFREEZE")) : 128;
+        std::vector<size_t> frozen_of;            // frozen_of[k] = sample index of batch record k (current freeze)
+        std::vector<ub200_placement> fbatch;
+        std::vector<uint64_t> fset_ptr;
+        std::vector<uint32_t> fbest_set;
+        std::unordered_map<size_t, size_t> frec;  // sample index -> record of the current freeze
+        std::unordered_set<MAT::Node*> changed;   // nodes of the frozen version whose mutation list a graft split
+        std::vector<MAT::Node*> created;          // nodes created since the freeze
+        bool have_freeze = false;
+        bool tree_dirty = false;
+        auto freeze_from = [&](size_t idx0) {
+            if (have_freeze || tree_dirty) dev.build(*T, device, indexes.size() - idx0 > 64);   // else: the build above
+            tree_dirty = false;
+            frozen_of.clear(); frec.clear(); changed.clear(); created.clear();
+            std::vector<uint64_t> sp{0};
+            std::vector<ub200_mutation> calls;
+            for (size_t k = idx0; k < indexes.size(); k++) {
+                if (T->get_node(missing_samples[indexes[k]].name)) continue;
+                frec[indexes[k]] = frozen_of.size();
+                frozen_of.push_back(indexes[k]);
+                sample_calls(missing_samples[indexes[k]], calls);
+                sp.push_back(calls.size());
+            }
+            fbatch.assign(frozen_of.size(), ub200_placement{});
+            fset_ptr.assign(frozen_of.size() + 1, 0);
+            fbest_set.assign(std::max<size_t>(16, 4 * frozen_of.size()), 0);
+            for (;;) {
+                if (frozen_of.empty()) break;
+                int rc = ub200_multi_place_batch(dev.multi, (uint32_t)frozen_of.size(), sp.data(), calls.data(), UB200_WANT_BEST_SET,
+                                                 fbatch.data(), nullptr, fbest_set.data(), fset_ptr.data(), fbest_set.size());
+                if (rc == UB200_E_CAPACITY) { fbest_set.assign(fset_ptr[frozen_of.size()] + 16, 0); continue; }
+                if (rc != UB200_OK) die_cuda();
+                break;
+            }
+            have_freeze = true;
+        };
         if (!print_parsimony_scores && (sort1 || sort2) && missing_samples.size() > 1) {
             timer.Start();
             fprintf(stderr, "Computing parsimony scores and number of parsimony-optimal placements for new samples and using them to sort the samples.\n");
@@ -246,7 +315,6 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
 
         const std::string stats_fn = outdir + "/placement_stats.tsv";
         FILE* stats = fopen(stats_fn.c_str(), "w");
-        bool tree_dirty = false;
         std::vector<int32_t> pps_scores;   // -p: per-node scores of samples indexes[pps_first .. pps_first + pps_count)
         size_t pps_first = 0, pps_count = 0;
         for (size_t idx = 0; idx < indexes.size(); idx++) {
@@ -266,25 +334,49 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
             }
             // ---- the search: one sample against the current tree version
             ub200_placement res;
-            std::vector<uint32_t> opt;   // optimal nodes (DFS index, bit 31 = node_has_unique)
+            std::vector<std::pair<MAT::Node*, bool>> optn;   // optimal nodes of the CURRENT tree, node_has_unique
             std::vector<int32_t> node_scores;
+            size_t current_nodes = dev.flat.dfs.size();
             if (frozen) {
                 res = batch[s];
-                opt.assign(best_set.begin() + set_ptr[s], best_set.begin() + set_ptr[s + 1]);
+                for (uint64_t k = set_ptr[s]; k < set_ptr[s + 1]; k++)
+                    optn.emplace_back(dev.flat.dfs[best_set[k] & 0x7fffffffu], (best_set[k] >> 31) != 0);
             } else {
-                if (tree_dirty) { dev.build(*T, device, false); tree_dirty = false; }
-                std::vector<ub200_mutation> calls;
-                sample_calls(missing_samples[s], calls);
-                uint64_t sp[2] = {0, calls.size()}, bp[2] = {0, 0};
-                opt.assign(64, 0);
-                for (;;) {
-                    int rc = ub200_place_batch(dev.mat, 1, sp, calls.data(), UB200_WANT_BEST_SET, &res, nullptr, opt.data(),
-                                               bp, opt.size());
-                    if (rc == UB200_E_CAPACITY) { opt.assign(bp[1] + 16, 0); continue; }
-                    if (rc != UB200_OK) die_cuda();
+                if (!have_freeze || created.size() >= 2 * kRefreeze) freeze_from(idx);
+                for (int attempt = 0;; attempt++) {
+                    const size_t k = frec.at(s);
+                    res = fbatch[k];
+                    optn.clear();
+                    for (uint64_t q = fset_ptr[k]; q < fset_ptr[k + 1]; q++) {
+                        MAT::Node* n = dev.flat.dfs[fbest_set[q] & 0x7fffffffu];
+                        if (!changed.count(n)) optn.emplace_back(n, (fbest_set[q] >> 31) != 0);
+                    }
+                    // every optimal node of the frozen version has been split since: the best score over the untouched
+                    // nodes is unknown -> flatten the live tree again (rare)
+                    if (optn.empty() && attempt == 0) { freeze_from(idx); continue; }
                     break;
                 }
-                opt.resize(bp[1]);
+                int best_sd = optn.empty() ? INT32_MAX : res.score;
+                std::vector<MAT::Mutation> ex, im;
+                auto consider = [&](MAT::Node* n) {
+                    const NodeEval ev = placement_vectors(n, missing_samples[s].mutations, ex, im);
+                    if (!ev.valid || ev.set_difference > best_sd) return;
+                    if (ev.set_difference < best_sd) { best_sd = ev.set_difference; optn.clear(); }
+                    optn.emplace_back(n, ev.has_unique);
+                };
+                for (MAT::Node* n : changed) consider(n);
+                for (MAT::Node* n : created) consider(n);
+                // tie-break on the live tree (:476-493): more leaves first, then the larger BFS index
+                size_t bi = 0, bl = 0;
+                for (size_t q = 0; q < optn.size(); q++) {
+                    const size_t nl = T->get_num_leaves(optn[q].first);
+                    if (q == 0 || nl > bl || (nl == bl && bfs_before(optn[bi].first, optn[q].first))) { bi = q; bl = nl; }
+                }
+                res.score = best_sd;
+                res.num_best = (uint32_t)optn.size();
+                res.has_unique = optn[bi].second ? 1u : 0u;
+                std::swap(optn[0], optn[bi]);               // the chosen node first
+                current_nodes += created.size();
             }
             if (print_parsimony_scores) {
                 // per-node scores of the next samples in ONE batched call (as many as fit ~1 GB of host memory),
@@ -305,9 +397,9 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
             }
             const int best_set_difference = res.score;
             size_t num_best = res.num_best;
-            MAT::Node* best_node = dev.flat.dfs[res.best_node];
+            MAT::Node* best_node = frozen ? dev.flat.dfs[res.best_node] : optn[0].first;
             const bool best_node_has_unique = res.has_unique != 0;
-            const size_t total_nodes = dev.flat.dfs.size();
+            const size_t total_nodes = current_nodes;
 
             if (!print_parsimony_scores) {
                 fprintf(stderr, "Current tree size (#nodes): %zu\tSample name: %s\tParsimony score: %d\tNumber of parsimony-optimal placements: %zu\n",
@@ -330,7 +422,7 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
             if (print_parsimony_scores) {   // :557-578, rows in BFS order
                 auto bfs = T->breadth_first_expansion();
                 std::unordered_map<const MAT::Node*, size_t> didx;
-                for (size_t i = 0; i < total_nodes; i++) didx[dev.flat.dfs[i]] = i;
+                for (size_t i = 0; i < dev.flat.dfs.size(); i++) didx[dev.flat.dfs[i]] = i;
                 std::vector<MAT::Mutation> ex, im;
                 for (auto n : bfs) {
                     const int sc = node_scores[didx[n]];
@@ -352,9 +444,9 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
                 missing_samples[s].clade_assignments.assign(na, {});
                 missing_samples[s].best_clade_assignment.assign(na, "");
                 for (size_t c = 0; c < na; c++) {
-                    for (auto code : opt) {
-                        MAT::Node* n = dev.flat.dfs[code & 0x7fffffffu];
-                        const bool include_self = !n->is_leaf() && !(code >> 31);
+                    for (auto& on : optn) {
+                        MAT::Node* n = on.first;
+                        const bool include_self = !n->is_leaf() && !on.second;
                         auto ca = T->get_clade_assignment(n, (int)c, include_self);
                         missing_samples[s].clade_assignments[c].push_back(ca);
                         if (n == best_node) missing_samples[s].best_clade_assignment[c] = ca;
@@ -388,6 +480,11 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
                         for (auto& m : common) T->get_node(nid)->add_mutation(m);
                         for (auto& m : l1) best_node->add_mutation(m);
                         for (auto& m : l2) T->get_node(sample)->add_mutation(m);
+                        // a node created since the freeze is re-scored anyway; a frozen-version node now differs from its
+                        // device copy
+                        if (std::find(created.begin(), created.end(), best_node) == created.end()) changed.insert(best_node);
+                        created.push_back(T->get_node(nid));
+                        created.push_back(T->get_node(sample));
                     } else {                                              // child
                         MAT::Node* node = T->create_node(sample, best_node->identifier);
                         for (auto& m1 : excess) {
@@ -395,6 +492,7 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
                             if (!m1.is_masked()) for (auto& m2 : branch) if (same(m1, m2)) { found = true; break; }
                             if (!found) node->add_mutation(m1);
                         }
+                        created.push_back(node);
                     }
                     tree_dirty = true;
                 }

@@ -4,13 +4,19 @@
   python bench.py --gpus N --steps K --warmup W            (our arm; N>1 under torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU path, rank 0 only)
 
-Workload (config.workload = "c4"): synthetic 10M-node MAT, ~30 mutations/node, 30 kb genome
+Workload (config.workload = "c4"; "c5" = the same tree with ambiguous + N-run samples): synthetic 10M-node MAT, ~30 mutations/node, 30 kb genome
 (G(1e7, 30, 30000, uniform, seed 20260929)); samples = the "40-SNV" family of config 2/4.
 A step = every rank places `samples_per_rank` fresh samples against the whole tree (weak scaling: the per-GPU
 batch is fixed; at 8 GPUs one step is the 10k-sample job of BASELINE config 4), followed by ONE NCCL
 allgather of the 32-byte per-sample records.  `value` times the steps with the samples' calls already
 resident in HBM; `e2e` times the same steps through ub200_place_batch with HOST (pinned) buffers, H2D and
 D2H inside the timed region.  The tree (1.36 GB) is far larger than L2 (126 MB), so no L2 flush is needed.
+
+`extra` carries the other BASELINE configs and operating points measured in the same run on rank 0 (leaf-derived and
+ambiguous + N-run samples on the 10M-node tree, 96 samples per launch with three groups sharing one scan, the
+optimal-set pass, the 2M-node SARS-CoV-2-shaped tree at 256 samples per launch); `parity_at_size` is the reference
+spot check of this tree's results (oracle/spotcheck.py), run after every timed region; `cpu_baseline` brackets the
+stride-1 time of the reference's search (see cpu_bracket).
 """
 import argparse
 import json

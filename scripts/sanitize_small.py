@@ -14,5 +14,7 @@ for seed, n, L, mu, shape in ((1, 900, 120, 4.0, "uniform"), (2, 700, 300, 2.0, 
     m.close()
 s = capi.Synth(20000, 30.0, 30000, 0, 5)
 m = capi.Mat.from_flat_struct(s.flat)
-sp, sc, _ = s.samples(64, 2, 1)
-print(m.place_batch(sp, sc)["placements"]["score"][:8])
+for ps, nc in ((32, 1), (64, 2), (96, 3)):       # single-group scans and shared scans (union bitmap, NC consumers)
+    m.set_pass_samples(ps); m.set_scan_sharing(nc)
+    sp, sc, _ = s.samples(100, 2, 1)
+    print(ps, nc, m.place_batch(sp, sc, best_set=True)["placements"]["score"][:8])

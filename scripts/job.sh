@@ -1,18 +1,5 @@
 set -x
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --durations=6 > gpurun_out/r_tests.log 2>&1
-tail -n 14 gpurun_out/r_tests.log
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r_bench_n1.json 2> gpurun_out/r_bench_n1.log
-cat gpurun_out/r_bench_n1.json | head -c 1500; echo
-tail -n 12 gpurun_out/r_bench_n1.log
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r_bench_ref.json 2> gpurun_out/r_bench_ref.log
-cat gpurun_out/r_bench_ref.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/r_launch_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c4_b32 python scripts/one_launch.py c4 0 32 32 2 1 > gpurun_out/r_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c4_b96 python scripts/one_launch.py c4 0 96 96 2 3 > gpurun_out/r_ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c3_b256 python scripts/one_launch.py c3 1 256 256 2 0 > gpurun_out/r_ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c4_leaf python scripts/one_launch.py c4 1 32 32 2 1 > gpurun_out/r_ncu4.log 2>&1
-for tool in memcheck synccheck racecheck; do
-  UB200_MIN_TILE=300 timeout 900 compute-sanitizer --tool $tool python scripts/sanitize_small.py > gpurun_out/r_san_$tool.log 2>&1
-  tail -n 3 gpurun_out/r_san_$tool.log
-done
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or sharing or tiny or random_vs_port" > gpurun_out/s_tests.log 2>&1
+tail -n 4 gpurun_out/s_tests.log
+python scripts/quick_bench2.py c4 0,1 32:1,96:3 2>&1 | tail -4
+python scripts/quick_bench2.py mid,c3 0,2 32:1,256:3 2>&1 | grep -v "^\["

@@ -59,8 +59,8 @@ struct Cfg4 {
     static constexpr uint32_t kORing = 0;                   // u32[1024]
     static constexpr uint32_t kOList = 4096;                // u32[8][64]
     static constexpr uint32_t kOMsg = kOList + kSlots4 * kSlotCap4 * 4;   // uint2[8]
-    static constexpr uint32_t kOBars = kOMsg + kSlots4 * 8;               // 8 full + 8 empty mbarriers
-    static constexpr uint32_t kShared = kOBars + 2 * kSlots4 * 8;
+    static constexpr uint32_t kOBars = kOMsg + kSlots4 * 8;               // 8 full + 8 empty mbarriers + 2 ring stages
+    static constexpr uint32_t kShared = kOBars + 2 * kSlots4 * 8 + 16;
     // per-consumer part
     static constexpr uint32_t kODnode = 0;                  // i32[32][32] packed deltas
     static constexpr uint32_t kOStack = 4096;               // i16[kStack][32]
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
     volatile uint2* msg = reinterpret_cast<volatile uint2*>(ubase + C::kOMsg);
     const uint32_t mring_a = smem_u32(mring), bars_a = smem_u32(ubase + C::kOBars), list_a = smem_u32(list);
     const uint32_t bm_a = smem_u32(bm_s);
-    constexpr uint32_t kBarFull = 0, kBarEmpty = kSlots4;
+    constexpr uint32_t kBarFull = 0, kBarEmpty = kSlots4, kBarStage = 2 * kSlots4;
 
     const uint32_t* bm_g = p.bitmap + (size_t)sg * p.bitmap_words;
     if (SMEM_BITMAP) {
@@ -264,6 +264,8 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 mbar_init(bars_a + 8 * (kBarFull + i), 1);
                 mbar_init(bars_a + 8 * (kBarEmpty + i), NC);
             }
+            mbar_init(bars_a + 8 * (kBarStage + 0), 1);
+            mbar_init(bars_a + 8 * (kBarStage + 1), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         // =====================================================================================================
         // scanner
         // =====================================================================================================
-        uint32_t lrow = 0, rows_end = 0;   // next ring row to load, end of the tile's rows
+        uint32_t rows_end = 0;   // end of the tile's rows
         uint32_t nmsg = 0;        // messages sent so far; the open one lives in slot nmsg % kSlots4
         uint32_t fill = 0;        // hit words in the open message
         auto open_msg = [&]() {   // wait until every consumer has released the slot
@@ -293,21 +295,26 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             }
             nmsg++;
         };
-        // ring loader: rows of 128 words (512 B, absolute-aligned), one 16-byte cp.async per lane per row
-        // (LDGSTS, L2 -> shared memory without registers); two counters and cp.async groups are all the
-        // bookkeeping.  Rows below cur_row are dead.
-        auto ring_fill = [&](uint32_t cur_row) {
-            const uint32_t lim_row = min(rows_end, cur_row + kRingRows4);
-            while (lrow < lim_row) {
-                cp_async16(mring_a + (((lrow & (kRingRows4 - 1u)) << 9) + (lane << 4)),
-                           p.stream + ((size_t)lrow << 7) + (lane << 2));
-                lrow++;
+        // ring loader: the ring is two stages of one step (4 rows = 2 KB) each; a step is ONE bulk async copy (TMA
+        // unit, cp.async.bulk) that completes on the stage's mbarrier, issued by one elected lane a whole step ahead.
+        // gstep counts the steps this scanner has started: stage = gstep & 1, barrier phase = (gstep >> 1) & 1.
+        // A copy is issued exactly for the steps that will be processed (first row < rows_end: the tile's piece is
+        // padded by less than half a step), so every barrier phase is consumed in order.
+        uint32_t gstep = 0;
+        auto stage_load = [&](uint32_t step_id, uint32_t first_row) {   // rows [first_row, first_row + 4) of the stream
+            const uint32_t nrows = min(4u, rows_end - min(rows_end, first_row));
+            __syncwarp();                                               // every lane is done reading this stage
+            if (nrows && elect_one()) {
+                const uint32_t st = step_id & 1u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bars_a + 8 * (kBarStage + st), nrows * 512u);
+                bulk_g2s(mring_a + st * 2048u, p.stream + ((size_t)first_row << 7), nrows * 512u, bars_a + 8 * (kBarStage + st));
             }
-            cp_async_commit();
         };
         // hand the hits of the current step that lie in stream words [off, lim) (multiples of 4, inside the step
         // starting at word `base`) to the open message; full messages are sent (not flagged last) and reopened
         uint4 q0, q1, q2, q3;   // the current step's four rows (16 words per lane)
+        uint32_t stage_a = mring_a;   // shared-memory address of the current step's stage
         auto emit = [&](uint32_t hb_step, uint32_t base, uint32_t off, uint32_t lim) {
             const uint32_t idx = base + 4u * lane;
             uint32_t hb = hb_step;                            // bit 4k+j = word j of quad k (row k of the step)
@@ -337,8 +344,9 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 remaining = __shfl_sync(FULL, incl, 31);
                 excl = incl - c;
             }
-            if (NC > 1) {
-                // Shared scans see 2-3 times the hits: the hit words are stored straight from the registers they were
+            if (NC > 1 || big != 0u) {
+                // Shared scans see 2-3 times the hits, and so do single-group scans of dense sample families (some lane
+                // holds more than three hits): the hit words are stored straight from the registers they were
                 // tested in (16 predicated stores, no ring re-read, no per-hit loop).  The eight 64-word slots are one
                 // circular buffer of 512 words: hit p of this run goes to word (64 * open slot + fill + p) mod 512.
                 // Hits that spill over into further messages first reserve every slot they need (a step holds at most
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                     asm("bfind.u32 %0, %1;" : "=r"(bit) : "r"(hb));   // highest set bit (FLO)
                     hb ^= 1u << bit;
                     const uint32_t wi = idx + ((bit & 12u) << 5) + (bit & 3u);
-                    sts32_4(pa, lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
+                    sts32_4(pa, lds32_4(stage_a + ((wi - base) << 2)));
                     pa += 4u;
                 }
                 fill += remaining;
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 hb &= hb - 1;
                 const uint32_t wi = idx + ((bit >> 2) << 7) + (bit & 3u);
                 const uint32_t slot = (nmsg + (pidx >> 6)) % kSlots4;
-                sts32_4(list_a + ((slot * kSlotCap4 + (pidx & 63u)) << 2), lds32_4(mring_a + ((wi & (kRingWords4 - 1u)) << 2)));
+                sts32_4(list_a + ((slot * kSlotCap4 + (pidx & 63u)) << 2), lds32_4(stage_a + ((wi - base) << 2)));
                 pidx++;
             }
             for (uint32_t i = 1; i < nslots; i++) {
@@ -437,9 +445,8 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 break;
             }
             send_msg(kMsgTile4, cur.t);
-            lrow = cur.w0 * (kChunk3 / 128u);
             rows_end = cur.w1 * (kChunk3 / 128u);
-            ring_fill(lrow);
+            stage_load(gstep, cur.w0 * (kChunk3 / 128u));
             // segments of the tile in stream order: seed segments, then one segment per block
             const uint32_t nseed = (cur.lvl0 + 31u) >> 5;
             const uint32_t b0 = cur.n0 >> 5, nb = (cur.n1 - cur.n0 + 31u) >> 5;
@@ -466,12 +473,15 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 // ---- one step: 4 rows = 16 words per lane, loaded and tested once
                 // everything issued so far has to be there (this step's rows went out one step ago)
                 PROF_T0(tl);
-                cp_async_wait<0>();
-                __syncwarp();
+                // the next step's copy goes out first (into the stage read one step ago), then wait for this step's
+                stage_load(gstep + 1u, (base >> 7) + 4u);
+                stage_a = mring_a + (gstep & 1u) * 2048u;
+                mbar_wait(bars_a + 8 * (kBarStage + (gstep & 1u)), (gstep >> 1) & 1u);
+                gstep++;
                 PROF_ADD(3, tl);
                 const uint32_t idx = base + 4u * lane;
                 uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
-                auto row_of = [&](uint32_t k) { return lds128_4(mring_a + (((idx + 128u * k) & (kRingWords4 - 1u)) << 2)); };
+                auto row_of = [&](uint32_t k) { return lds128_4(stage_a + ((128u * k + 4u * lane) << 2)); };
                 auto test4 = [&](const uint4& q) {
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.x), 0u, q.x), 1u);
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.y), 0u, q.y), 1u);
@@ -479,9 +489,6 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                     acc = __funnelshift_r(acc, __funnelshift_r(bitmap_word<SMEM_BITMAP, NARROW>(bm_a, bm_g, q.w), 0u, q.w), 1u);
                 };
                 q0 = row_of(0); q1 = row_of(1); q2 = row_of(2); q3 = row_of(3);
-                // rows below this step are dead: top the ring up (needed one step from now) while the loads fly.
-                // With shared scans the hit words are taken from the registers, so this step's rows are dead too.
-                ring_fill((base >> 7) + (NC > 1 ? 4u : 0u));
                 test4(q0); test4(q1); test4(q2); test4(q3);
                 const uint32_t hb_step = acc >> 16;                // bit 4k+j = word j of quad k
                 PROF_ADD(4, tl);                                   // load wait + test

@@ -108,6 +108,9 @@ struct ub200_samples {
     unsigned long long* set_ptr = nullptr;
     uint32_t* set_fill = nullptr;
     uint64_t set_total = 0, set_cap = 0;
+    int32_t* tile_min = nullptr;   // [groups][tiles][32]: per tile the best candidate score of a sample (optimal-set pass)
+    size_t tile_min_cap = 0;
+    bool tile_min_on = false;
     bool have_results = false, have_node_scores = false, have_set = false;
     float prep_ms = 0.f;
     uint64_t max_calls = 0;    // longest call list in the batch
@@ -284,7 +287,7 @@ int launch_score4(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngro
     p.part_key = S->part_key; p.part_cnt = S->part_cnt;
     p.gstack = M->gstack3; p.gstack_levels = M->gstack3_levels;
     p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
-    p.base = S->base; p.node_scores = S->node_scores;
+    p.base = S->base; p.node_scores = S->node_scores; p.tile_min = S->tile_min_on ? S->tile_min : nullptr;
     p.tile_counter = S->tile_counter;
     p.prof = reinterpret_cast<unsigned long long*>(S->tile_counter + 64);   // 16 counters behind the tile counters
     CU(cudaMemsetAsync(S->tile_counter, 0, 256, M->stream));
@@ -506,7 +509,7 @@ void ub200_samples_free(ub200_samples* S) {
     cudaSetDevice(S->mat->device);
     cudaFree(S->calls); cudaFree(S->sample_ptr); cudaFree(S->call_sample); cudaFree(S->bitmap); cudaFree(S->tab);
     cudaFree(S->base); cudaFree(S->gbest); cudaFree(S->tile_counter); cudaFree(S->results); cudaFree(S->best_rel); cudaFree(S->part_key); cudaFree(S->part_cnt);
-    cudaFree(S->node_scores); cudaFree(S->set_out); cudaFree(S->set_ptr); cudaFree(S->set_fill);
+    cudaFree(S->node_scores); cudaFree(S->set_out); cudaFree(S->set_ptr); cudaFree(S->set_fill); cudaFree(S->tile_min);
     delete S;
 }
 
@@ -638,6 +641,21 @@ static int place_resident_impl(ub200_mat* M, ub200_samples* S, uint32_t flags, i
                         S->max_calls <= ub200::kMaxCallsV4;
     if (!use_v3) { int rc = ensure_v1(M); if (rc) return rc; }   // the first-generation layout, only when it is needed
     const uint32_t NG = M->pass_groups;
+    // optimal sets: pass 1 notes per tile the best candidate score of every sample, so that the collect pass only scans
+    // the few tiles that hold an optimal node (up to 1 GB of notes; beyond that the collect pass scans every tile)
+    S->tile_min_on = false;
+    if (use_v3 && (flags & UB200_WANT_BEST_SET)) {
+        const size_t bytes = (size_t)S->n_groups * M->n_tiles3 * 32 * sizeof(int32_t);
+        if (bytes <= ((size_t)1 << 30)) {
+            if (bytes > S->tile_min_cap) {
+                cudaFree(S->tile_min); S->tile_min = nullptr; S->tile_min_cap = 0;
+                CU(cudaMalloc((void**)&S->tile_min, bytes));
+                S->tile_min_cap = bytes;
+            }
+            CU(cudaMemsetAsync(S->tile_min, 0x7f, bytes, M->stream));
+            S->tile_min_on = true;
+        }
+    }
     M->spans.clear(); M->ev_used = 0;
     M->last = {};
     // k_score (per-node scores, fallback) indexes one bitmap per group: no shared scans then

@@ -5,24 +5,26 @@
 // range of whole 32-node blocks whose mutations are ONE contiguous piece of the stream, [seed segments][block
 // segments].  A CTA holds kUnits UNITS of 1 + NC warps; a unit works on one tile at a time:
 //
-//   scanner warp   pulls the tile's stream through a 4 KB shared-memory ring of 512 B rows (16-byte cp.async per
-//                  lane per row) in STEPS of 4 rows that are aligned to the tile, not to its segments: every word
-//                  is loaded and tested exactly once against the scan group's UNION bitmap (per word: byte offset
-//                  of the bitmap word, LDS, a wrap shift and a funnel shift collecting the hit bits).  The hit
-//                  bits of a step are then handed out segment by segment: masked to the segment's quads,
+//   scanner warp   pulls the tile's stream through a 4 KB shared-memory ring of two 2 KB stages: a STEP = 4 rows of
+//                  128 words = ONE bulk async copy (TMA unit, cp.async.bulk, completion on the stage's mbarrier)
+//                  issued by an elected lane a whole step ahead.  Steps are aligned to the tile, not to its segments:
+//                  every word is loaded and tested exactly once against the scan group's UNION bitmap (per word:
+//                  byte offset of the bitmap word, LDS, a wrap shift and a funnel shift collecting the hit bits).
+//                  The hit bits of a step are then handed out segment by segment: masked to the segment's quads,
 //                  compacted with two ballots and copied into one of eight 64-word message slots that all NC
-//                  consumers read (full barrier: 1 arrival, empty barrier: NC arrivals).  A segment = one or more
-//                  messages, the last one flagged.  The scanner needs no sample state.
+//                  consumers read (full barrier: 1 arrival, empty barrier: NC arrivals).  Sparse single-group steps
+//                  re-read the few hit words from the ring; shared scans and dense steps store them from the
+//                  registers they were tested in, into the slots used as one circular buffer.  A segment = one or
+//                  more messages, the last one flagged.  The scanner needs no sample state.
 //   consumer warp  owns the state of ONE group of 32 samples.  Per block:
 //     rec            16-byte block record fetched a block ahead (min(G - nmut), open-chain mask and level): the 32
 //                    node headers are only read for blocks that can still hold an optimum
 //     C  lane = hit  table row of the position (32 B, L2; two rows per lane in flight).  Rows whose sample mask is
-//                    empty belong to another group of the scan group and are dropped.  Sparse messages apply the
-//                    (hit, sample) pairs straight from the lanes; dense ones (any lane with more than two pairs)
-//                    first EXPAND the pairs into a shared-memory list and then apply them lane = pair, so that a
-//                    position called by many samples does not serialise the warp: packed (dcorr, da, dcommon)
+//                    empty belong to another group of the scan group and are dropped.  Per 32 hits, by cost: the
+//                    SPARSE form (lane = hit walks the samples that call its position: packed (dcorr, da, dcommon)
 //                    from a 1024-entry LUT, shared-memory atomics into dnode[node][sample], neg[sample] +=
-//                    min(dcorr, 0)
+//                    min(dcorr, 0)) or the DENSE form (32 x 32 bit transpose with 5 shuffles, then lane = SAMPLE
+//                    walks its own hits, owns its dnode column: no atomics, no bank conflicts, neg in a register)
 //     bound          exact lower bound of every pair of the block:  min(G - nmut) + gmin + neg  against the running
 //                    best; blocks that cannot hold an optimum skip E and F entirely
 //     E  lane = node     non-hit pairs of a sample that can still improve or tie
@@ -38,8 +40,7 @@
 
 namespace ub200 {
 
-constexpr uint32_t kRingRows4 = 8;                         // rows of 128 words (512 B)
-constexpr uint32_t kRingWords4 = kRingRows4 * 128;         // 1024 words = 4 KB
+constexpr uint32_t kRingWords4 = 1024;                     // two stages of one step (4 rows of 128 words) = 4 KB
 constexpr uint32_t kSlots4 = 8, kSlotCap4 = 64;            // scanner -> consumer messages
 constexpr uint32_t kAreaWords4 = 192;                      // per-consumer scratch (dense-form staging: 160, header copies: 160)
 constexpr uint32_t kLut4Bytes = 4096;
@@ -99,6 +100,9 @@ struct Score4Params {
     uint32_t* set_out;
     const unsigned long long* set_ptr;
     uint32_t* set_fill;
+    int32_t* tile_min;            // [groups of the batch][T][32] or NULL.  MODE 0 leaves in it the smallest score a
+                                  // sample's candidates reached inside a tile; MODE 1 then only scans the tiles whose
+                                  // minimum equals the sample's final best (every optimal node was such a candidate)
     const int32_t* base;          // MODE 2: per sample, the calls that already disagree with the bare reference
     int32_t* node_scores;         // MODE 2: [n_samples][n_nodes]
     uint32_t* tile_counter;
@@ -129,12 +133,6 @@ __device__ __forceinline__ uint4 lds128_4(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -429,8 +427,21 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         auto fetch_tile = [&]() -> TileMeta {
             TileMeta m;
             uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(p.tile_counter + sg, 1u);
-            m.t = __shfl_sync(FULL, t, 0);
+            for (;;) {
+                if (lane == 0) t = atomicAdd(p.tile_counter + sg, 1u);
+                m.t = __shfl_sync(FULL, t, 0);
+                if (!COLLECT || !p.tile_min || m.t >= p.n_tiles) break;
+                // collect pass: does any sample of this scan's groups have a candidate at its final best in this tile?
+                bool want = false;
+                for (uint32_t c = 0; c < (uint32_t)NC; c++) {
+                    const uint32_t lg = sg * NC + c;
+                    if (lg >= p.ngroups) break;
+                    const uint32_t smp = (p.group0 + lg) * 32u + lane;
+                    if (smp < p.n_samples)
+                        want |= p.tile_min[((size_t)(p.group0 + lg) * p.n_tiles + m.t) * 32u + lane] == p.target_rel[smp];
+                }
+                if (__any_sync(FULL, want)) break;
+            }
             const uint32_t tt = min(m.t, p.n_tiles - 1u);
             m.n0 = p.tile_start[tt]; m.n1 = p.tile_start[tt + 1];
             m.lvl0 = p.tile_lvl[tt]; m.sseg = p.tile_sseg[tt];
@@ -476,8 +487,11 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 // the next step's copy goes out first (into the stage read one step ago), then wait for this step's
                 stage_load(gstep + 1u, (base >> 7) + 4u);
                 stage_a = mring_a + (gstep & 1u) * 2048u;
-                mbar_wait(bars_a + 8 * (kBarStage + (gstep & 1u)), (gstep >> 1) & 1u);
-                gstep++;
+                // (a tile without any mutation has no rows: its empty segments still take one pass through this loop)
+                if ((base >> 7) < rows_end) {
+                    mbar_wait(bars_a + 8 * (kBarStage + (gstep & 1u)), (gstep >> 1) & 1u);
+                    gstep++;
+                }
                 PROF_ADD(3, tl);
                 const uint32_t idx = base + 4u * lane;
                 uint32_t acc = 0;                                  // hit bits enter at bit 31, oldest ends lowest
@@ -551,6 +565,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         int bsc = COLLECT ? (live ? p.target_rel[sample] : (int)0x80000000) : 0x7fffffff;
         unsigned long long bkey = ~0ull;
         uint32_t cnt = 0;
+        int32_t* tmin_row = nullptr;   // MODE 0: this group's row of tile_min for the current tile
         auto merge = [&](int sc, uint32_t hu, uint32_t node) {
             if (COLLECT) {
                 if (sc == bsc) {
@@ -564,6 +579,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 ((unsigned long long)(uint32_t)(sc + kScoreBias) << 33) | ((unsigned long long)tiekey << 1) | hu;
             if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
             else if (sc == bsc) { cnt++; if (key < bkey) bkey = key; }
+            if (tmin_row) atomicMin(tmin_row + lane, sc);   // candidates are rare: a few per tile and sample
         };
         int negr = 0;   // this lane's (= sample's) share of neg accumulated by the dense form of C
         auto zero_dnode = [&]() {
@@ -680,6 +696,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             }
             const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
             const uint32_t lvl0 = p.tile_lvl[t];
+            if (MODE == kMode4Best && p.tile_min) tmin_row = p.tile_min + ((size_t)ggroup * p.n_tiles + t) * 32u;
             // block records: one 16-byte word per block (same address for every lane), fetched one block ahead
             const uint4* recp = p.blk_rec + (n0 >> 5);
             uint4 rnext = __ldg(recp);

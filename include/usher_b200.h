@@ -175,6 +175,21 @@ int ub200_multi_place_batch(ub200_multi* multi, uint32_t n_samples, const uint64
                             const ub200_mutation* sample_calls, uint32_t flags, ub200_placement* out,
                             int32_t* node_scores, uint32_t* best_set, uint64_t* best_set_ptr, uint64_t best_set_cap);
 
+/* ---- Fitch-Sankoff per VCF site: the parsimony assignment that builds a MAT from a tree and a VCF (replaces
+ * mapper_body::operator(), reference src/usher_mapper.cpp:6-161, driven by the tbb::flow graph of
+ * src/mutation_annotated_tree.cpp:2099-2179).  Nodes are given in the order of Tree::breadth_first_expansion()
+ * (parent_bfs[0] == -1).  A site = its reference base (0..3 = A,C,G,T) and the genotype overrides of tree nodes:
+ * var_node (BFS index) / var_nuc (4-bit allele set, 15 = N); leaves without an override carry the reference allele.
+ * Output: one record per (site, node) whose assigned state differs from its parent's (the root's parent state is the
+ * reference allele): out_states = parent state << 4 | state, both 0..3.  Records come in no particular order.
+ * Returns UB200_E_CAPACITY (with *out_count = the number needed) when out_cap is too small. */
+typedef struct ub200_fs_tree ub200_fs_tree;
+int ub200_fs_tree_create(uint32_t n_nodes, const int32_t* parent_bfs, int device, ub200_fs_tree** out);
+void ub200_fs_tree_destroy(ub200_fs_tree* tree);
+int ub200_fs_sites(ub200_fs_tree* tree, uint32_t n_sites, const uint8_t* ref_code, const uint64_t* var_ptr,
+                   const uint32_t* var_node, const uint8_t* var_nuc, uint64_t out_cap, uint32_t* out_site,
+                   uint32_t* out_node, uint8_t* out_states, uint64_t* out_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,17 +1,18 @@
 set -x
-timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_cli.py -m gpu -x -q > gpurun_out/t_tests.log 2>&1
-tail -n 4 gpurun_out/t_tests.log
-python - <<'PY'
-import sys, time
-sys.path.insert(0, ".")
-from usher_b200 import capi
-s = capi.Synth(10_000_000, 30.0, 30000, 0, 20260929)
-m = capi.Mat.from_flat_struct(s.flat)
-for fam in (0, 1, 2):
-    sp, sc, _ = s.samples(256, fam, 11)
-    S = m.upload(sp, sc)
-    for flags in (0, 2):
-        S.place(flags); t = time.time(); S.place(flags); S.place(flags); dt = (time.time() - t) / 2
-        print(f"c4 fam={fam} flags={flags}: {dt*1e3:.1f} ms per 256 samples -> {256/dt:.0f} placements/s", flush=True)
-    S.close()
-PY
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --durations=5 > gpurun_out/u_tests.log 2>&1
+tail -n 12 gpurun_out/u_tests.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/u_bench_n1.json 2> gpurun_out/u_bench_n1.log
+head -c 1200 gpurun_out/u_bench_n1.json; echo
+grep "extra\|spot check" gpurun_out/u_bench_n1.log | cut -c1-260
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/u_bench_ref.json 2> gpurun_out/u_bench_ref.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/u_launch_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c4_b32 python scripts/one_launch.py c4 0 32 32 2 1 > gpurun_out/u_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c4_b96 python scripts/one_launch.py c4 0 96 96 2 3 > gpurun_out/u_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c3_b256 python scripts/one_launch.py c3 1 256 256 2 0 > gpurun_out/u_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_score4 -s 1 -c 1 -f -o gpurun_out/r02_k4_c4_leaf python scripts/one_launch.py c4 1 32 32 2 1 > gpurun_out/u_ncu4.log 2>&1
+for tool in memcheck synccheck racecheck; do
+  UB200_MIN_TILE=300 timeout 900 compute-sanitizer --tool $tool python scripts/sanitize_small.py > gpurun_out/r_san_$tool.log 2>&1
+  tail -n 2 gpurun_out/r_san_$tool.log
+done
+python scripts/seq_check.py 2000000 100 2>&1 | tail -4 > gpurun_out/u_seq.log; cat gpurun_out/u_seq.log

@@ -80,3 +80,86 @@ def test_reference_score_nodes_matches_golden(path):
         u = {int(a): int(b) for a, b in zip(nodes, (valid >> 1) & 1)}
         assert [u[int(a)] for a in g["exp_best_set"][lo:hi]] == g["exp_best_set_unique"][lo:hi].tolist()
     rt.close()
+
+
+def _random_fs_case(seed, n_leaves, n_sites, p_amb=0.1):
+    """A random multifurcating tree (newick with named leaves) and per-site leaf genotypes; returns the tree in BFS order
+    plus the VCF text the reference reads."""
+    rng = np.random.default_rng(seed)
+    kids = {0: []}
+    nxt = 1
+    frontier = [0]
+    leaves = []
+    while len(leaves) + len(frontier) < n_leaves:
+        u = frontier.pop(int(rng.integers(len(frontier))))
+        for _ in range(int(rng.integers(2, 5))):
+            kids[u].append(nxt); kids[nxt] = []; frontier.append(nxt); nxt += 1
+    leaves = sorted(v for v in kids if not kids[v])
+    name = {v: f"s{v}" for v in leaves}
+
+    def nwk(u):
+        return name[u] if not kids[u] else "(" + ",".join(nwk(c) for c in kids[u]) + ")"
+    newick = nwk(0) + ";"
+    # BFS order
+    order, q = [], [0]
+    while q:
+        u = q.pop(0); order.append(u); q.extend(kids[u])
+    idx = {v: i for i, v in enumerate(order)}
+    parent_bfs = np.array([-1] + [idx[next(p for p in kids if v in kids[p])] for v in order[1:]], np.int32)
+    nuc = "NACMGRSVTWYHKDBN"
+    ref_code, var_ptr, var_node, var_nuc, rows = [], [0], [], [], []
+    for s in range(n_sites):
+        ref = int(rng.integers(4))
+        gts = {}
+        for v in leaves:
+            r = rng.random()
+            if r < 0.25:
+                a = 1 << int(rng.integers(4))
+                if rng.random() < p_amb:
+                    a |= 1 << int(rng.integers(4))
+                if rng.random() < 0.05:
+                    a = 15
+                if a != (1 << ref):
+                    gts[v] = a
+        alts = sorted(set(gts.values()))
+        if not alts:
+            continue
+        ref_code.append(ref)
+        for v in leaves:
+            if v in gts:
+                var_node.append(idx[v]); var_nuc.append(gts[v])
+        var_ptr.append(len(var_node))
+        rows.append("\t".join(["c", str(10 * s + 1), ".", nuc[1 << ref], ",".join(nuc[a] for a in alts), ".", ".", ".", "GT"] +
+                              [str(1 + alts.index(gts[v])) if v in gts else "0" for v in leaves]))
+    vcf = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(name[v] for v in leaves) + "\n" + "\n".join(rows) + "\n"
+    return newick, vcf, parent_bfs, np.array(ref_code, np.uint8), np.array(var_ptr, np.uint64), np.array(var_node, np.uint32), np.array(var_nuc, np.uint8)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(4))
+def test_fitch_sankoff_oracle_matches_reference(seed, tmp_path):
+    """oracle/fitch_sankoff.py against the reference's own mapper_body: a MAT built by oracle/_ref from a random newick +
+    VCF (no condensing) carries exactly the mutations the restatement assigns, node by node."""
+    from oracle import fitch_sankoff
+    newick, vcf, parent_bfs, ref_code, var_ptr, var_node, var_nuc = _random_fs_case(700 + seed, [6, 20, 60, 150][seed], 40)
+    (tmp_path / "t.nh").write_text(newick)
+    (tmp_path / "v.vcf").write_text(vcf)
+    rt = ref.RefTree.from_newick_vcf(str(tmp_path / "t.nh"), str(tmp_path / "v.vcf"), False, 1)
+    parent, row_ptr, muts, names = rt.export()      # DFS order
+    rt.close()
+    site, node, par, st = fitch_sankoff.assign(parent_bfs, ref_code, var_ptr, var_node, var_nuc)
+    # BFS index -> DFS index through the structure: rebuild the BFS order of the exported tree
+    n = len(parent)
+    kids = [[] for _ in range(n)]
+    for i in range(1, n):
+        kids[parent[i]].append(i)
+    bfs, q = [], [0]
+    while q:
+        u = q.pop(0); bfs.append(u); q.extend(kids[u])
+    assert len(bfs) == len(parent_bfs)
+    positions = sorted(set(int(p) for p in muts["position"]))
+    got = sorted((int(muts[k]["position"]), i, int(muts[k]["par_nuc"]), int(muts[k]["mut_nuc"])) for i in range(n)
+                 for k in range(int(row_ptr[i]), int(row_ptr[i + 1])))
+    site_pos = [int(l.split("\t")[1]) for l in vcf.splitlines() if not l.startswith("#")]
+    exp = sorted((site_pos[int(s)], bfs[int(v)], 1 << int(a), 1 << int(b)) for s, v, a, b in zip(site, node, par, st))
+    assert got == exp

@@ -67,6 +67,7 @@ EXPORTS = [
     "ub200_samples_upload", "ub200_samples_free", "ub200_place_resident", "ub200_results_download",
     "ub200_results_device_ptr", "ub200_node_scores_download", "ub200_best_set_download", "ub200_mat_set_stream",
     "ub200_mat_synchronize", "ub200_last_timing", "ub200_results_copy_device", "ub200_mat_set_scan_sharing",
+    "ub200_fs_tree_create", "ub200_fs_tree_destroy", "ub200_fs_sites",
     "ub200_multi_create", "ub200_multi_destroy", "ub200_multi_size", "ub200_multi_mat", "ub200_multi_place_batch",
 ]
 
@@ -106,6 +107,10 @@ def lib():
         L.ub200_multi_mat.argtypes = [vp, C.c_int]
         L.ub200_multi_mat.restype = vp
         L.ub200_multi_place_batch.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, u64]
+        L.ub200_fs_tree_create.argtypes = [u32, vp, C.c_int, C.POINTER(vp)]
+        L.ub200_fs_tree_destroy.argtypes = [vp]
+        L.ub200_fs_tree_destroy.restype = None
+        L.ub200_fs_sites.argtypes = [vp, u32, vp, vp, vp, vp, u64, vp, vp, vp, C.POINTER(u64)]
         L.ub200_debug_derive.argtypes = [C.POINTER(FlatMat), u32, u32, C.POINTER(vp), C.POINTER(DerivedView),
                                          C.c_char_p, C.c_size_t]
         L.ub200_debug_derive_free.argtypes = [vp]
@@ -324,6 +329,35 @@ class MultiMat:
         if self.h:
             lib().ub200_multi_destroy(self.h)
             self.h = None
+
+
+def fitch_sankoff(parent_bfs, ref_code, var_ptr, var_node, var_nuc, device=0):
+    """ub200_fs_*: per-site parsimony assignment on a tree given in BFS order.  Returns (site, node, par_state, state)
+    arrays sorted by (site, node)."""
+    parent_bfs = np.ascontiguousarray(parent_bfs, dtype=np.int32)
+    ref_code = np.ascontiguousarray(ref_code, dtype=np.uint8)
+    var_ptr = np.ascontiguousarray(var_ptr, dtype=np.uint64)
+    var_node = np.ascontiguousarray(var_node, dtype=np.uint32)
+    var_nuc = np.ascontiguousarray(var_nuc, dtype=np.uint8)
+    h = C.c_void_p()
+    _check(lib().ub200_fs_tree_create(len(parent_bfs), _p(parent_bfs), device, C.byref(h)))
+    try:
+        cap = max(1024, 4 * len(var_node))
+        while True:
+            o_site, o_node, o_st = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.uint8)
+            cnt = C.c_uint64()
+            rc = lib().ub200_fs_sites(h, len(ref_code), _p(ref_code), _p(var_ptr), _p(var_node), _p(var_nuc), cap,
+                                      _p(o_site), _p(o_node), _p(o_st), C.byref(cnt))
+            if rc == E_CAPACITY:
+                cap = int(cnt.value) + 16
+                continue
+            _check(rc)
+            break
+    finally:
+        lib().ub200_fs_tree_destroy(h)
+    k = int(cnt.value)
+    order = np.lexsort((o_node[:k], o_site[:k]))
+    return o_site[:k][order], o_node[:k][order], (o_st[:k][order] >> 4), (o_st[:k][order] & 15)
 
 
 class Samples:

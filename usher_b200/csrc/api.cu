@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "score_kernel.cuh"
+#include "fs_kernel.cuh"
 #include "score_kernel4.cuh"
 #include "ub200_internal.h"
 #include "usher_b200.h"
@@ -977,6 +978,123 @@ int ub200_multi_place_batch(ub200_multi* X, uint32_t n_samples, const uint64_t* 
             if (sh[i].ns) memcpy(best_set + best_set_ptr[sh[i].s0], sh[i].set.data(), (size_t)sh[i].ptr[sh[i].ns] * 4);
     }
     return UB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fitch-Sankoff per VCF site (mapper_body, src/usher_mapper.cpp:6-161): building a MAT from a tree and a VCF.
+struct ub200_fs_tree {
+    int device = 0;
+    uint32_t n = 0, n_levels = 0;
+    uint32_t *level_start = nullptr, *parent = nullptr, *child_start = nullptr, *n_children = nullptr;
+    uint8_t* scratch = nullptr;
+    uint32_t grid = 0;
+    cudaStream_t stream = nullptr;
+};
+
+void ub200_fs_tree_destroy(ub200_fs_tree* F) {
+    if (!F) return;
+    cudaSetDevice(F->device);
+    cudaFree(F->level_start); cudaFree(F->parent); cudaFree(F->child_start); cudaFree(F->n_children); cudaFree(F->scratch);
+    if (F->stream) cudaStreamDestroy(F->stream);
+    delete F;
+}
+
+int ub200_fs_tree_create(uint32_t n_nodes, const int32_t* parent_bfs, int device, ub200_fs_tree** out) {
+    if (!parent_bfs || !out || n_nodes == 0) return fail(UB200_E_ARG, "ub200_fs_tree_create: bad argument");
+    *out = nullptr;
+    const int ndev = ub200_device_count();
+    if (ndev <= 0) return fail(UB200_E_NO_DEVICE, "ub200_fs_tree_create: no CUDA device");
+    if (device < 0 || device >= ndev) return fail(UB200_E_ARG, "ub200_fs_tree_create: bad device ordinal");
+    // BFS order: parents before children, levels non-decreasing, the children of a node contiguous
+    std::vector<uint32_t> level(n_nodes, 0), par(n_nodes, 0), cstart(n_nodes, 0), nch(n_nodes, 0), lstart;
+    if (parent_bfs[0] != -1) return fail(UB200_E_TREE_ORDER, "fs tree: node 0 must be the root");
+    lstart.push_back(0);
+    for (uint32_t i = 1; i < n_nodes; i++) {
+        const int32_t p = parent_bfs[i];
+        if (p < 0 || (uint32_t)p >= i) return fail(UB200_E_TREE_ORDER, "fs tree: parent is not an earlier node");
+        par[i] = (uint32_t)p;
+        level[i] = level[p] + 1;
+        if (level[i] < level[i - 1] || p < parent_bfs[i - 1]) return fail(UB200_E_TREE_ORDER, "fs tree: nodes are not in BFS order");
+        if (level[i] != level[i - 1]) lstart.push_back(i);
+        if (nch[p]++ == 0) cstart[p] = i;
+    }
+    lstart.push_back(n_nodes);
+    auto* F = new ub200_fs_tree();
+    F->device = device; F->n = n_nodes; F->n_levels = (uint32_t)lstart.size() - 1;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete F;
+        return fail(1, "ub200_fs_tree_create: cannot use the device");
+    }
+    // one CTA per site in flight; scratch = 2 bytes per node and CTA, at most ~2 GB
+    const uint64_t per = 2ull * n_nodes;
+    F->grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)prop.multiProcessorCount * 2, ((uint64_t)2 << 30) / per));
+    int rc = 0;
+    auto guard = [&](int r) { if (r && !rc) rc = r; };
+    if (cudaStreamCreateWithFlags(&F->stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(1, "cudaStreamCreate failed");
+    if (!rc) {
+        guard(dev_upload(&F->level_start, lstart.data(), lstart.size(), F->stream));
+        guard(dev_upload(&F->parent, par.data(), par.size(), F->stream));
+        guard(dev_upload(&F->child_start, cstart.data(), cstart.size(), F->stream));
+        guard(dev_upload(&F->n_children, nch.data(), nch.size(), F->stream));
+        if (!rc && cudaMalloc((void**)&F->scratch, per * F->grid) != cudaSuccess) rc = fail(1, "cudaMalloc scratch failed");
+        if (!rc && cudaStreamSynchronize(F->stream) != cudaSuccess) rc = fail(1, "fs tree upload failed");
+    }
+    if (rc) { ub200_fs_tree_destroy(F); return rc; }
+    *out = F;
+    return UB200_OK;
+}
+
+int ub200_fs_sites(ub200_fs_tree* F, uint32_t n_sites, const uint8_t* ref_code, const uint64_t* var_ptr,
+                   const uint32_t* var_node, const uint8_t* var_nuc, uint64_t out_cap, uint32_t* out_site,
+                   uint32_t* out_node, uint8_t* out_states, uint64_t* out_count) {
+    if (!F || !ref_code || !var_ptr || !out_count) return fail(UB200_E_ARG, "ub200_fs_sites: NULL argument");
+    *out_count = 0;
+    if (n_sites == 0) return UB200_OK;
+    const uint64_t nv = var_ptr[n_sites];
+    if (nv && (!var_node || !var_nuc)) return fail(UB200_E_ARG, "ub200_fs_sites: NULL genotype arrays");
+    for (uint32_t s = 0; s < n_sites; s++)
+        if (ref_code[s] > 3 || var_ptr[s + 1] < var_ptr[s]) return fail(UB200_E_ARG, "ub200_fs_sites: bad site " + std::to_string(s));
+    for (uint64_t k = 0; k < nv; k++)
+        if (var_node[k] >= F->n || var_nuc[k] == 0 || var_nuc[k] > 15) return fail(UB200_E_ARG, "ub200_fs_sites: bad genotype entry");
+    CU(cudaSetDevice(F->device));
+    uint8_t *d_ref = nullptr, *d_nuc = nullptr, *d_ostates = nullptr;
+    unsigned long long *d_ptr = nullptr, *d_count = nullptr;
+    uint32_t *d_node = nullptr, *d_osite = nullptr, *d_onode = nullptr;
+    int rc = 0;
+    auto guard = [&](int r) { if (r && !rc) rc = r; };
+    guard(dev_upload(&d_ref, ref_code, n_sites, F->stream));
+    guard(dev_upload(&d_ptr, reinterpret_cast<const unsigned long long*>(var_ptr), (size_t)n_sites + 1, F->stream));
+    guard(dev_upload(&d_node, var_node, nv, F->stream));
+    guard(dev_upload(&d_nuc, var_nuc, nv, F->stream));
+    auto dmalloc = [&](void** q, size_t bytes) { if (!rc && cudaMalloc(q, std::max<size_t>(bytes, 16)) != cudaSuccess) rc = fail(1, "cudaMalloc failed"); };
+    dmalloc((void**)&d_osite, out_cap * 4); dmalloc((void**)&d_onode, out_cap * 4); dmalloc((void**)&d_ostates, out_cap);
+    dmalloc((void**)&d_count, 8);
+    if (!rc) {
+        cudaMemsetAsync(d_count, 0, 8, F->stream);
+        ub200::FsParams p;
+        p.n_nodes = F->n; p.n_levels = F->n_levels; p.n_sites = n_sites;
+        p.level_start = F->level_start; p.parent = F->parent; p.child_start = F->child_start; p.n_children = F->n_children;
+        p.ref_code = d_ref; p.var_ptr = d_ptr; p.var_node = d_node; p.var_nuc = d_nuc; p.scratch = F->scratch;
+        p.out_cap = out_cap; p.out_site = d_osite; p.out_node = d_onode; p.out_states = d_ostates; p.out_count = d_count;
+        const uint32_t threads = F->n >= 4096 ? 1024u : (F->n >= 512 ? 256u : 64u);
+        ub200::k_fitch_sankoff<<<std::min(F->grid, n_sites), threads, 0, F->stream>>>(p);
+        unsigned long long cnt = 0;
+        cudaError_t e = cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, F->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(F->stream);
+        if (e != cudaSuccess) rc = fail((int)e, std::string("k_fitch_sankoff: ") + cudaGetErrorString(e));
+        *out_count = cnt;
+        if (!rc && cnt > out_cap) rc = fail(UB200_E_CAPACITY, "ub200_fs_sites: output capacity too small: need " + std::to_string(cnt));
+        if (!rc && cnt) {
+            cudaMemcpyAsync(out_site, d_osite, cnt * 4, cudaMemcpyDeviceToHost, F->stream);
+            cudaMemcpyAsync(out_node, d_onode, cnt * 4, cudaMemcpyDeviceToHost, F->stream);
+            cudaMemcpyAsync(out_states, d_ostates, cnt, cudaMemcpyDeviceToHost, F->stream);
+            if (cudaStreamSynchronize(F->stream) != cudaSuccess) rc = fail(1, "ub200_fs_sites: download failed");
+        }
+    }
+    cudaFree(d_ref); cudaFree(d_ptr); cudaFree(d_node); cudaFree(d_nuc); cudaFree(d_osite); cudaFree(d_onode);
+    cudaFree(d_ostates); cudaFree(d_count);
+    return rc;
 }
 
 }  // extern "C"

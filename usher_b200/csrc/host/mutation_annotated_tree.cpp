@@ -2,6 +2,7 @@
 // cited per function); the code is an independent implementation.
 #include "mutation_annotated_tree.hpp"
 #include "flat_mat.hpp"
+#include "usher_b200.h"
 
 #include <zlib.h>
 
@@ -924,8 +925,12 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
     bool header = false;
     std::vector<std::string> ids;
     std::vector<long> col_node;      // BFS index of the column's sample, or -(1+k) for missing sample k
-    std::vector<std::array<int, 4>> score(bfs.size());
-    std::vector<int8_t> state(bfs.size());
+    // Sites are parsed first; the assignment itself runs on the GPU (ub200_fs_*, one CTA per site) when a device is
+    // there, else with the serial restatement below (UB200_FS_HOST=1 forces it).
+    struct Site { int pos; int8_t ref; std::string chrom; size_t v0, v1; };
+    std::vector<Site> sites;
+    std::vector<uint32_t> var_node;
+    std::vector<uint8_t> var_nuc;
     while (std::getline(in, line)) {
         std::vector<std::string> w;
         string_split(line, w);
@@ -949,17 +954,14 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
             fprintf(stderr, "ERROR! Incorrect VCF format.\n");
             exit(1);
         }
-        const int pos = std::stoi(w[1]);
-        const int8_t ref = get_nuc_id(w[3][0]);
-        const int ref_nt = get_nt(ref);
+        Site st;
+        st.pos = std::stoi(w[1]);
+        st.ref = get_nuc_id(w[3][0]);
+        st.chrom = w[0];
+        st.v0 = var_node.size();
         std::vector<std::string> alleles;
         string_split(w[4], ',', alleles);
-        fprintf(stderr, "At variant site %i\n", pos);
-        // leaves: reference allele free, everything else "impossible" (:33-44); internal nodes start at 0
-        for (size_t i = 0; i < bfs.size(); i++) {
-            for (int j = 0; j < 4; j++) score[i][j] = (is_leaf[i] && j != ref_nt) ? big : 0;
-            state[i] = 0;
-        }
+        fprintf(stderr, "At variant site %i\n", st.pos);
         for (size_t c = 0; c < ids.size(); c++) {
             const std::string& gt = w[9 + c];
             int8_t nuc;
@@ -971,18 +973,81 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
                 nuc = 15;
             }
             if (col_node[c] >= 0) {
-                for (int j = 0; j < 4; j++) score[(size_t)col_node[c]][j] = (nuc & (1 << j)) ? 0 : big;
+                var_node.push_back((uint32_t)col_node[c]);
+                var_nuc.push_back((uint8_t)nuc);
             } else {
                 Mutation m;
                 m.chrom = w[0];
-                m.position = pos;
-                m.ref_nuc = ref;
-                m.par_nuc = ref;   // the reference leaves par_nuc unset here (:65-82); scoring never reads it
+                m.position = st.pos;
+                m.ref_nuc = st.ref;
+                m.par_nuc = st.ref;   // the reference leaves par_nuc unset here (:65-82); scoring never reads it
                 m.is_missing = (nuc == 15);
                 m.mut_nuc = nuc;
                 missing_samples[(size_t)(-col_node[c] - 1)].mutations.push_back(m);
             }
         }
+        st.v1 = var_node.size();
+        sites.push_back(st);
+    }
+    auto add = [&](const Site& st, size_t node, int par_state, int state) {
+        Mutation m;
+        m.chrom = st.chrom;
+        m.position = st.pos;
+        m.ref_nuc = st.ref;
+        m.par_nuc = (int8_t)(1 << par_state);
+        m.mut_nuc = (int8_t)(1 << state);
+        bfs[node]->add_mutation(m);
+    };
+    const bool on_gpu = ub200_device_count() > 0 && !getenv("UB200_FS_HOST");
+    if (on_gpu) {
+        fprintf(stderr, "Fitch-Sankoff on the GPU: %zu sites x %zu nodes\n", sites.size(), bfs.size());
+        std::vector<int32_t> par(bfs.size());
+        for (size_t i = 0; i < bfs.size(); i++) par[i] = parent_idx[i] == (size_t)-1 ? -1 : (int32_t)parent_idx[i];
+        ub200_fs_tree* F = nullptr;
+        if (ub200_fs_tree_create((uint32_t)bfs.size(), par.data(), 0, &F) != UB200_OK) {
+            fprintf(stderr, "ERROR: %s\n", ub200_last_error());
+            exit(1);
+        }
+        const size_t kBatch = 4096;
+        for (size_t s0 = 0; s0 < sites.size(); s0 += kBatch) {
+            const size_t ns = std::min(kBatch, sites.size() - s0);
+            std::vector<uint8_t> refc(ns);
+            std::vector<uint64_t> ptr(ns + 1);
+            for (size_t k = 0; k < ns; k++) { refc[k] = (uint8_t)get_nt(sites[s0 + k].ref); ptr[k] = sites[s0 + k].v0 - sites[s0].v0; }
+            ptr[ns] = sites[s0 + ns - 1].v1 - sites[s0].v0;
+            std::vector<uint32_t> o_site, o_node;
+            std::vector<uint8_t> o_st;
+            uint64_t cap = std::max<uint64_t>(4096, 2 * ptr[ns]), cnt = 0;
+            for (;;) {
+                o_site.resize(cap); o_node.resize(cap); o_st.resize(cap);
+                const int rc = ub200_fs_sites(F, (uint32_t)ns, refc.data(), ptr.data(), var_node.data() + sites[s0].v0,
+                                              var_nuc.data() + sites[s0].v0, cap, o_site.data(), o_node.data(), o_st.data(), &cnt);
+                if (rc == UB200_E_CAPACITY) { cap = cnt + 16; continue; }
+                if (rc != UB200_OK) { fprintf(stderr, "ERROR: %s\n", ub200_last_error()); exit(1); }
+                break;
+            }
+            // mutations are added site by site, nodes in BFS order, as the reference's serial loop would
+            std::vector<size_t> ord(cnt);
+            for (size_t k = 0; k < cnt; k++) ord[k] = k;
+            std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+                return o_site[a] != o_site[b] ? o_site[a] < o_site[b] : o_node[a] < o_node[b];
+            });
+            for (size_t k : ord) add(sites[s0 + o_site[k]], o_node[k], o_st[k] >> 4, o_st[k] & 15);
+        }
+        ub200_fs_tree_destroy(F);
+        return;
+    }
+    std::vector<std::array<int, 4>> score(bfs.size());
+    std::vector<int8_t> state(bfs.size());
+    for (const Site& st : sites) {
+        const int ref_nt = get_nt(st.ref);
+        // leaves: reference allele free, everything else "impossible" (:33-44); internal nodes start at 0
+        for (size_t i = 0; i < bfs.size(); i++) {
+            for (int j = 0; j < 4; j++) score[i][j] = (is_leaf[i] && j != ref_nt) ? big : 0;
+            state[i] = 0;
+        }
+        for (size_t k = st.v0; k < st.v1; k++)
+            for (int j = 0; j < 4; j++) score[var_node[k]][j] = (var_nuc[k] & (1 << j)) ? 0 : big;
         // Sankoff forward pass: children before parents = reverse BFS (:86-111)
         for (size_t i = bfs.size(); i-- > 1;) {
             const size_t p = parent_idx[i];
@@ -995,19 +1060,11 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
         // backward pass: keep the parent's state unless another base is strictly cheaper (:114-156)
         for (size_t i = 0; i < bfs.size(); i++) {
             const int8_t par_state = parent_idx[i] == (size_t)-1 ? (int8_t)ref_nt : state[parent_idx[i]];
-            int8_t st = par_state;
+            int8_t s2 = par_state;
             int best = score[i][par_state];
-            for (int j = 0; j < 4; j++) if (score[i][j] < best) { best = score[i][j]; st = (int8_t)j; }
-            state[i] = st;
-            if (st != par_state) {
-                Mutation m;
-                m.chrom = w[0];
-                m.position = pos;
-                m.ref_nuc = ref;
-                m.par_nuc = (int8_t)(1 << par_state);
-                m.mut_nuc = (int8_t)(1 << st);
-                bfs[i]->add_mutation(m);
-            }
+            for (int j = 0; j < 4; j++) if (score[i][j] < best) { best = score[i][j]; s2 = (int8_t)j; }
+            state[i] = s2;
+            if (s2 != par_state) add(st, i, par_state, s2);
         }
     }
 }

@@ -107,10 +107,11 @@ def lib():
         L.ub200_multi_mat.argtypes = [vp, C.c_int]
         L.ub200_multi_mat.restype = vp
         L.ub200_multi_place_batch.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, u64]
-        L.ub200_fs_tree_create.argtypes = [u32, vp, C.c_int, C.POINTER(vp)]
-        L.ub200_fs_tree_destroy.argtypes = [vp]
-        L.ub200_fs_tree_destroy.restype = None
-        L.ub200_fs_sites.argtypes = [vp, u32, vp, vp, vp, vp, u64, vp, vp, vp, C.POINTER(u64)]
+        if hasattr(L, "ub200_fs_tree_create"):   # (developer A/B runs load older builds of the library)
+            L.ub200_fs_tree_create.argtypes = [u32, vp, C.c_int, C.POINTER(vp)]
+            L.ub200_fs_tree_destroy.argtypes = [vp]
+            L.ub200_fs_tree_destroy.restype = None
+            L.ub200_fs_sites.argtypes = [vp, u32, vp, vp, vp, vp, u64, vp, vp, vp, C.POINTER(u64)]
         L.ub200_debug_derive.argtypes = [C.POINTER(FlatMat), u32, u32, C.POINTER(vp), C.POINTER(DerivedView),
                                          C.c_char_p, C.c_size_t]
         L.ub200_debug_derive_free.argtypes = [vp]

@@ -260,12 +260,17 @@ int launch_score4_nc(ub200_mat* M, ub200_samples* S, const ub200::Score4Params& 
         } else {
             return fail(UB200_E_ARG, "per-node scores run one sample group per scan");
         }
-    } else if (M->d.narrow3) {
-        if (smem_bitmap) rc = mode ? go(k_score4<NC, true, kMode4Collect, true>) : go(k_score4<NC, true, kMode4Best, true>);
-        else rc = mode ? go(k_score4<NC, false, kMode4Collect, true>) : go(k_score4<NC, false, kMode4Best, true>);
     } else {
-        if (smem_bitmap) rc = mode ? go(k_score4<NC, true, kMode4Collect, false>) : go(k_score4<NC, true, kMode4Best, false>);
-        else rc = mode ? go(k_score4<NC, false, kMode4Collect, false>) : go(k_score4<NC, false, kMode4Best, false>);
+        // best placement (with the tile notes when the optimal sets follow) or the collect pass
+        const bool notes = mode == kMode4Best && p.tile_min != nullptr;
+        auto pick = [&](auto best, auto best_notes, auto collect) { return mode == kMode4Collect ? go(collect) : (notes ? go(best_notes) : go(best)); };
+        if (M->d.narrow3) {
+            if (smem_bitmap) rc = pick(k_score4<NC, true, kMode4Best, true>, k_score4<NC, true, kMode4BestNotes, true>, k_score4<NC, true, kMode4Collect, true>);
+            else rc = pick(k_score4<NC, false, kMode4Best, true>, k_score4<NC, false, kMode4BestNotes, true>, k_score4<NC, false, kMode4Collect, true>);
+        } else {
+            if (smem_bitmap) rc = pick(k_score4<NC, true, kMode4Best, false>, k_score4<NC, true, kMode4BestNotes, false>, k_score4<NC, true, kMode4Collect, false>);
+            else rc = pick(k_score4<NC, false, kMode4Best, false>, k_score4<NC, false, kMode4BestNotes, false>, k_score4<NC, false, kMode4Collect, false>);
+        }
     }
     if (rc) return rc;
     CU(cudaGetLastError());

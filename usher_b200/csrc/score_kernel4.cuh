@@ -205,11 +205,12 @@ __device__ __forceinline__ void unpack_delta4(int v, int& dcorr, int& da, int& d
 // (best_j_vec + node_has_unique); the final best score is the bound, so almost every block is pruned.  MODE 2: the
 // reported score of EVERY node (`-p`, src/usher_common.cpp:557-578: score + 1 on invalid nodes): every block is
 // evaluated, non-hit pairs are written lane = node (coalesced), hit pairs one by one.
-constexpr int kMode4Best = 0, kMode4Collect = 1, kMode4NodeScores = 2;
+constexpr int kMode4Best = 0, kMode4Collect = 1, kMode4NodeScores = 2, kMode4BestNotes = 3;   // 3 = MODE 0 + tile_min notes
 template <int NC, bool SMEM_BITMAP, int MODE, bool NARROW>
 __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Params p) {
     using C = Cfg4<NC>;
     constexpr bool COLLECT = MODE == kMode4Collect, SCORES = MODE == kMode4NodeScores;
+    constexpr bool BEST = MODE == kMode4Best || MODE == kMode4BestNotes, NOTES = MODE == kMode4BestNotes;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     // unit / role of this warp; the scanners are spread over the four SM sub-partitions (warp % 4)
@@ -430,7 +431,8 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             for (;;) {
                 if (lane == 0) t = atomicAdd(p.tile_counter + sg, 1u);
                 m.t = __shfl_sync(FULL, t, 0);
-                if (!COLLECT || !p.tile_min || m.t >= p.n_tiles) break;
+                if (!COLLECT) break;
+                if (!p.tile_min || m.t >= p.n_tiles) break;
                 // collect pass: does any sample of this scan's groups have a candidate at its final best in this tile?
                 bool want = false;
                 for (uint32_t c = 0; c < (uint32_t)NC; c++) {
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         int bsc = COLLECT ? (live ? p.target_rel[sample] : (int)0x80000000) : 0x7fffffff;
         unsigned long long bkey = ~0ull;
         uint32_t cnt = 0;
-        int32_t* tmin_row = nullptr;   // MODE 0: this group's row of tile_min for the current tile
+        uint32_t cur_t = 0;            // the tile being scored (tile_min notes)
         auto merge = [&](int sc, uint32_t hu, uint32_t node) {
             if (COLLECT) {
                 if (sc == bsc) {
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 ((unsigned long long)(uint32_t)(sc + kScoreBias) << 33) | ((unsigned long long)tiekey << 1) | hu;
             if (sc < bsc) { bsc = sc; cnt = 1; bkey = key; }
             else if (sc == bsc) { cnt++; if (key < bkey) bkey = key; }
-            if (tmin_row) atomicMin(tmin_row + lane, sc);   // candidates are rare: a few per tile and sample
+            if (NOTES) atomicMin(p.tile_min + ((size_t)ggroup * p.n_tiles + cur_t) * 32u + lane, sc);   // candidates are rare
         };
         int negr = 0;   // this lane's (= sample's) share of neg accumulated by the dense form of C
         auto zero_dnode = [&]() {
@@ -696,7 +698,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             }
             const uint32_t n0 = p.tile_start[t], n1 = p.tile_start[t + 1];
             const uint32_t lvl0 = p.tile_lvl[t];
-            if (MODE == kMode4Best && p.tile_min) tmin_row = p.tile_min + ((size_t)ggroup * p.n_tiles + t) * 32u;
+            if (NOTES) cur_t = t;
             // block records: one 16-byte word per block (same address for every lane), fetched one block ahead
             const uint4* recp = p.blk_rec + (n0 >> 5);
             uint4 rnext = __ldg(recp);
@@ -837,7 +839,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
                 __syncwarp();
             }
             // publish an improved bound for the other units working on this sample group
-            if (MODE == kMode4Best && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
+            if (BEST && live && bsc < gb) atomicMin(p.gbest + sample, bsc);
             __syncwarp();
         }
 
@@ -845,14 +847,14 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
         pc[8] = (unsigned long long)(clock64() - prof_start);
         if (lane == 0 && !dead) for (int i = 8; i < 16; i++) atomicAdd(p.prof + i, pc[i]);
 #endif
-        if (MODE == kMode4Best) {
+        if (BEST) {
             // park the consumer's result in its own rows for the fold below
             reinterpret_cast<unsigned long long*>(dnode)[lane] = bkey;
             neg[lane] = (int)cnt;
         }
     }
 
-    if (MODE != kMode4Best) return;
+    if (!BEST) return;
     // fold the CTA's units, one partial row per CTA and group: warp c folds consumer c of every unit
     __syncthreads();
     if (warp < (uint32_t)NC && sg * NC + warp < p.ngroups) {

@@ -36,12 +36,12 @@ from oracle import ref
 if ref.available():
     import tempfile
     from test_oracle import _random_fs_case
-    newick, vcf, pb, rc2, vp2, vn2, vc2 = _random_fs_case(3, 20_000, 300, p_amb=0.1)
+    newick, vcf, pb, rc2, vp2, vn2, vc2 = _random_fs_case(3, 6_000, 300, p_amb=0.1)
     d = tempfile.mkdtemp(); open(d + "/t.nh", "w").write(newick); open(d + "/v.vcf", "w").write(vcf)
     thr = len(os.sched_getaffinity(0))
     t = time.time(); rt = ref.RefTree.from_newick_vcf(d + "/t.nh", d + "/v.vcf", False, thr); tr = time.time() - t
     rt.close()
-    capi.fitch_sankoff(pb, rc2[:4], vp2[:5], vn2[:int(vp2[4])], vc2[:int(vp2[4])])
+    capi.fitch_sankoff(pb, rc2, vp2, vn2, vc2)
     t = time.time(); capi.fitch_sankoff(pb, rc2, vp2, vn2, vc2); tg = time.time() - t
     print(f"{len(pb)} nodes x {len(rc2)} sites: reference from_newick_vcf (parse + mapper_body, {thr} threads) {tr:.2f}s = {len(rc2)/tr:.0f} sites/s; "
           f"GPU assignment through the C ABI {tg*1e3:.1f} ms = {len(rc2)/tg:.0f} sites/s")

@@ -76,8 +76,14 @@ __global__ void __launch_bounds__(1024) k_fitch_sankoff(const FsParams p) {
                 const uint32_t m = m0[i];
                 const uint32_t s = ((m >> par) & 1u) ? par : (uint32_t)(__ffs((int)m) - 1);
                 st[i] = (uint8_t)s;
+                // one atomic per warp for the records of its lanes
+                const unsigned am = __activemask();
+                const unsigned em = __ballot_sync(am, s != par);
                 if (s != par) {
-                    const unsigned long long o = atomicAdd(p.out_count, 1ull);
+                    const unsigned lane = threadIdx.x & 31u, leader = (unsigned)__ffs((int)em) - 1u;
+                    unsigned long long o = 0;
+                    if (lane == leader) o = atomicAdd(p.out_count, (unsigned long long)__popc(em));
+                    o = __shfl_sync(em, o, (int)leader) + (unsigned long long)__popc(em & ((1u << lane) - 1u));
                     if (o < p.out_cap) { p.out_site[o] = site; p.out_node[o] = i; p.out_states[o] = (uint8_t)((par << 4) | s); }
                 }
             }

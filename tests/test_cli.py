@@ -183,3 +183,45 @@ def test_flat_placement_equals_no_add_run(usher, vcf, key):
         str(common.load(os.path.join(common.GOLDEN, "hostgold.npz"))["no_add__placement_stats.tsv"])
     exp = [l.split("\t")[:3] for l in exp_txt.splitlines() if l]
     assert got == exp
+
+
+def _compat_binary():
+    import shutil
+    out = os.path.join(tempfile.mkdtemp(), "compat_main")
+    host = os.path.join(build.CSRC, "host")
+    subprocess.check_call([build.HOSTCXX, "-std=c++17", "-O1", "-I", build.INC, "-I", host,
+                           os.path.join(common.HERE, "compat_main.cpp"), os.path.join(host, "mutation_annotated_tree.cpp"),
+                           "-o", out, "-L", build.PKG, "-lusher_b200", f"-Wl,-rpath,{build.PKG}", "-lz"])
+    return out
+
+
+def test_compat_adapter_compiles_against_the_mat_api(usher):
+    """include/usher_b200_compat.hpp (adapter for the matUtils / ripples callers of mapper2_body) builds against the MAT
+    API and links the C ABI."""
+    assert os.path.exists(_compat_binary())
+
+
+@pytest.mark.gpu
+def test_compat_adapter_with_dfs_tie_index(usher):
+    """The other callers pass j = DFS index (src/matUtils/annotate.cpp:629): same score, num_best and optimal set as the
+    reference's search, and the best node is the optimal node with the most leaves, then the LARGEST DFS index."""
+    exe = _compat_binary()
+    g = common.load(os.path.join(common.GOLDEN, "config1.npz"))
+    r = subprocess.run([exe, PB, VCF], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    rows = [l.split("\t") for l in r.stdout.splitlines()]
+    parent = g["parent"]
+    n = len(parent)
+    nchild = np.bincount(parent[1:], minlength=n)
+    leaves = (nchild == 0).astype(np.int64)
+    for i in range(n - 1, 0, -1):
+        leaves[parent[i]] += leaves[i]
+    names = g["names"].tolist()
+    assert [x[0] for x in rows] == g["snames"].tolist()
+    for s, x in enumerate(rows):
+        lo, hi = int(g["exp_best_set_ptr"][s]), int(g["exp_best_set_ptr"][s + 1])
+        opt = g["exp_best_set"][lo:hi].astype(np.int64)
+        assert int(x[2]) == int(g["exp_score"][s]) and int(x[3]) == int(g["exp_num_best"][s])
+        assert [int(v) for v in x[6].split(",")] == opt.tolist()
+        best = max(opt.tolist(), key=lambda v: (leaves[v], v))
+        assert x[1] == names[best] and int(x[4]) == best

@@ -104,6 +104,8 @@ struct ub200_samples {
     unsigned long long* part_key = nullptr;
     uint32_t* part_cnt = nullptr;
     uint32_t part_groups = 0, part_wpg = 0;
+    size_t part_rows = 0;          // rows of 32 lanes allocated in part_key / part_cnt
+    uint32_t launch_idx = 0;       // scoring launches of the current place call (tile counter block)
     int32_t* node_scores = nullptr;
     uint32_t* set_out = nullptr;
     unsigned long long* set_ptr = nullptr;
@@ -280,7 +282,7 @@ int launch_score4_nc(ub200_mat* M, ub200_samples* S, const ub200::Score4Params& 
 // One pass: groups [group0, group0 + ngroups) of the batch, `nc` groups per scanner; bm0 = index of the pass's first
 // union bitmap.  *wpg_out = partial rows per group (CTAs per scan group) for k_reduce.
 int launch_score4(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngroups, uint32_t nc, uint32_t bm0,
-                  uint32_t* wpg_out, int mode = 0) {
+                  uint32_t* wpg_out, int mode = 0, uint32_t part_stride = 0) {
     using namespace ub200;
     Score4Params p;
     p.stream = M->mstream; p.hdr = M->hdr3; p.tiekey = M->tiekey;
@@ -294,11 +296,15 @@ int launch_score4(ub200_mat* M, ub200_samples* S, uint32_t group0, uint32_t ngro
     p.gstack = M->gstack3; p.gstack_levels = M->gstack3_levels;
     p.target_rel = S->best_rel; p.set_out = S->set_out; p.set_ptr = S->set_ptr; p.set_fill = S->set_fill;
     p.base = S->base; p.node_scores = S->node_scores; p.tile_min = S->tile_min_on ? S->tile_min : nullptr;
-    p.tile_counter = S->tile_counter;
-    p.prof = reinterpret_cast<unsigned long long*>(S->tile_counter + 64);   // 16 counters behind the tile counters
-    CU(cudaMemsetAsync(S->tile_counter, 0, 256, M->stream));
+    // every launch of a place call takes its own block of 16 tile counters (one memset per 256 launches, not per launch)
+    if (S->launch_idx % 256u == 0) CU(cudaMemsetAsync(S->tile_counter, 0, 4096 * 4, M->stream));
+    p.tile_counter = S->tile_counter + 16u * (S->launch_idx % 256u);
+    S->launch_idx++;
+    p.prof = reinterpret_cast<unsigned long long*>(S->tile_counter + 4096);   // 16 counters behind the tile counters
     const uint32_t grid = std::max<uint32_t>(p.nsg, ((uint32_t)M->num_sms / p.nsg) * p.nsg);
     *wpg_out = grid / p.nsg;
+    p.part_group0 = part_stride ? group0 : 0u;
+    p.part_stride = part_stride ? part_stride : grid / p.nsg;
     if (nc == 1) return launch_score4_nc<1>(M, S, p, grid, mode);
     if (nc == 2) return launch_score4_nc<2>(M, S, p, grid, mode);
     return launch_score4_nc<3>(M, S, p, grid, mode);
@@ -568,19 +574,22 @@ static int samples_fill(ub200_mat* M, ub200_samples* S, uint32_t n_samples, cons
         if (!rc) rc = alloc((void**)&S->base, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->gbest, (size_t)g * 32 * 4);
         if (!rc && !S->tile_counter) {
-            rc = alloc((void**)&S->tile_counter, 256 + 128);
-            if (!rc) CU(cudaMemset(S->tile_counter, 0, 256 + 128));
+            rc = alloc((void**)&S->tile_counter, (4096 + 32) * 4);   // 256 blocks of 16 counters + 16 profile counters
+            if (!rc) CU(cudaMemset(S->tile_counter, 0, (4096 + 32) * 4));
         }
         if (!rc) rc = alloc((void**)&S->results, (size_t)g * 32 * sizeof(ub200_placement));
         if (!rc) rc = alloc((void**)&S->best_rel, (size_t)g * 32 * 4);
         if (!rc) rc = alloc((void**)&S->sample_ptr, ((size_t)g * 32 + 1) * 8);
         if (!rc) rc = alloc((void**)&S->set_ptr, ((size_t)g * 32 + 1) * 8);
         if (!rc) rc = alloc((void**)&S->set_fill, (size_t)g * 32 * 4);
-        // per-CTA partial bests of one pass: one row of 32 lanes per CTA and group it serves (up to 3), or per
-        // warp-slice of k_score
-        const size_t part_rows = (size_t)std::max<uint32_t>(M->grid, 8u) * 3u + 32u;
+        // partial bests: one row of 32 lanes per (group, CTA serving it); all groups of the batch keep their rows until
+        // ONE reduction at the end of the call (up to 256 MB; larger batches reduce pass by pass)
+        const size_t per_pass_rows = (size_t)std::max<uint32_t>(M->grid, 8u) * 3u + 32u;
+        const size_t all_rows = (size_t)g * (size_t)std::max(M->num_sms, 8);
+        const size_t part_rows = std::max(per_pass_rows, all_rows * 32 * 12 <= ((size_t)256 << 20) ? all_rows : 0);
         if (!rc) rc = alloc((void**)&S->part_key, part_rows * 32 * 8);
         if (!rc) rc = alloc((void**)&S->part_cnt, part_rows * 32 * 4);
+        S->part_rows = part_rows;
         if (rc) { S->cap_groups = 0; return rc; }
         S->cap_groups = g;
     }
@@ -669,25 +678,47 @@ static int place_resident_impl(ub200_mat* M, ub200_samples* S, uint32_t flags, i
     const uint32_t nsgpp = (NG + nc - 1) / nc;   // union bitmaps per pass
     { int rc = run_prep(M, S, NG, nc); if (rc) return rc; }
     M->last.total_launches += 5;
+    // k_score4 keeps the partial rows of every group and reduces ONCE after the last pass (one launch per distinct
+    // number of CTAs per group: the full passes, and a shorter last one)
+    const uint32_t R = (uint32_t)std::max(M->num_sms, 8);
+    const bool deferred = use_v3 && (size_t)S->n_groups * R <= S->part_rows;
+    S->launch_idx = 0;
+    auto reduce = [&](uint32_t g0, uint32_t ng, uint32_t wpg, uint32_t stride, uint32_t part_g0) -> int {
+        ub200::ReduceParams rp;
+        rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = wpg; rp.stride = stride; rp.part_group0 = part_g0;
+        rp.group0 = g0; rp.n_samples = S->n_samples; rp.base = S->base; rp.key_to_node = M->key_to_node;
+        rp.tie_index = M->tie_index; rp.num_leaves = M->num_leaves; rp.out = S->results; rp.best_rel = S->best_rel;
+        int rc = span_begin(M, 2); if (rc) return rc;
+        ub200::k_reduce<<<ng, 256, 0, M->stream>>>(rp);
+        CU(cudaGetLastError());
+        rc = span_end(M); if (rc) return rc;
+        M->last.total_launches += 1;
+        return 0;
+    };
+    uint32_t wpg_first = 0, wpg_last = 0, last_g0 = 0;
     for (uint32_t g0 = 0; g0 < S->n_groups; g0 += NG) {
         const uint32_t ng = std::min(NG, S->n_groups - g0);
         int rc = span_begin(M, 1); if (rc) return rc;
         uint32_t wpg = std::max<uint32_t>(ng, (M->grid / ng) * ng) / ng;
-        if (use_v3) rc = launch_score4(M, S, g0, ng, nc, (g0 / NG) * nsgpp, &wpg);
+        if (use_v3) rc = launch_score4(M, S, g0, ng, nc, (g0 / NG) * nsgpp, &wpg, 0, deferred ? R : 0u);
         else rc = launch_score<ub200::kModeBest>(M, S, g0, ng, smem_bitmap);
         if (rc) return rc;
         rc = span_end(M); if (rc) return rc;
-        ub200::ReduceParams rp;
-        rp.part_key = S->part_key; rp.part_cnt = S->part_cnt; rp.wpg = wpg;   // one partial row per CTA and group
-        rp.group0 = g0; rp.n_samples = S->n_samples; rp.base = S->base; rp.key_to_node = M->key_to_node;
-        rp.tie_index = M->tie_index; rp.num_leaves = M->num_leaves; rp.out = S->results; rp.best_rel = S->best_rel;
-        rc = span_begin(M, 2); if (rc) return rc;
-        ub200::k_reduce<<<ng, 256, 0, M->stream>>>(rp);
-        CU(cudaGetLastError());
-        rc = span_end(M); if (rc) return rc;
+        if (!deferred) { rc = reduce(g0, ng, wpg, wpg, 0); if (rc) return rc; }
+        if (g0 == 0) wpg_first = wpg;
+        wpg_last = wpg; last_g0 = g0;
         M->last.score_launches++;
-        M->last.total_launches += 2;
+        M->last.total_launches += 1;
         M->last.score_bytes += 4ull * M->m + 16ull * M->n;
+    }
+    if (deferred) {
+        int rc = 0;
+        if (wpg_last == wpg_first) rc = reduce(0, S->n_groups, wpg_first, R, 0);
+        else {
+            rc = reduce(0, last_g0, wpg_first, R, 0);
+            if (!rc) rc = reduce(last_g0, S->n_groups - last_g0, wpg_last, R, last_g0);
+        }
+        if (rc) return rc;
     }
     S->have_results = true;
     if (flags & UB200_WANT_NODE_SCORES) {
@@ -769,8 +800,8 @@ int ub200_debug_prof(ub200_mat* M, ub200_samples* S, unsigned long long* out16) 
     if (!M || !S || !out16) return fail(UB200_E_ARG, "ub200_debug_prof: NULL argument");
     CU(cudaSetDevice(M->device));
     CU(cudaStreamSynchronize(M->stream));
-    CU(cudaMemcpy(out16, S->tile_counter + 64, 128, cudaMemcpyDeviceToHost));
-    CU(cudaMemset(S->tile_counter + 64, 0, 128));
+    CU(cudaMemcpy(out16, S->tile_counter + 4096, 128, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(S->tile_counter + 4096, 0, 128));
     return UB200_OK;
 }
 

@@ -415,7 +415,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_score(const ScoreParams p) {
 struct ReduceParams {
     const unsigned long long* part_key;
     const uint32_t* part_cnt;
-    uint32_t wpg;
+    uint32_t wpg;          // partial rows per group
+    uint32_t stride;       // rows reserved per group (>= wpg)
+    uint32_t part_group0;  // first group's row block
     uint32_t group0;
     uint32_t n_samples;
     const int32_t* base;
@@ -431,8 +433,8 @@ __global__ void __launch_bounds__(256) k_reduce(const ReduceParams p) {
     __shared__ uint32_t scnt[8][32];
     const uint32_t lane = threadIdx.x & 31u, slice = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x;
-    const unsigned long long* pk = p.part_key + (size_t)group * p.wpg * 32u;
-    const uint32_t* pc = p.part_cnt + (size_t)group * p.wpg * 32u;
+    const unsigned long long* pk = p.part_key + (size_t)(p.part_group0 + group) * p.stride * 32u;
+    const uint32_t* pc = p.part_cnt + (size_t)(p.part_group0 + group) * p.stride * 32u;
     unsigned long long best = ~0ull;
     for (uint32_t w = slice; w < p.wpg; w += 8) best = min(best, pk[(size_t)w * 32u + lane]);
     skey[slice][lane] = best;

@@ -94,6 +94,7 @@ struct Score4Params {
     uint32_t n_samples, group0, ngroups, nsg;   // first group / number of groups / scan groups of this pass
     unsigned long long* part_key;
     uint32_t* part_cnt;
+    uint32_t part_group0, part_stride;   // partial row of (group g of the pass, CTA c) = (part_group0 + g) * part_stride + c
     int32_t* gstack;
     uint32_t gstack_levels;
     const int32_t* target_rel;
@@ -869,7 +870,7 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             if ((reinterpret_cast<const unsigned long long*>(pb + C::kODnode)[lane] >> 33) == (best >> 33))
                 c += reinterpret_cast<const uint32_t*>(pb + C::kONeg)[lane];
         }
-        const size_t o = ((size_t)(sg * NC + warp) * ctas_per_sg + cta_in_sg) * 32u + lane;
+        const size_t o = ((size_t)(p.part_group0 + sg * NC + warp) * p.part_stride + cta_in_sg) * 32u + lane;
         p.part_key[o] = best;
         p.part_cnt[o] = c;
     }

@@ -1,4 +1,3 @@
 set -x
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
-timeout 200 python bench.py --no-extra > gpurun_out/w_bench.json 2> gpurun_out/w_bench.log
-head -c 1200 gpurun_out/w_bench.json; echo; tail -n 3 gpurun_out/w_bench.log
+timeout 280 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/r_launch_bench.log 2>&1
+tail -c 300 gpurun_out/r_launch_bench.log; wc -l gpurun_out/r_launches.csv

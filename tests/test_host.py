@@ -230,3 +230,35 @@ def test_derivation_does_not_depend_on_the_host_thread_count(monkeypatch):
             assert sorted(o) == sorted(outs[0])
             for k, v in outs[0].items():
                 assert np.array_equal(np.asarray(v), np.asarray(o[k])), (seed, k)
+
+
+def test_leaf_counts_bfs_index_and_tie_order_against_a_plain_restatement(monkeypatch):
+    """num_leaves (mutation_annotated_tree.cpp:866-879), the breadth-first index (:1225-1251, children in DFS order) and
+    the tie-break rank (usher_mapper.cpp:483-486) are computed by chunks of the node range: compare them with a
+    sequential restatement, also for a caller's tie_index that repeats (equal keys keep node order)."""
+    import small_synth
+    for seed, n, shape in ((21, 1500, "uniform"), (22, 1200, "chain"), (23, 2, "uniform")):
+        parent, row_ptr, muts, _ = small_synth.random_mat(seed, n, 80, 2.0, shape=shape)
+        n = len(parent)
+        leaves = np.zeros(n, np.int64)
+        kids = [[] for _ in range(n)]
+        for i in range(1, n):
+            kids[parent[i]].append(i)
+        for i in range(n - 1, -1, -1):
+            if not kids[i]:
+                leaves[i] = 1
+            if i:
+                leaves[parent[i]] += leaves[i]
+        bfs, q = np.zeros(n, np.int64), [0]
+        for h, u in enumerate(q):
+            bfs[u] = h
+            q.extend(kids[u])
+        rep = np.random.default_rng(seed).integers(0, 5, n).astype(np.uint32)   # a tie_index with many repeats
+        for nt in (1, 4):
+            monkeypatch.setenv("UB200_HOST_THREADS", str(nt))
+            d = capi.debug_derive(parent, row_ptr, muts, target_tiles=16, min_tile_cost=64)
+            assert np.array_equal(d["num_leaves"], leaves) and np.array_equal(d["tie_index"], bfs)
+            d = capi.debug_derive(parent, row_ptr, muts, tie_index=rep, target_tiles=16, min_tile_cost=64)
+            exp = sorted(range(n), key=lambda v: (-int(leaves[v]), -int(rep[v]), v))
+            assert d["key_to_node"].tolist() == exp
+            assert np.array_equal(d["tiekey"][d["key_to_node"]], np.arange(n))

@@ -57,6 +57,32 @@ void parallel_chunks(uint32_t n, unsigned nthr, F body) {   // body(chunk, lo, h
 }
 }  // namespace
 
+// Sort the keys of one segment (bits [4, 4 + kbits) carry position and lane, unique inside a segment).  Segments are a
+// few hundred to a thousand words: an LSD radix sort with 7..8-bit digits beats a comparison sort about three times.
+static void sort_segment(std::vector<uint32_t>& seg, std::vector<uint32_t>& tmp, uint32_t kbits) {
+    const size_t m = seg.size();
+    if (m <= 48) { std::sort(seg.begin(), seg.end()); return; }
+    const uint32_t passes = (kbits + 7) / 8, dbits = (kbits + passes - 1) / passes, mask = (1u << dbits) - 1u;
+    uint32_t hist[4][256];
+    for (uint32_t p = 0; p < passes; p++) std::memset(hist[p], 0, sizeof(uint32_t) << dbits);
+    for (size_t i = 0; i < m; i++) {
+        const uint32_t k = seg[i] >> 4;
+        for (uint32_t p = 0; p < passes; p++) hist[p][(k >> (p * dbits)) & mask]++;
+    }
+    tmp.resize(m);
+    uint32_t* src = seg.data();
+    uint32_t* dst = tmp.data();
+    for (uint32_t p = 0; p < passes; p++) {
+        uint32_t* h = hist[p];
+        uint32_t run = 0;
+        for (uint32_t b = 0; b <= mask; b++) { const uint32_t c = h[b]; h[b] = run; run += c; }
+        const uint32_t sh = 4 + p * dbits;
+        for (size_t i = 0; i < m; i++) dst[h[(src[i] >> sh) & mask]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != seg.data()) seg.swap(tmp);
+}
+
 // The k_score3 layout (ub200_internal.h), built from the arrays derive() has already filled.
 static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min_tile_cost, Derived& d) {
     const uint32_t n = d.n;
@@ -65,30 +91,32 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     d.narrow3 = d.L <= kMaxPos3Narrow && !getenv("UB200_WIDE_WORDS");   // env: test hook for the wide form
     const uint32_t nblk = (n + 31) / 32;
     PhaseTimer pt;
-    // subtree ends (DFS pre-order: subtree of i = [i, send[i])), words on the root path above each node
-    std::vector<uint32_t> send(n);
-    for (uint32_t i = 0; i < n; i++) send[i] = i + 1;
-    for (uint32_t i = n; i-- > 1;) send[f.parent[i]] = std::max(send[f.parent[i]], send[i]);
-    std::vector<uint64_t> pathw(n, 0);
-    for (uint32_t i = 1; i < n; i++) {
-        const uint32_t p = (uint32_t)f.parent[i];
-        pathw[i] = pathw[p] + (d.row32[p + 1] - d.row32[p]);
-    }
-    // headers: y = in-block ancestor mask, flags + open
+    // words on the root path above a node (the seed stream of a tile that starts there)
+    auto path_words = [&](uint32_t node) {
+        uint64_t w = 0;
+        for (int32_t a = f.parent[node]; a >= 0; a = f.parent[a]) w += d.row32[a + 1] - d.row32[a];
+        return w;
+    };
+    // headers: y = in-block ancestor mask, flags + open.  A node is open when its subtree runs past its block, i.e.
+    // when it is an ancestor of the next block's first node (DFS pre-order: subtrees are contiguous).
     d.hdr3 = d.hdr;
-    {
-        std::vector<uint32_t> am(n, 0);
-        for (uint32_t i = 0; i < n; i++) {
-            if (i && (uint32_t)f.parent[i] >= (i & ~31u)) am[i] = am[f.parent[i]] | (1u << (f.parent[i] & 31));
-            NodeHdr& h = d.hdr3[i];
-            const uint32_t flags = hdr_flags(h.level_flags);
-            const bool leaf = flags & kFlagLeaf;
-            const bool open = !leaf && send[i] > (i | 31u) + 1u;
-            h.tiekey = am[i];
-            h.level_flags = (d.level[i] << kLevelShift) | flags | (open ? kFlagOpen : 0u);
+    parallel_chunks(nblk, host_threads(n), [&](unsigned, uint32_t blo, uint32_t bhi) {
+        for (uint32_t b = blo; b < bhi; b++) {
+            const uint32_t n0 = b * 32, n1 = std::min(n, n0 + 32);
+            uint32_t open = 0, am[32];
+            if (n0 + 32 < n)
+                for (int32_t a = f.parent[n0 + 32]; a >= (int32_t)n0; a = f.parent[a]) open |= 1u << (a & 31);
+            for (uint32_t i = n0; i < n1; i++) {
+                const uint32_t p = (uint32_t)f.parent[i];
+                am[i & 31] = (i && p >= n0) ? (am[p & 31] | (1u << (p & 31))) : 0u;
+                NodeHdr& h = d.hdr3[i];
+                const uint32_t flags = hdr_flags(h.level_flags);
+                h.tiekey = am[i & 31];
+                h.level_flags = (d.level[i] << kLevelShift) | flags | (((open >> (i & 31)) & 1u) ? kFlagOpen : 0u);
+            }
         }
-    }
-    pt.lap("  3: subtree ends, headers");
+    });
+    pt.lap("  3: headers");
     // tiles: whole blocks, roughly equal cost; the seed stream must stay a small fraction of the tree
     const uint64_t node_cost = 4;
     const uint64_t total = d.m + node_cost * n;
@@ -106,7 +134,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
             const uint64_t lim = seen * 10 > total * 9 ? per / 4 : (seen * 10 > total * 7 ? per / 2 : per);
             if (acc >= std::max<uint64_t>(lim, min_tile_cost ? min_tile_cost : 2048) && e < n) {
                 d.tile3_start.push_back(e);
-                seed += pathw[e];
+                seed += path_words(e);
                 acc = 0;
             }
         }
@@ -122,78 +150,123 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     d.seed_end.clear();
     d.blk_words.assign(nblk, 0);
     const bool nw = d.narrow3;
-    const uint32_t pad = pack_mut3(nw, d.L, 0, 0, 0);
-    auto conv = [&](uint32_t w, uint32_t lane) { return pack_mut3(nw, w >> 6, lane, (w >> 2) & 3u, w & 3u); };
-    const uint32_t pshift = nw ? 16 : 14;
     const bool pad_steps = !getenv("UB200_NO_STEP_PAD");   // developer switch: measure what the padding buys
-    // Every tile's piece of the stream starts on a 1 KB boundary, so the pieces are built independently (one
-    // host thread per slice of tiles) and concatenated afterwards.
-    struct Piece { std::vector<uint32_t> words; std::vector<uint32_t> seed_end4; uint64_t seed_words = 0; };
+    // Length a segment of `raw` words takes when it is appended at word `at` of its tile's piece: a multiple of 4;
+    // the kernel takes the piece in steps of 512 words (4 rows) counted from the tile's start and hands the hits of a
+    // step out segment by segment, so a segment that starts on a step boundary is padded up to the next one when that
+    // costs at most an eighth of its length: it then spans the fewest possible steps, every step it touches belongs to
+    // it alone, and the segments behind it stay aligned.
+    auto seg_len = [&](size_t at, size_t raw) {
+        size_t m = (raw + 3) & ~(size_t)3;
+        if (pad_steps && at % 512 == 0) {
+            const size_t padw = (512 - m % 512) % 512;
+            if (padw && padw * 8 <= m) m += padw;
+        }
+        return m;
+    };
+    // Every tile's piece of the stream starts on a 1 KB boundary and its length follows from the row lengths alone:
+    // pass 1 lays the pieces out (sizes, seed-segment ends, block words), pass 2 has one host thread per slice of tiles
+    // sort and write its pieces straight into the stream.
+    struct Piece { uint64_t words = 0, seed_words = 0; uint32_t nseed = 0; };
     std::vector<Piece> pieces(T);
-    auto build_tile = [&](size_t t, std::vector<uint32_t>& chain, std::vector<uint32_t>& seg) {
-        Piece& pc = pieces[t];
-        std::vector<uint32_t>& out = pc.words;
+    auto root_chain = [&](uint32_t n0, std::vector<uint32_t>& chain) {   // chain[level] = ancestor of n0 at that level
+        chain.assign(d.level[n0], 0);
+        for (int32_t a = f.parent[n0]; a >= 0; a = f.parent[a]) chain[d.level[a]] = (uint32_t)a;
+    };
+    parallel_chunks((uint32_t)T, host_threads(n), [&](unsigned, uint32_t tlo, uint32_t thi) {
+        std::vector<uint32_t> chain;
+        for (uint32_t t = tlo; t < thi; t++) {
+            const uint32_t n0 = d.tile3_start[t], n1 = d.tile3_start[t + 1], lvl0 = d.level[n0];
+            d.tile3_lvl[t] = lvl0;
+            root_chain(n0, chain);
+            size_t at = 0;
+            for (uint32_t l0 = 0; l0 < lvl0; l0 += 32) {
+                size_t raw = 0;
+                for (uint32_t l = l0; l < std::min(lvl0, l0 + 32); l++) raw += d.row32[chain[l] + 1] - d.row32[chain[l]];
+                at += seg_len(at, raw);
+                pieces[t].nseed++;
+            }
+            pieces[t].seed_words = at;
+            for (uint32_t b = n0; b < n1; b += 32) {
+                const size_t m = seg_len(at, d.row32[std::min(n1, b + 32)] - d.row32[b]);
+                d.blk_words[b >> 5] = (uint32_t)m;
+                at += m;
+            }
+            pieces[t].words = (at + kChunk3 - 1) / kChunk3 * kChunk3;
+        }
+    });
+    std::vector<uint64_t> piece_off(T + 1, 0);
+    d.seed_words = 0;
+    for (size_t t = 0; t < T; t++) {
+        piece_off[t + 1] = piece_off[t] + pieces[t].words;
+        d.tile3_w0[t] = (uint32_t)(piece_off[t] / kChunk3);
+        d.tile3_sseg[t + 1] = d.tile3_sseg[t] + pieces[t].nseed;
+        d.seed_words += pieces[t].seed_words;
+    }
+    d.tile3_w0[T] = (uint32_t)(piece_off[T] / kChunk3);
+    d.seed_end.assign((size_t)d.tile3_sseg[T] + 1, 0);   // never empty (one spare entry)
+    d.stream.resize(piece_off[T]);
+    pt.lap("  3: piece layout");
+    // sort key of a stream word: pos | lane:5 | prev:2 | mut:2 -- the order of (position, stream word)
+    uint32_t pbits = 1;
+    while ((1ull << pbits) <= d.L) pbits++;
+    const uint32_t kbits = pbits + 5;
+    const uint32_t padk = d.L << 9;
+    auto build_tile = [&](size_t t, std::vector<uint32_t>& chain, std::vector<uint32_t>& seg, std::vector<uint32_t>& tmp) {
+        uint32_t* const out = d.stream.data() + piece_off[t];
+        size_t at = 0;
         // A segment's words go out sorted by position and transposed inside every 128-word row piece: the
         // scanner reads a row with one 16-byte load per lane, so component j of the 32 lanes should hold 32
         // CONSECUTIVE sorted words -> their bitmap words are consecutive too and the 32 bitmap reads fall into
         // distinct shared-memory banks (a random order costs ~3.5 wavefronts per read).  Which node (or level) a
         // word belongs to is in the word, so the order inside a segment is free.
         auto emit_segment = [&]() {
-            std::sort(seg.begin(), seg.end(), [&](uint32_t x, uint32_t y) {
-                const uint32_t px = ((x >> pshift) << 5) | (x & 31u), py = ((y >> pshift) << 5) | (y & 31u);
-                return px != py ? px < py : x < y;
-            });
-            while (seg.size() % 4) seg.push_back(pad);
-            // The kernel takes the tile's piece in steps of 512 words (4 rows) counted from the tile's start and
-            // hands the hits of a step out segment by segment.  A segment that starts on a step boundary is padded
-            // up to the next one when that costs at most an eighth of its length: it then spans the fewest possible
-            // steps, every step it touches belongs to it alone, and the segments behind it stay aligned.
-            if (pad_steps && out.size() % 512 == 0) {
-                const size_t padw = (512 - seg.size() % 512) % 512;
-                if (padw && padw * 8 <= seg.size()) seg.resize(seg.size() + padw, pad);
-            }
+            sort_segment(seg, tmp, kbits);
+            seg.resize(seg_len(at, seg.size()), padk);
             size_t s0 = 0;
             while (s0 < seg.size()) {
-                const size_t off = out.size();
-                const size_t m = std::min<size_t>(128 - off % 128, seg.size() - s0), nl = m / 4;
-                out.resize(off + m);
-                for (size_t i = 0; i < nl; i++)
-                    for (size_t j = 0; j < 4; j++) out[off + 4 * i + j] = seg[s0 + j * nl + i];
+                const size_t m = std::min<size_t>(128 - at % 128, seg.size() - s0), nl = m / 4;
+                for (size_t j = 0; j < 4; j++) {
+                    const uint32_t* src = seg.data() + s0 + j * nl;
+                    for (size_t i = 0; i < nl; i++) {
+                        const uint32_t k = src[i];
+                        out[at + 4 * i + j] = pack_mut3(nw, k >> 9, (k >> 4) & 31u, (k >> 2) & 3u, k & 3u);
+                    }
+                }
                 s0 += m;
+                at += m;
             }
             seg.clear();
         };
+        auto take_row = [&](uint32_t node, uint32_t lane) {
+            for (uint32_t k = d.row32[node]; k < d.row32[node + 1]; k++) {
+                const uint32_t w = d.mutw[k];
+                seg.push_back(((w >> 6) << 9) | (lane << 4) | (w & 15u));
+            }
+        };
         const uint32_t n0 = d.tile3_start[t], n1 = d.tile3_start[t + 1];
         const uint32_t lvl0 = d.level[n0];
-        d.tile3_lvl[t] = lvl0;
-        chain.assign(lvl0, 0);
-        for (int32_t a = f.parent[n0]; a >= 0; a = f.parent[a]) chain[d.level[a]] = (uint32_t)a;
-        out.reserve((size_t)(d.row32[n1] - d.row32[n0]) + (size_t)(pathw[n0]) + (n1 - n0) * 3 + 1024);
+        root_chain(n0, chain);
+        uint32_t* se = d.seed_end.data() + d.tile3_sseg[t];
         for (uint32_t l0 = 0; l0 < lvl0; l0 += 32) {
-            for (uint32_t l = l0; l < std::min(lvl0, l0 + 32); l++)
-                for (uint32_t k = d.row32[chain[l]]; k < d.row32[chain[l] + 1]; k++)
-                    seg.push_back(conv(d.mutw[k], l & 31u));
+            for (uint32_t l = l0; l < std::min(lvl0, l0 + 32); l++) take_row(chain[l], l & 31u);
             emit_segment();
-            pc.seed_end4.push_back((uint32_t)(out.size() / 4));
+            *se++ = (uint32_t)((piece_off[t] + at) / 4);
         }
-        pc.seed_words = out.size();
         for (uint32_t b = n0; b < n1; b += 32) {
-            const uint32_t e = std::min(n1, b + 32);
-            const size_t s0 = out.size();
-            for (uint32_t i = b; i < e; i++)
-                for (uint32_t k = d.row32[i]; k < d.row32[i + 1]; k++) seg.push_back(conv(d.mutw[k], i & 31u));
+            for (uint32_t i = b; i < std::min(n1, b + 32); i++) take_row(i, i & 31u);
             emit_segment();
-            d.blk_words[b >> 5] = (uint32_t)(out.size() - s0);
         }
-        while (out.size() % kChunk3) out.push_back(pad);
+        const uint32_t pad = pack_mut3(nw, d.L, 0, 0, 0);
+        while (at < pieces[t].words) out[at++] = pad;
     };
     {
         unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
         if (d.m < (1u << 20)) nthr = 1;
         std::atomic<size_t> next{0};
         auto worker = [&]() {
-            std::vector<uint32_t> chain, seg;
-            for (size_t t = next.fetch_add(1); t < T; t = next.fetch_add(1)) build_tile(t, chain, seg);
+            std::vector<uint32_t> chain, seg, tmp;
+            for (size_t t = next.fetch_add(1); t < T; t = next.fetch_add(1)) build_tile(t, chain, seg, tmp);
         };
         std::vector<std::thread> pool;
         for (unsigned i = 1; i < nthr; i++) pool.emplace_back(worker);
@@ -201,47 +274,25 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         for (auto& th : pool) th.join();
     }
     pt.lap("  3: tile pieces (threads)");
-    uint64_t total_words = 0;
-    for (size_t t = 0; t < T; t++) total_words += pieces[t].words.size();
-    d.stream.resize(total_words);
-    d.seed_words = 0;
-    uint64_t w = 0;
-    std::vector<uint64_t> piece_off(T + 1, 0);
-    for (size_t t = 0; t < T; t++) {
-        Piece& pc = pieces[t];
-        piece_off[t] = w;
-        d.tile3_w0[t] = (uint32_t)(w / kChunk3);
-        for (uint32_t e4 : pc.seed_end4) d.seed_end.push_back((uint32_t)(w / 4) + e4);
-        d.tile3_sseg[t + 1] = (uint32_t)d.seed_end.size();
-        d.seed_words += pc.seed_words;
-        w += pc.words.size();
-    }
-    parallel_chunks((uint32_t)T, host_threads(total_words), [&](unsigned, uint32_t lo, uint32_t hi) {
-        for (uint32_t t = lo; t < hi; t++) {
-            Piece& pc = pieces[t];
-            std::memcpy(d.stream.data() + piece_off[t], pc.words.data(), pc.words.size() * sizeof(uint32_t));
-            std::vector<uint32_t>().swap(pc.words);
+    // ---- block records: what the consumer needs of a block that cannot hold an optimum (score_kernel4.cuh)
+    d.blk_rec.resize((size_t)nblk * 4);
+    parallel_chunks(nblk, host_threads(n), [&](unsigned, uint32_t blo, uint32_t bhi) {
+        for (uint32_t bi = blo; bi < bhi; bi++) {
+            const uint32_t b = bi * 32, e = std::min(n, b + 32);
+            int32_t omin = INT32_MAX;
+            uint32_t open = 0, lv0 = 0;
+            for (uint32_t i = b; i < e; i++) {
+                omin = std::min(omin, d.hdr3[i].g - (int32_t)(d.hdr3[i].nmut_c0 >> 16));
+                if (d.hdr3[i].level_flags & kFlagOpen) {
+                    if (!open) lv0 = d.level[i];
+                    open |= 1u << (i & 31);
+                }
+            }
+            uint32_t* r = &d.blk_rec[(size_t)bi * 4];
+            r[0] = (uint32_t)omin; r[1] = open; r[2] = lv0; r[3] = d.blk_words[bi];
         }
     });
-    d.tile3_w0[T] = (uint32_t)(w / kChunk3);
-    d.seed_end.push_back(0);   // never empty
-    pt.lap("  3: concatenate");
-    // ---- block records: what the consumer needs of a block that cannot hold an optimum (score_kernel4.cuh)
-    d.blk_rec.assign((size_t)nblk * 4, 0);
-    for (uint32_t b = 0; b < n; b += 32) {
-        const uint32_t e = std::min(n, b + 32);
-        int32_t omin = INT32_MAX;
-        uint32_t open = 0, lv0 = 0;
-        for (uint32_t i = b; i < e; i++) {
-            omin = std::min(omin, d.hdr3[i].g - (int32_t)(d.hdr3[i].nmut_c0 >> 16));
-            if (d.hdr3[i].level_flags & kFlagOpen) {
-                if (!open) lv0 = d.level[i];
-                open |= 1u << (i & 31);
-            }
-        }
-        uint32_t* r = &d.blk_rec[(size_t)(b >> 5) * 4];
-        r[0] = (uint32_t)omin; r[1] = open; r[2] = lv0; r[3] = d.blk_words[b >> 5];
-    }
+    pt.lap("  3: block records");
 }
 
 int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::string& err, uint32_t min_tile_cost) {
@@ -281,55 +332,107 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
     }
     d.max_level = *std::max_element(d.level.begin(), d.level.end());
     pt.lap("topology checks");
-    // ---- leaves, leaf counts (reverse sweep), BFS index
-    std::vector<uint32_t> nchild(n + 1, 0);
-    for (uint32_t i = 1; i < n; i++) nchild[f.parent[i] + 1]++;
-    d.num_leaves.assign(n, 0);
-    for (uint32_t i = n; i-- > 0;) {
-        if (nchild[i + 1] == 0) d.num_leaves[i] = 1;
-        if (i) d.num_leaves[f.parent[i]] += d.num_leaves[i];
+    // ---- leaves, leaf counts, BFS index (chunks of the node range in parallel)
+    // DFS pre-order: a node is a leaf iff the next node is not its child.
+    auto is_leaf = [&](uint32_t i) { return i + 1 == n || (uint32_t)f.parent[i + 1] != i; };
+    {
+        // leaf counts: a reverse sweep inside every chunk; what a chunk owes to nodes before it goes to ancestors of
+        // the chunk's first node (subtrees are contiguous), collected per ancestor level and handed up afterwards
+        const unsigned nt = host_threads(n);
+        std::vector<uint32_t> cut(nt + 1);
+        for (unsigned c = 0; c <= nt; c++) cut[c] = (uint32_t)((uint64_t)n * c / nt);
+        d.num_leaves.assign(n, 0);
+        std::vector<std::vector<std::pair<uint32_t, uint32_t>>> owed(nt);   // (level of the ancestor, leaves)
+        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            for (uint32_t i = hi; i-- > lo;) {
+                if (is_leaf(i)) d.num_leaves[i] = 1;
+                if (!i) continue;
+                const uint32_t p = (uint32_t)f.parent[i];
+                if (p >= lo) d.num_leaves[p] += d.num_leaves[i];
+                else owed[c].push_back({d.level[p], d.num_leaves[i]});
+            }
+        });
+        for (unsigned c = 1; c < nt; c++) {
+            if (owed[c].empty()) continue;
+            std::vector<uint32_t> by_level(d.level[cut[c]], 0);
+            for (auto& o : owed[c]) by_level[o.first] += o.second;
+            uint32_t run = 0;
+            for (int32_t a = f.parent[cut[c]]; a >= 0; a = f.parent[a]) {   // deepest ancestor first
+                run += by_level[d.level[a]];
+                d.num_leaves[a] += run;
+            }
+        }
     }
     d.tie_index.resize(n);
     if (f.tie_index) {
         std::memcpy(d.tie_index.data(), f.tie_index, sizeof(uint32_t) * n);
     } else {
-        std::vector<uint32_t> off(nchild);
-        for (uint32_t i = 0; i < n; i++) off[i + 1] += off[i];
-        std::vector<uint32_t> kids(n > 1 ? n - 1 : 1), fill(off.begin(), off.end() - 1);
-        for (uint32_t i = 1; i < n; i++) kids[fill[f.parent[i]]++] = i;
-        std::vector<uint32_t> q(n);
-        uint32_t head = 0, tail = 0;
-        q[tail++] = 0;
-        while (head < tail) {
-            uint32_t u = q[head];
-            d.tie_index[u] = head++;
-            for (uint32_t k = off[u]; k < off[u + 1]; k++) q[tail++] = kids[k];
-        }
+        // breadth-first index (children in DFS order): nodes of one level appear in DFS order, so the index is a
+        // stable counting sort of the nodes by level
+        const unsigned nt = host_threads(n);
+        const uint32_t nl = d.max_level + 1;
+        std::vector<std::vector<uint32_t>> cnt(nt, std::vector<uint32_t>(nl, 0));
+        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            for (uint32_t i = lo; i < hi; i++) cnt[c][d.level[i]]++;
+        });
+        uint32_t run = 0;
+        for (uint32_t l = 0; l < nl; l++)
+            for (unsigned c = 0; c < nt; c++) { const uint32_t k = cnt[c][l]; cnt[c][l] = run; run += k; }
+        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            for (uint32_t i = lo; i < hi; i++) d.tie_index[i] = cnt[c][d.level[i]]++;
+        });
     }
     pt.lap("leaves + BFS index");
-    // ---- tie-break order: preferred = more leaves, then larger j  -> tiekey 0 is the most preferred
+    // ---- tie-break order: preferred = more leaves, then larger j  -> tiekey 0 is the most preferred; equal keys (a
+    // caller's tie_index may repeat) keep node order.  A stable LSD radix sort of (~key, node) in 11-bit digits, every
+    // pass split over the host threads; digits on which all keys agree are skipped.
     {
-        std::vector<uint64_t> keys(n);
-        for (uint32_t i = 0; i < n; i++) keys[i] = ((uint64_t)d.num_leaves[i] << 32) | d.tie_index[i];
-        std::vector<uint32_t> ord(n);
-        std::iota(ord.begin(), ord.end(), 0u);
-        auto before = [&](uint32_t a, uint32_t b) { return keys[a] != keys[b] ? keys[a] > keys[b] : a < b; };
-        // sorted runs by thread, then pairwise merges (a strict total order: the result does not depend on the split)
         const unsigned nt = host_threads(n);
-        std::vector<uint32_t> cut(nt + 1);
-        for (unsigned c = 0; c <= nt; c++) cut[c] = (uint32_t)((uint64_t)n * c / nt);
-        parallel_chunks(n, nt, [&](unsigned, uint32_t lo, uint32_t hi) { std::sort(ord.begin() + lo, ord.begin() + hi, before); });
-        for (unsigned w = 1; w < nt; w *= 2) {
-            std::vector<std::thread> pool;
-            for (unsigned c = 0; c + w < nt; c += 2 * w)
-                pool.emplace_back([&, c]() {
-                    std::inplace_merge(ord.begin() + cut[c], ord.begin() + cut[c + w], ord.begin() + cut[std::min(nt, c + 2 * w)], before);
-                });
-            for (auto& th : pool) th.join();
+        std::vector<uint64_t, NoInitAlloc<uint64_t>> ka(n), kb(n);
+        std::vector<uint32_t, NoInitAlloc<uint32_t>> ia(n), ib(n);
+        std::vector<uint64_t> diff_part(nt, 0);
+        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            uint64_t df = 0;
+            const uint64_t k0 = ~(((uint64_t)d.num_leaves[0] << 32) | d.tie_index[0]);
+            for (uint32_t i = lo; i < hi; i++) {
+                ka[i] = ~(((uint64_t)d.num_leaves[i] << 32) | d.tie_index[i]);
+                ia[i] = i;
+                df |= ka[i] ^ k0;
+            }
+            diff_part[c] = df;
+        });
+        uint64_t differ = 0;   // bits on which some keys differ
+        for (uint64_t x : diff_part) differ |= x;
+        constexpr uint32_t kDigit = 11, kBuckets = 1u << kDigit;
+        std::vector<uint32_t> hist((size_t)nt * kBuckets);
+        uint64_t* ks = ka.data(); uint64_t* kd = kb.data();
+        uint32_t* is = ia.data(); uint32_t* id = ib.data();
+        for (uint32_t sh = 0; sh < 64; sh += kDigit) {
+            if (((differ >> sh) & (kBuckets - 1)) == 0) continue;
+            std::fill(hist.begin(), hist.end(), 0u);
+            parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+                uint32_t* h = &hist[(size_t)c * kBuckets];
+                for (uint32_t i = lo; i < hi; i++) h[(ks[i] >> sh) & (kBuckets - 1)]++;
+            });
+            uint32_t run = 0;
+            for (uint32_t b = 0; b < kBuckets; b++)
+                for (unsigned c = 0; c < nt; c++) { uint32_t& h = hist[(size_t)c * kBuckets + b]; const uint32_t k = h; h = run; run += k; }
+            parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+                uint32_t* h = &hist[(size_t)c * kBuckets];
+                for (uint32_t i = lo; i < hi; i++) {
+                    const uint32_t at = h[(ks[i] >> sh) & (kBuckets - 1)]++;
+                    kd[at] = ks[i];
+                    id[at] = is[i];
+                }
+            });
+            std::swap(ks, kd);
+            std::swap(is, id);
         }
         d.tiekey.resize(n);
-        d.key_to_node = ord;
-        for (uint32_t r = 0; r < n; r++) d.tiekey[ord[r]] = r;
+        d.key_to_node.resize(n);
+        parallel_chunks(n, nt, [&](unsigned, uint32_t lo, uint32_t hi) {
+            for (uint32_t r = lo; r < hi; r++) { d.key_to_node[r] = is[r]; d.tiekey[is[r]] = r; }
+        });
     }
     pt.lap("tie-break rank (sort)");
     // ---- mutation checks, genome extent (chunks of nodes in parallel; the first error in node order is reported)
@@ -415,7 +518,8 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
     d.row32.assign((size_t)n + 1, 0);
     for (uint32_t i = 0; i < n; i++) d.row32[i + 1] = d.row32[i] + row_kept_of[i];
     std::vector<uint32_t>().swap(row_kept_of);
-    d.mutw.assign(((kept + kMutChunk - 1) / kMutChunk + 1) * kMutChunk, 0);
+    d.mutw.resize(((kept + kMutChunk - 1) / kMutChunk + 1) * kMutChunk);   // not zero-filled: every row is written below
+    std::fill(d.mutw.begin() + kept, d.mutw.end(), 0u);
     d.hdr.assign(((size_t)n + kHdrChunk - 1) / kHdrChunk * kHdrChunk + kHdrChunk, NodeHdr{0, 0, 0, 0});
     std::vector<int32_t> dref(n, 0);
     {
@@ -431,7 +535,7 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
             if (lo >= hi) return;
             std::vector<uint8_t> state(d.L, 0);  // 0 = never mutated on the current path, else one-hot
             struct Undo { uint32_t node; uint32_t pos; uint8_t old; };
-            std::vector<Undo> undo;
+            std::vector<Undo> undo;              // rows of the ancestors above the chunk only
             std::vector<uint32_t> path;
             std::vector<int32_t> dref_anc;       // Dref of the ancestors of `lo`, by level
             // root path of the chunk's first node, root first
@@ -454,13 +558,18 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
                 while (!path.empty() && (int32_t)path.back() != f.parent[i]) {
                     uint32_t top = path.back();
                     path.pop_back();
-                    while (!undo.empty() && undo.back().node == top) {
-                        state[undo.back().pos] = undo.back().old;
-                        undo.pop_back();
+                    if (top >= lo) {   // a row this chunk wrote: put back the state above it (ref allele = never mutated)
+                        for (uint64_t k = d.row32[top]; k < d.row32[top + 1]; k++)
+                            state[d.mutw[k] >> 6] = (uint8_t)(1u << ((d.mutw[k] >> 2) & 3u));
+                    } else {
+                        while (!undo.empty() && undo.back().node == top) {
+                            state[undo.back().pos] = undo.back().old;
+                            undo.pop_back();
+                        }
                     }
                 }
                 const bool is_root = (i == 0);
-                const bool leaf = nchild[i + 1] == 0;
+                const bool leaf = is_leaf(i);
                 bool masked = false;
                 int32_t dd = 0, a0 = 0;
                 uint32_t c0 = 0, nm = 0;
@@ -475,7 +584,6 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
                     if (!rm) { c0++; a0 += rp; }   // LOOP 1 for an absent position: common iff back to ref (:244-259)
                     d.mutw[w++] = pack_mut(pos, (uint32_t)nuc_code(m.ref_nuc), (uint32_t)nuc_code(prev),
                                            (uint32_t)nuc_code(m.mut_nuc));
-                    undo.push_back({i, pos, state[pos]});
                     state[pos] = m.mut_nuc;
                     nm++;
                 }

@@ -91,7 +91,7 @@ struct Derived {
     uint32_t max_row = 0;    // longest unmasked mutation row
     std::vector<uint32_t> level, tie_index, num_leaves, tiekey, key_to_node;
     std::vector<uint32_t> row32;      // [n+1] offsets into mutw
-    std::vector<uint32_t> mutw;       // padded to kMutChunk
+    StreamVec mutw;                   // padded to kMutChunk
     std::vector<NodeHdr> hdr;         // padded to kHdrChunk
     std::vector<uint8_t> ref_of;      // [L] one-hot reference allele where the tree mutates, else 0
     // tiles = contiguous DFS ranges; anc = root..parent chain of each tile's first node

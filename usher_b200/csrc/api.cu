@@ -450,7 +450,7 @@ static int mat_upload(std::shared_ptr<ub200::Derived> dp, int device, ub200_mat*
 
 static void drop_streamed_host_arrays(ub200::Derived& d) {
     ub200::StreamVec().swap(d.stream);
-    std::vector<ub200::NodeHdr>().swap(d.hdr3);
+    ub200::RawVec<ub200::NodeHdr>().swap(d.hdr3);
 }
 
 int ub200_mat_create(const ub200_flat_mat* flat, int device, ub200_mat** out) {

@@ -99,7 +99,8 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
     };
     // headers: y = in-block ancestor mask, flags + open.  A node is open when its subtree runs past its block, i.e.
     // when it is an ancestor of the next block's first node (DFS pre-order: subtrees are contiguous).
-    d.hdr3 = d.hdr;
+    d.hdr3.resize(d.hdr.size());
+    std::copy(d.hdr.begin() + n, d.hdr.end(), d.hdr3.begin() + n);   // the zero padding
     parallel_chunks(nblk, host_threads(n), [&](unsigned, uint32_t blo, uint32_t bhi) {
         for (uint32_t b = blo; b < bhi; b++) {
             const uint32_t n0 = b * 32, n1 = std::min(n, n0 + 32);
@@ -110,6 +111,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
                 const uint32_t p = (uint32_t)f.parent[i];
                 am[i & 31] = (i && p >= n0) ? (am[p & 31] | (1u << (p & 31))) : 0u;
                 NodeHdr& h = d.hdr3[i];
+                h = d.hdr[i];
                 const uint32_t flags = hdr_flags(h.level_flags);
                 h.tiekey = am[i & 31];
                 h.level_flags = (d.level[i] << kLevelShift) | flags | (((open >> (i & 31)) & 1u) ? kFlagOpen : 0u);
@@ -308,26 +310,43 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
     }
     PhaseTimer pt;
     d.n = n;
-    // ---- topology checks: DFS pre-order <=> parent[i] lies on the root path of node i-1
-    d.level.assign(n, 0);
+    // ---- topology checks: DFS pre-order <=> parent[i] lies on the root path of node i-1.  Chunks of the node range
+    // in parallel: a chunk starts from the root path of the node before it, rebuilt by walking the parents (safe once
+    // every parent is known to be an earlier node); the first error in node order is the one reported.
+    d.level.resize(n);
+    d.level[0] = 0;
     if (f.parent[0] != -1) { err = "flat MAT: node 0 must be the root (parent -1)"; return UB200_E_TREE_ORDER; }
     {
-        std::vector<uint32_t> path;
-        path.push_back(0);
-        for (uint32_t i = 1; i < n; i++) {
-            int32_t p = f.parent[i];
-            if (p < 0 || (uint32_t)p >= i) {
-                err = "flat MAT: parent[" + std::to_string(i) + "] is not an earlier node";
-                return UB200_E_TREE_ORDER;
+        const unsigned nt = host_threads(n);
+        std::vector<uint32_t> first_bad(nt, n);
+        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            for (uint32_t i = std::max(lo, 1u); i < hi; i++)
+                if (f.parent[i] < 0 || (uint32_t)f.parent[i] >= i) { first_bad[c] = i; break; }
+        });
+        const uint32_t bad_parent = *std::min_element(first_bad.begin(), first_bad.end());
+        struct Bad { uint32_t node; int rc; const char* what; };
+        std::vector<Bad> bad(nt, Bad{n, 0, nullptr});
+        parallel_chunks(bad_parent, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {   // nodes before the first bad parent
+            std::vector<uint32_t> path;
+            if (lo == 0) { path.push_back(0); lo = 1; }
+            else {
+                for (int32_t a = (int32_t)lo - 1; a >= 0; a = f.parent[a]) path.push_back((uint32_t)a);
+                std::reverse(path.begin(), path.end());
             }
-            while (!path.empty() && path.back() != (uint32_t)p) path.pop_back();
-            if (path.empty()) {
-                err = "flat MAT: nodes are not in DFS pre-order at node " + std::to_string(i);
-                return UB200_E_TREE_ORDER;
+            for (uint32_t i = lo; i < hi; i++) {
+                const uint32_t p = (uint32_t)f.parent[i];
+                while (!path.empty() && path.back() != p) path.pop_back();
+                if (path.empty()) { bad[c] = Bad{i, UB200_E_TREE_ORDER, "flat MAT: nodes are not in DFS pre-order at node "}; return; }
+                d.level[i] = (uint32_t)path.size();   // = level of the parent + 1
+                if (d.level[i] > kMaxLevel) { bad[c] = Bad{i, UB200_E_LIMIT, "flat MAT: tree deeper than 2^18-1 at node "}; return; }
+                path.push_back(i);
             }
-            d.level[i] = d.level[p] + 1;
-            if (d.level[i] > kMaxLevel) { err = "flat MAT: tree deeper than 2^18-1"; return UB200_E_LIMIT; }
-            path.push_back(i);
+        });
+        for (const Bad& x : bad)
+            if (x.rc) { err = x.what + std::to_string(x.node); return x.rc; }
+        if (bad_parent < n) {
+            err = "flat MAT: parent[" + std::to_string(bad_parent) + "] is not an earlier node";
+            return UB200_E_TREE_ORDER;
         }
     }
     d.max_level = *std::max_element(d.level.begin(), d.level.end());
@@ -441,39 +460,60 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
     std::vector<uint32_t> row_kept_of(n);
     {
         const unsigned nt = host_threads(f.n_mutations + n);
-        struct Part { int64_t maxpos = 0; uint64_t kept = 0; uint32_t max_row = 0; int rc = 0; std::string err; };
+        // ref = the chunk's own view of the reference allele per position (grown on demand): one pass over the mutations
+        // checks them, and the views are merged afterwards -- positions whose mutations disagree fail either way
+        struct Part { int64_t maxpos = 0, bad_ref = -1; uint64_t kept = 0; uint32_t max_row = 0; int rc = 0; std::string err; std::vector<uint8_t> ref; };
         std::vector<Part> part(nt);
         parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
+            // running values live in locals (the byte stores into the reference view would otherwise force every field
+            // of the shared record to be re-read per mutation); one-hot test: exactly one of the low four bits
             Part& P = part[c];
             auto bad = [&](int rc, std::string msg) { P.rc = rc; P.err = std::move(msg); };
+            std::vector<uint8_t> ref;
+            uint8_t* rp = nullptr;
+            size_t rn = 0;
+            int64_t maxp = 0, bad_ref = -1;
+            uint64_t kept_c = 0;
+            uint32_t max_row = 0;
+            auto one_hot = [](uint8_t x) { return x && x < 16 && !(x & (x - 1)); };
             for (uint32_t i = lo; i < hi && !P.rc; i++) {
-                if (f.row_ptr[i + 1] < f.row_ptr[i]) { bad(UB200_E_ARG, "flat MAT: row_ptr not monotone"); break; }
+                const uint64_t k0 = f.row_ptr[i], k1 = f.row_ptr[i + 1];
+                if (k1 < k0 || k1 > f.n_mutations) { bad(UB200_E_ARG, "flat MAT: row_ptr not monotone"); break; }
                 int32_t last = INT32_MIN;
-                uint64_t row_kept = 0;
-                for (uint64_t k = f.row_ptr[i]; k < f.row_ptr[i + 1]; k++) {
-                    const ub200_mutation& m = f.mutations[k];
-                    if (m.position < last) { bad(UB200_E_POSITION, "flat MAT: row " + std::to_string(i) + " is not position-sorted"); break; }
-                    if (m.position >= 0 && m.position == last) {
+                uint32_t row_kept = 0;
+                for (uint64_t k = k0; k < k1; k++) {
+                    const ub200_mutation m = f.mutations[k];
+                    const int32_t pos = m.position;
+                    if (pos < last) { bad(UB200_E_POSITION, "flat MAT: row " + std::to_string(i) + " is not position-sorted"); break; }
+                    if (pos >= 0 && pos == last) {
                         bad(UB200_E_POSITION, "flat MAT: row " + std::to_string(i) + " repeats position " + std::to_string(last));
                         break;
                     }
-                    last = m.position;
-                    if (m.position < 0) continue;
-                    if ((uint32_t)m.position > kMaxPos) { bad(UB200_E_POSITION, "flat MAT: position >= 2^26-1"); break; }
-                    if (nuc_code(m.mut_nuc) < 0 || nuc_code(m.ref_nuc) < 0) {
-                        bad(UB200_E_NOT_ONE_HOT, "flat MAT: node " + std::to_string(i) + " position " + std::to_string(m.position) +
+                    last = pos;
+                    if (pos < 0) continue;
+                    if ((uint32_t)pos > kMaxPos) { bad(UB200_E_POSITION, "flat MAT: position >= 2^26-1"); break; }
+                    if (!one_hot(m.mut_nuc) || !one_hot(m.ref_nuc)) {
+                        bad(UB200_E_NOT_ONE_HOT, "flat MAT: node " + std::to_string(i) + " position " + std::to_string(pos) +
                                                      " has a non-one-hot ref/mut nucleotide");
                         break;
                     }
-                    P.maxpos = std::max<int64_t>(P.maxpos, m.position);
+                    if ((size_t)pos >= rn) {
+                        ref.resize(std::max<size_t>((size_t)pos + 1, rn * 2), 0);
+                        rp = ref.data(); rn = ref.size();
+                    }
+                    const uint8_t r = rp[pos];
+                    if (!r) rp[pos] = m.ref_nuc;
+                    else if (r != m.ref_nuc && bad_ref < 0) bad_ref = pos;
                     row_kept++;
                 }
                 if (P.rc) break;
-                P.max_row = std::max<uint32_t>(P.max_row, (uint32_t)row_kept);
+                if (last > maxp) maxp = last;   // rows are position-sorted: the last one is the row's largest
+                max_row = std::max(max_row, row_kept);
                 if (row_kept > kMaxRow) { bad(UB200_E_LIMIT, "flat MAT: a branch with more than 65534 mutations"); break; }
-                row_kept_of[i] = (uint32_t)row_kept;
-                P.kept += row_kept;
+                row_kept_of[i] = row_kept;
+                kept_c += row_kept;
             }
+            P.maxpos = maxp; P.bad_ref = bad_ref; P.kept = kept_c; P.max_row = max_row; P.ref.swap(ref);
         });
         for (auto& P : part) {
             if (P.rc) { err = P.err; return P.rc; }
@@ -481,36 +521,31 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
             kept += P.kept;
             d.max_row = std::max(d.max_row, P.max_row);
         }
+        d.L = (uint32_t)maxpos + 1;
+        d.ref_of.assign(d.L, 0);
+        int64_t bad_ref = -1;
+        for (auto& P : part)
+            if (P.bad_ref >= 0 && bad_ref < 0) bad_ref = P.bad_ref;
+        std::vector<int64_t> bad_merge(nt, -1);
+        parallel_chunks(d.L, d.L < (1u << 16) ? 1u : nt, [&](unsigned c, uint32_t plo, uint32_t phi) {   // slices of the genome
+            for (auto& P : part)
+                for (size_t pos = plo, e = std::min<size_t>(P.ref.size(), phi); pos < e; pos++) {
+                    const uint8_t v = P.ref[pos];
+                    if (!v) continue;
+                    if (!d.ref_of[pos]) d.ref_of[pos] = v;
+                    else if (d.ref_of[pos] != v && bad_merge[c] < 0) bad_merge[c] = (int64_t)pos;
+                }
+        });
+        for (int64_t b : bad_merge)
+            if (b >= 0 && bad_ref < 0) bad_ref = b;
+        if (bad_ref >= 0) {
+            err = "flat MAT: tree mutations disagree on the reference allele at position " + std::to_string(bad_ref);
+            return UB200_E_ARG;
+        }
     }
     if (kept >= (1ull << 32) - kMutChunk) { err = "flat MAT: more than 2^32 mutations"; return UB200_E_LIMIT; }
     d.m = kept;
-    d.L = (uint32_t)maxpos + 1;
-    d.ref_of.assign(d.L, 0);
     d.root_init_extra = (int32_t)(f.row_ptr[1] - f.row_ptr[0]);
-    // reference allele per position: any writer wins (relaxed byte stores; all writers agree on a consistent tree),
-    // then every mutation is checked against what was kept, so an inconsistent tree fails whoever won
-    parallel_chunks(n, host_threads(f.n_mutations), [&](unsigned, uint32_t lo, uint32_t hi) {
-        for (uint64_t k = f.row_ptr[lo]; k < f.row_ptr[hi]; k++) {
-            const ub200_mutation& m = f.mutations[k];
-            if (m.position >= 0 && __atomic_load_n(&d.ref_of[m.position], __ATOMIC_RELAXED) == 0)
-                __atomic_store_n(&d.ref_of[m.position], m.ref_nuc, __ATOMIC_RELAXED);
-        }
-    });
-    {
-        const unsigned nt = host_threads(f.n_mutations);
-        std::vector<int64_t> bad_pos(nt, -1);
-        parallel_chunks(n, nt, [&](unsigned c, uint32_t lo, uint32_t hi) {
-            for (uint64_t k = f.row_ptr[lo]; k < f.row_ptr[hi]; k++) {
-                const ub200_mutation& m = f.mutations[k];
-                if (m.position >= 0 && d.ref_of[m.position] != m.ref_nuc) { bad_pos[c] = m.position; break; }
-            }
-        });
-        for (int64_t bp : bad_pos)
-            if (bp >= 0) {
-                err = "flat MAT: tree mutations disagree on the reference allele at position " + std::to_string(bp);
-                return UB200_E_ARG;
-            }
-    }
 
     pt.lap("mutation checks");
     // ---- path states: one DFS with a live state array per chunk of the node range.  A chunk starts from the state of
@@ -520,7 +555,8 @@ int derive(const ub200_flat_mat& f, uint32_t target_tiles, Derived& d, std::stri
     std::vector<uint32_t>().swap(row_kept_of);
     d.mutw.resize(((kept + kMutChunk - 1) / kMutChunk + 1) * kMutChunk);   // not zero-filled: every row is written below
     std::fill(d.mutw.begin() + kept, d.mutw.end(), 0u);
-    d.hdr.assign(((size_t)n + kHdrChunk - 1) / kHdrChunk * kHdrChunk + kHdrChunk, NodeHdr{0, 0, 0, 0});
+    d.hdr.resize(((size_t)n + kHdrChunk - 1) / kHdrChunk * kHdrChunk + kHdrChunk);   // rows [0, n) are written below
+    std::fill(d.hdr.begin() + n, d.hdr.end(), NodeHdr{0, 0, 0, 0});
     std::vector<int32_t> dref(n, 0);
     {
         const unsigned nt = host_threads(kept + n);

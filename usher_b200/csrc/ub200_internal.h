@@ -81,7 +81,8 @@ struct NoInitAlloc : std::allocator<T> {
         if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
     }
 };
-using StreamVec = std::vector<uint32_t, NoInitAlloc<uint32_t>>;
+template <class T> using RawVec = std::vector<T, NoInitAlloc<T>>;
+using StreamVec = RawVec<uint32_t>;
 
 struct Derived {
     uint32_t n = 0;
@@ -92,7 +93,7 @@ struct Derived {
     std::vector<uint32_t> level, tie_index, num_leaves, tiekey, key_to_node;
     std::vector<uint32_t> row32;      // [n+1] offsets into mutw
     StreamVec mutw;                   // padded to kMutChunk
-    std::vector<NodeHdr> hdr;         // padded to kHdrChunk
+    RawVec<NodeHdr> hdr;              // padded to kHdrChunk
     std::vector<uint8_t> ref_of;      // [L] one-hot reference allele where the tree mutates, else 0
     // tiles = contiguous DFS ranges; anc = root..parent chain of each tile's first node
     std::vector<uint32_t> tile_start; // [T+1]
@@ -105,7 +106,7 @@ struct Derived {
     bool have3 = false;               // false: genome too long for the 23-bit position field
     bool narrow3 = false;             // stream words in the narrow form
     StreamVec stream;                 // padded to kChunk3
-    std::vector<NodeHdr> hdr3;        // padded like hdr
+    RawVec<NodeHdr> hdr3;             // padded like hdr
     std::vector<uint32_t> tile3_start;// [T3+1] first node of each tile (multiple of 32)
     std::vector<uint32_t> tile3_w0;   // [T3+1] first stream chunk of each tile (tile t ends where t+1 starts)
     std::vector<uint32_t> tile3_lvl;  // [T3]   level of the tile's first node = number of seeded levels

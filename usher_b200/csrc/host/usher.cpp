@@ -49,6 +49,12 @@ void usage() {
         if (o.sht) fprintf(stderr, "  -%c [ --%s ]%s  %s\n", o.sht, o.lng, o.arg ? " arg" : "", o.help);
         else fprintf(stderr, "  --%s%s  %s\n", o.lng, o.arg ? " arg" : "", o.help);
     }
+    fprintf(stderr,
+            "Input restrictions of this build (the reference scores such input on the CPU, src/usher_mapper.cpp):\n"
+            "  * every VCF REF allele of a placed sample is ONE base A/C/G/T, and equals the reference allele of the\n"
+            "    tree's mutations at that position (the device keeps one reference allele per position);\n"
+            "  * a sample that breaks this makes the run stop with the sample and position named -- nothing is placed\n"
+            "    on a CPU fallback.\n");
 }
 }  // namespace
 

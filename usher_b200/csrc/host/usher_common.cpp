@@ -181,6 +181,9 @@ bool bfs_before(const MAT::Node* a, const MAT::Node* b) {
 
 void die_cuda() {
     fprintf(stderr, "ERROR: %s\n", ub200_last_error());
+    // (the device path keeps one reference allele per position: see `usher --help`, "Input restrictions")
+    fprintf(stderr, "Samples are scored in batches on the GPU; a batch with a sample the device path cannot take is refused "
+                    "as a whole.  Remove the sample named above from the VCF (or fix its REF column) and run again.\n");
     exit(1);
 }
 

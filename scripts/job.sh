@@ -1,3 +1,1 @@
-set -x
-timeout 280 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/r_launch_bench.log 2>&1
-tail -c 300 gpurun_out/r_launch_bench.log; wc -l gpurun_out/r_launches.csv
+timeout 170 python scripts/variants.py c4 0 256:32:1,1152:96:3 base acc2 nofence tw acc2_nofence_tw base 2>&1 | tee gpurun_out/x_variants.log | tail -14

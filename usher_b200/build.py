@@ -13,7 +13,11 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INC = os.path.join(ROOT, "include")
 PROFILE = bool(os.environ.get("UB200_PROFILE"))   # developer build with in-kernel cycle counters
-LIB = os.path.join(PKG, "libusher_b200_prof.so" if PROFILE else "libusher_b200.so")
+# developer A/B builds of the kernel: UB200_VARIANT="acc2,nofence" compiles with -DUB200_V_ACC2 -DUB200_V_NOFENCE into
+# libusher_b200_v_acc2_nofence.so (scripts/variants.py times them side by side)
+VARIANT = [v for v in os.environ.get("UB200_VARIANT", "").split(",") if v]
+LIB = os.path.join(PKG, "libusher_b200_prof.so" if PROFILE else
+                   ("libusher_b200_v_" + "_".join(VARIANT) + ".so" if VARIANT else "libusher_b200.so"))
 SYNTH = os.path.join(PKG, "libub200_synth.so")
 USHER = os.path.join(PKG, "usher")   # the drop-in CLI (host C++ over the C ABI)
 # The image exports CXX=/opt/gcc/bin/g++, a wrapper that links libstdc++ statically; a second libstdc++ in a
@@ -44,7 +48,7 @@ def build(force=False, verbose=False):
             _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC", "-shared", "-I", INC, "-I", CSRC,
             "-Xptxas", "-v" if verbose else "-warn-spills", "-o", LIB,
-        ] + (["-DUB200_PROFILE"] if PROFILE else []) + srcs
+        ] + (["-DUB200_PROFILE"] if PROFILE else []) + ["-DUB200_V_" + v.upper() for v in VARIANT] + srcs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
@@ -56,7 +60,7 @@ def build(force=False, verbose=False):
     hdir = os.path.join(CSRC, "host")
     hsrc = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir)) if f.endswith(".cpp")]
     hhdr = [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".hpp")]
-    if not PROFILE and (force or _stale(USHER, hsrc + hhdr + hdrs + [LIB])):
+    if not PROFILE and not VARIANT and (force or _stale(USHER, hsrc + hhdr + hdrs + [LIB])):
         subprocess.check_call([HOSTCXX, "-std=c++17", "-O2", "-I", INC, "-I", hdir] + hsrc +
                               ["-o", USHER, "-L", PKG, "-lusher_b200", "-Wl,-rpath,$ORIGIN", "-lz"])
     return LIB, SYNTH

@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
     if (role == 0) {
         // lanes past a segment's end still index the bitmap with what the ring holds: only ever valid words
         for (uint32_t i = lane; i < kRingWords4; i += 32) mring[i] = 0u;
+        // the zeros above are the only generic-proxy WRITES the ring ever sees: order them before the bulk copies once.
+        // No proxy fence per step: a stage is only re-filled after every lane has consumed what it read from it
+        // (measured: -0.8 % per launch at one group per scan, -2 % at three)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (lane == 0) {
             for (uint32_t i = 0; i < kSlots4; i++) {
                 mbar_init(bars_a + 8 * (kBarFull + i), 1);
@@ -306,7 +310,6 @@ __global__ void __launch_bounds__(Cfg4<NC>::kThreads, 1) k_score4(const Score4Pa
             __syncwarp();                                               // every lane is done reading this stage
             if (nrows && elect_one()) {
                 const uint32_t st = step_id & 1u;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(bars_a + 8 * (kBarStage + st), nrows * 512u);
                 bulk_g2s(mring_a + st * 2048u, p.stream + ((size_t)first_row << 7), nrows * 512u, bars_a + 8 * (kBarStage + st));
             }

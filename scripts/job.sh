@@ -1,1 +1,4 @@
-timeout 170 python scripts/variants.py c4 0 256:32:1,1152:96:3 base acc2 nofence tw acc2_nofence_tw base 2>&1 | tee gpurun_out/x_variants.log | tail -14
+set -x
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 200 python bench.py --no-extra > gpurun_out/y_bench.json 2> gpurun_out/y_bench.log
+head -c 1500 gpurun_out/y_bench.json; echo; grep -E "flatten|spot check|cpu" gpurun_out/y_bench.log | head -5

@@ -168,6 +168,11 @@ def test_flat_loader_round_trip_is_byte_identical(usher):
     subprocess.check_call([usher, "-i", PB, "--flat-resave", d + "/f.pb.gz"], stderr=subprocess.DEVNULL)
     subprocess.check_call([usher, "-i", d + "/f.pb.gz", "--flat-resave", d + "/g.pb"], stderr=subprocess.DEVNULL)
     assert open(d + "/g.pb", "rb").read() == open(PB, "rb").read()
+    # the mutation lists are parsed by slices of the node range on host threads: same bytes for any split
+    for nt in ("1", "3", "16"):
+        subprocess.check_call([usher, "-i", PB, "--flat-resave", d + f"/t{nt}.pb"], stderr=subprocess.DEVNULL,
+                              env=dict(os.environ, UB200_HOST_THREADS=nt))
+        assert open(d + f"/t{nt}.pb", "rb").read() == open(PB, "rb").read()
 
 
 @pytest.mark.gpu

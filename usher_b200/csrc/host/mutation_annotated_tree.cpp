@@ -4,9 +4,15 @@
 #include "flat_mat.hpp"
 #include "usher_b200.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <array>
 #include <cstdio>
 #include <cstdlib>
@@ -453,6 +459,39 @@ static bool read_all(const std::string& filename, std::string& out) {
     gzclose(f);
     return n == 0;
 }
+// The bytes of a file: an uncompressed file is mapped (a 10 M-node protobuf is > 3 GB; no copy), a gzip one inflated.
+struct FileBytes {
+    const char* data = nullptr;
+    size_t size = 0;
+    std::string owned;
+    void* map = nullptr;
+    size_t map_len = 0;
+    FileBytes() = default;
+    FileBytes(const FileBytes&) = delete;
+    FileBytes& operator=(const FileBytes&) = delete;
+    ~FileBytes() { if (map) munmap(map, map_len); }
+    bool open(const std::string& filename) {
+        int fd = ::open(filename.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        unsigned char magic[2] = {0, 0};
+        struct stat st;
+        const bool plain = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 &&
+                           !(pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b);
+        if (plain) {
+            void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                map = m; map_len = (size_t)st.st_size;
+                data = (const char*)m; size = map_len;
+                ::close(fd);
+                return true;
+            }
+        }
+        ::close(fd);
+        if (!read_all(filename, owned)) return false;
+        data = owned.data(); size = owned.size();
+        return true;
+    }
+};
 static bool write_all(const std::string& filename, const std::string& data) {
     if (filename.find(".gz") != std::string::npos) {
         gzFile f = gzopen(filename.c_str(), "wb");
@@ -518,12 +557,12 @@ inline void put_i32(std::string& o, uint32_t field, int32_t v) {   // proto3: de
 }  // namespace pb
 
 Tree load_mutation_annotated_tree(const std::string& filename) {   // reference :522-612
-    std::string raw;
-    if (!read_all(filename, raw)) {
+    FileBytes raw;
+    if (!raw.open(filename)) {
         fprintf(stderr, "ERROR: Could not load the mutation-annotated tree object from file: %s!\n", filename.c_str());
         exit(1);
     }
-    pb::Reader top(raw.data(), raw.size());
+    pb::Reader top(raw.data, raw.size);
     std::string newick;
     std::vector<pb::Reader> lists, conds, metas;
     while (top.more()) {
@@ -662,9 +701,18 @@ void save_mutation_annotated_tree(const Tree& tree, const std::string& filename)
 
 // ---------------------------------------------------------------- flat loader / saver (flat_mat.hpp)
 bool load_flat_mutation_annotated_tree(const std::string& filename, FlatTree& t, std::string& err) {
-    std::string raw;
-    if (!read_all(filename, raw)) { err = "could not read " + filename; return false; }
-    pb::Reader top(raw.data(), raw.size());
+    const bool timing = getenv("UB200_LOAD_TIMING") != nullptr;   // developer switch: phase times on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[flat load] %-24s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    FileBytes raw;
+    if (!raw.open(filename)) { err = "could not read " + filename; return false; }
+    lap("read file");
+    pb::Reader top(raw.data, raw.size);
     pb::Reader nwk(nullptr, 0);
     std::vector<pb::Reader> lists, conds, metas;
     while (top.more()) {
@@ -681,6 +729,7 @@ bool load_flat_mutation_annotated_tree(const std::string& filename, FlatTree& t,
         }
     }
     if (!top.ok) { err = filename + " is not a valid parsimony.proto message"; return false; }
+    lap("top-level fields");
     // ---- newick -> parent[] / names[]: the reference's tokeniser (split at ',', '(' opens an internal node, the
     // text before the first ':' or ')' names the leaf, ')' closes), nodes numbered as they are created
     t = FlatTree();
@@ -717,63 +766,128 @@ bool load_flat_mutation_annotated_tree(const std::string& filename, FlatTree& t,
         }
         if (!stack.empty()) { err = "incorrect Newick format"; return false; }
     }
+    lap("newick");
     const size_t n = t.parent.size();
     if (lists.size() < n) { err = "protobuf holds " + std::to_string(lists.size()) + " mutation lists for " + std::to_string(n) + " nodes"; return false; }
     t.n_children.assign(n, 0);
     for (size_t i = 1; i < n; i++) t.n_children[t.parent[i]]++;
-    // ---- mutation lists -> CSR rows
+    // ---- mutation lists -> CSR rows.  The lists are independent length-delimited fields (a 10 M-node tree is > 3 GB of
+    // varints): slices of the node range are parsed on host threads, twice -- pass 1 counts the entries every row keeps
+    // (and checks the chromosome names), pass 2 writes them straight into their place, so nothing is buffered or copied.
     t.row_ptr.assign(n + 1, 0);
-    bool chrom_set = false;
-    for (size_t i = 0; i < n; i++) {
-        pb::Reader l = lists[i];
-        const size_t row0 = t.muts.size();
-        while (l.more()) {
-            const uint64_t tag = l.varint();
-            if (!((tag >> 3) == 1 && (tag & 7) == 2)) { l.skip((uint32_t)(tag & 7)); continue; }
-            pb::Reader mr = l.sub();
-            int32_t pos = 0, refn = 0, parn = 0;
-            int8_t mut = 0;
-            const char* chrom_p = nullptr;
-            size_t chrom_n = 0;
-            while (mr.more()) {
-                const uint64_t t2 = mr.varint();
-                const uint32_t f2 = (uint32_t)(t2 >> 3), w2 = (uint32_t)(t2 & 7);
-                if (f2 == 1 && w2 == 0) pos = (int32_t)mr.varint();
-                else if (f2 == 2 && w2 == 0) refn = (int32_t)mr.varint();
-                else if (f2 == 3 && w2 == 0) parn = (int32_t)mr.varint();
-                else if (f2 == 4 && w2 == 0) mut |= (int8_t)(1 << (int)mr.varint());
-                else if (f2 == 4 && w2 == 2) { pb::Reader pk = mr.sub(); while (pk.more()) mut |= (int8_t)(1 << (int)pk.varint()); }
-                else if (f2 == 5 && w2 == 2) { pb::Reader s = mr.sub(); chrom_p = (const char*)s.p; chrom_n = (size_t)(s.end - s.p); }
-                else mr.skip(w2);
+    {
+        unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (raw.size < (1u << 20)) nt = 1;
+        if (const char* e = getenv("UB200_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));   // tests force the split
+        struct Part {
+            bool chrom_set = false, any_unnamed = false;   // any_unnamed: a mutation without a chromosome name
+            std::string chrom, err;
+        };
+        std::vector<Part> part(nt);
+        // slices of roughly equal bytes
+        std::vector<size_t> cut(nt + 1, n);
+        cut[0] = 0;
+        {
+            const uint8_t* base = n ? lists[0].p : nullptr;
+            const size_t span = n ? (size_t)(lists[n - 1].end - base) : 0;
+            size_t i = 0;
+            for (unsigned c = 1; c < nt; c++) {
+                while (i < n && (size_t)(lists[i].p - base) < span * c / nt) i++;
+                cut[c] = i;
             }
-            if (!l.ok || !mr.ok) { err = "malformed mutation list of node " + std::to_string(i); return false; }
-            if (chrom_n || chrom_set) {
-                if (!chrom_set) { t.chrom.assign(chrom_p ? chrom_p : "", chrom_n); chrom_set = true; }
-                else if (t.chrom.size() != chrom_n || (chrom_n && memcmp(t.chrom.data(), chrom_p, chrom_n) != 0)) {
-                    err = "the tree names more than one chromosome: not representable in the flat form";
-                    return false;
-                }
-            }
-            ub200_mutation m;
-            m.position = pos;
-            m.is_missing = 0;
-            if (pos >= 0) {
-                m.ref_nuc = (uint8_t)(1 << refn);
-                m.par_nuc = (uint8_t)(1 << parn);
-                m.mut_nuc = (uint8_t)mut;
-                if (m.mut_nuc == m.par_nuc) continue;   // :580: entries that change nothing are dropped
-            } else {
-                m.ref_nuc = m.par_nuc = m.mut_nuc = 0;
-            }
-            t.muts.push_back(m);
         }
-        // rows are stored position-sorted (Node::add_mutation keeps them so; masked entries first)
-        if (!std::is_sorted(t.muts.begin() + row0, t.muts.end(),
-                            [](const ub200_mutation& a, const ub200_mutation& b) { return a.position < b.position; }))
-            std::stable_sort(t.muts.begin() + row0, t.muts.end(),
-                             [](const ub200_mutation& a, const ub200_mutation& b) { return a.position < b.position; });
-        t.row_ptr[i + 1] = t.muts.size();
+        // one node's list; dst == nullptr: count only.  Returns the entries kept, or (size_t)-1 after setting P.err.
+        auto parse_list = [&](size_t i, Part& P, ub200_mutation* dst) -> size_t {
+            pb::Reader l = lists[i];
+            size_t kept = 0;
+            while (l.more()) {
+                const uint64_t tag = l.varint();
+                if (!((tag >> 3) == 1 && (tag & 7) == 2)) { l.skip((uint32_t)(tag & 7)); continue; }
+                pb::Reader mr = l.sub();
+                int32_t pos = 0, refn = 0, parn = 0;
+                int8_t mut = 0;
+                const char* chrom_p = nullptr;
+                size_t chrom_n = 0;
+                while (mr.more()) {
+                    const uint64_t t2 = mr.varint();
+                    const uint32_t f2 = (uint32_t)(t2 >> 3), w2 = (uint32_t)(t2 & 7);
+                    if (f2 == 1 && w2 == 0) pos = (int32_t)mr.varint();
+                    else if (f2 == 2 && w2 == 0) refn = (int32_t)mr.varint();
+                    else if (f2 == 3 && w2 == 0) parn = (int32_t)mr.varint();
+                    else if (f2 == 4 && w2 == 0) mut |= (int8_t)(1 << (int)mr.varint());
+                    else if (f2 == 4 && w2 == 2) { pb::Reader pk = mr.sub(); while (pk.more()) mut |= (int8_t)(1 << (int)pk.varint()); }
+                    else if (f2 == 5 && w2 == 2) { pb::Reader s = mr.sub(); chrom_p = (const char*)s.p; chrom_n = (size_t)(s.end - s.p); }
+                    else mr.skip(w2);
+                }
+                if (!l.ok || !mr.ok) { P.err = "malformed mutation list of node " + std::to_string(i); return (size_t)-1; }
+                if (!dst) {
+                    if (!chrom_n) P.any_unnamed = true;
+                    if (chrom_n || P.chrom_set) {
+                        if (!P.chrom_set) { P.chrom.assign(chrom_p ? chrom_p : "", chrom_n); P.chrom_set = true; }
+                        else if (P.chrom.size() != chrom_n || (chrom_n && memcmp(P.chrom.data(), chrom_p, chrom_n) != 0)) {
+                            P.err = "the tree names more than one chromosome: not representable in the flat form";
+                            return (size_t)-1;
+                        }
+                    }
+                }
+                ub200_mutation m;
+                m.position = pos;
+                m.is_missing = 0;
+                if (pos >= 0) {
+                    m.ref_nuc = (uint8_t)(1 << refn);
+                    m.par_nuc = (uint8_t)(1 << parn);
+                    m.mut_nuc = (uint8_t)mut;
+                    if (m.mut_nuc == m.par_nuc) continue;   // :580: entries that change nothing are dropped
+                } else {
+                    m.ref_nuc = m.par_nuc = m.mut_nuc = 0;
+                }
+                if (dst) dst[kept] = m;
+                kept++;
+            }
+            return kept;
+        };
+        auto run = [&](auto body) {
+            if (nt == 1) { body(0u); return; }
+            std::vector<std::thread> pool;
+            for (unsigned c = 0; c < nt; c++) pool.emplace_back(body, c);
+            for (auto& th : pool) th.join();
+        };
+        run([&](unsigned c) {
+            Part P;   // filled locally, published at the end: neighbouring records would share cache lines
+            for (size_t i = cut[c]; i < cut[c + 1]; i++) {
+                const size_t k = parse_list(i, P, nullptr);
+                if (k == (size_t)-1) break;
+                t.row_ptr[i + 1] = k;   // row length; offsets follow below
+            }
+            part[c] = std::move(P);
+        });
+        lap("  count (threads)");
+        bool chrom_set = false;
+        for (auto& P : part) {   // first error in node order; one chromosome name across the slices
+            if (!P.err.empty()) { err = P.err; return false; }
+            // (as in one sequential pass: once a name has been seen, every later mutation must carry the same one)
+            if (chrom_set && (P.any_unnamed || (P.chrom_set && t.chrom != P.chrom))) {
+                err = "the tree names more than one chromosome: not representable in the flat form";
+                return false;
+            }
+            if (P.chrom_set && !chrom_set) { t.chrom = P.chrom; chrom_set = true; }
+        }
+        for (size_t i = 0; i < n; i++) t.row_ptr[i + 1] += t.row_ptr[i];
+        t.muts.resize(t.row_ptr[n]);
+        lap("  offsets, resize");
+        run([&](unsigned c) {
+            Part P;
+            auto by_pos = [](const ub200_mutation& x, const ub200_mutation& y) { return x.position < y.position; };
+            for (size_t i = cut[c]; i < cut[c + 1]; i++) {
+                ub200_mutation* row = t.muts.data() + t.row_ptr[i];
+                const size_t k = parse_list(i, P, row);
+                // rows are stored position-sorted (Node::add_mutation keeps them so; masked entries first)
+                if (!std::is_sorted(row, row + k, by_pos)) std::stable_sort(row, row + k, by_pos);
+            }
+        });
+        lap("  fill (threads)");
     }
+    lap("mutation lists");
     t.have_metadata = !metas.empty();
     t.annotations.assign(n, {});
     for (size_t i = 0; i < n && i < metas.size(); i++) {
@@ -798,6 +912,7 @@ bool load_flat_mutation_annotated_tree(const std::string& filename, FlatTree& t,
         }
         t.condensed.emplace_back(std::move(name), std::move(members));
     }
+    lap("metadata, condensed");
     return true;
 }
 

@@ -58,6 +58,18 @@ def test_pb_round_trip_is_byte_identical(usher):
     assert open(d + "/re2.pb", "rb").read() == open(PB, "rb").read()
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/scripts/testBranchLen2.nwk"), reason="reference not mounted")
+def test_create_mat_mode_has_no_silent_cpu_path(usher, has_gpu):
+    """Without a CUDA device `usher -t ... -v ...` stops with an error instead of falling back to a host assignment."""
+    if has_gpu:
+        pytest.skip("a GPU is visible")
+    d = tempfile.mkdtemp()
+    env = {k: v for k, v in os.environ.items() if k != "UB200_FS_HOST"}
+    r = subprocess.run([usher, "-t", "/root/reference/scripts/testBranchLen2.nwk", "-v",
+                        "/root/reference/scripts/testBranchLen2.vcf", "--dump-flat", d + "/f.txt"], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
 def test_cli_rejects_unsupported_and_missing_arguments(usher):
     assert subprocess.run([usher], capture_output=True).returncode != 0
     assert subprocess.run([usher, "-v", VCF], capture_output=True).returncode != 0
@@ -114,8 +126,10 @@ def test_build_mat_from_newick_and_vcf_matches_reference(usher):
     """`usher -t global_phylo.nh -v global_samples.vcf -o tree.pb` (Fitch-Sankoff per site + condense + save):
     same nodes, names, mutations, newick and condensed sets as the MAT the reference builds (config 1)."""
     d = tempfile.mkdtemp()
+    # (no GPU in this test: the serial host restatement of the assignment is asked for by name; the GPU kernel has its
+    # own parity tests in test_gpu_fitch_sankoff.py)
     r = subprocess.run([usher, "-t", REF_TEST + "/global_phylo.nh", "-v", REF_TEST + "/global_samples.vcf", "-o",
-                        d + "/tree.pb", "-d", d], capture_output=True, text=True)
+                        d + "/tree.pb", "-d", d], capture_output=True, text=True, env=dict(os.environ, UB200_FS_HOST="1"))
     assert r.returncode == 0 and "The parsimony score for this tree is: 500" in r.stderr
     subprocess.check_call([usher, "-i", d + "/tree.pb", "-v", VCF, "--dump-flat", d + "/a.txt"], stderr=subprocess.DEVNULL)
     subprocess.check_call([usher, "-i", PB, "-v", VCF, "--dump-flat", d + "/b.txt"], stderr=subprocess.DEVNULL)
@@ -129,7 +143,8 @@ def test_fitch_sankoff_known_answer(usher):
     """scripts/testBranchLen2.*: the input branch lengths are the expected per-branch mutation counts."""
     d = tempfile.mkdtemp()
     subprocess.check_call([usher, "-t", "/root/reference/scripts/testBranchLen2.nwk", "-v",
-                           "/root/reference/scripts/testBranchLen2.vcf", "--dump-flat", d + "/f.txt"], stderr=subprocess.DEVNULL)
+                           "/root/reference/scripts/testBranchLen2.vcf", "--dump-flat", d + "/f.txt"], stderr=subprocess.DEVNULL,
+                          env=dict(os.environ, UB200_FS_HOST="1"))
     nwk = [l for l in open(d + "/f.txt") if l.startswith("NEWICK\t")][0].split("\t")[1].strip()
     assert nwk == "((a:0,(b:0,(c:0,d:1)node_4:1)node_3:2,((e:0,f:1)node_6:3,g:0)node_5:4)node_2:5,h:0)node_1:0;"
 

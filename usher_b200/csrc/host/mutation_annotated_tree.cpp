@@ -1040,8 +1040,8 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
     bool header = false;
     std::vector<std::string> ids;
     std::vector<long> col_node;      // BFS index of the column's sample, or -(1+k) for missing sample k
-    // Sites are parsed first; the assignment itself runs on the GPU (ub200_fs_*, one CTA per site) when a device is
-    // there, else with the serial restatement below (UB200_FS_HOST=1 forces it).
+    // Sites are parsed first; the assignment itself runs on the GPU (ub200_fs_*, one CTA per site).  The serial
+    // restatement further down only runs when UB200_FS_HOST=1 asks for it.
     struct Site { int pos; int8_t ref; std::string chrom; size_t v0, v1; };
     std::vector<Site> sites;
     std::vector<uint32_t> var_node;
@@ -1113,7 +1113,15 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
         m.mut_nuc = (int8_t)(1 << state);
         bfs[node]->add_mutation(m);
     };
-    const bool on_gpu = ub200_device_count() > 0 && !getenv("UB200_FS_HOST");
+    // No silent CPU path: without a device the run stops, unless the serial host restatement below is asked for by name
+    // (UB200_FS_HOST=1: a diagnostic, and what the CPU-only tests of the readers / condense / save around it use).
+    const bool host_asked = getenv("UB200_FS_HOST") != nullptr;
+    if (!host_asked && ub200_device_count() <= 0) {
+        fprintf(stderr, "ERROR: no CUDA device: the per-site parsimony assignment of the create-MAT mode (-t with -v) runs on "
+                        "the GPU.  (UB200_FS_HOST=1 runs the serial host restatement instead; diagnostic only.)\n");
+        exit(1);
+    }
+    const bool on_gpu = !host_asked;
     if (on_gpu) {
         fprintf(stderr, "Fitch-Sankoff on the GPU: %zu sites x %zu nodes\n", sites.size(), bfs.size());
         std::vector<int32_t> par(bfs.size());

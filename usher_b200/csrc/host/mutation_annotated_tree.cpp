@@ -1205,72 +1205,124 @@ void read_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Samp
 void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(const std::string&)>& in_tree,
                       std::vector<Missing_Sample>& missing_samples) {
     fprintf(stderr, "Loading VCF file\n");   // reference :2180-2278
-    std::string raw;
-    if (!read_all(vcf_filename, raw)) {
+    const auto t_start = std::chrono::steady_clock::now();
+    FileBytes raw;
+    if (!raw.open(vcf_filename)) {
         fprintf(stderr, "ERROR: Could not open the VCF file: %s!\n", vcf_filename.c_str());
         exit(1);
     }
-    std::istringstream in(raw);
+    // Same observable behaviour as the reference's getline + whitespace split + per-genotype Mutation objects, without
+    // materialising them: a 10 000-sample VCF holds 3e8 genotype tokens, almost all of them "0".  Tokens are (pointer,
+    // length) views of the mapped file; a Mutation is only built for a genotype that adds one.
+    struct Tok { const char* p; size_t n; };
+    auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f' || c == '\n'; };
+    auto leading_int = [](const Tok& t, const char* what) -> long {   // std::stoi on a token that starts with [+-]digits
+        size_t i = 0;
+        bool neg = false;
+        if (i < t.n && (t.p[i] == '+' || t.p[i] == '-')) neg = t.p[i++] == '-';
+        if (i >= t.n || !isdigit((unsigned char)t.p[i])) {
+            fprintf(stderr, "ERROR! Incorrect VCF format: %s '%.*s' is not a number.\n", what, (int)t.n, t.p);
+            exit(1);
+        }
+        long v = 0;
+        for (; i < t.n && isdigit((unsigned char)t.p[i]); i++) v = std::min<long>(v * 10 + (t.p[i] - '0'), 1L << 40);
+        return neg ? -v : v;
+    };
     int8_t stale_mut_nuc = 0;   // see the genotype loop below
     bool header = false;
-    std::vector<std::string> ids;
+    size_t n_ids = 0;
     std::vector<size_t> cols;
-    std::string line;
-    while (std::getline(in, line)) {
-        std::vector<std::string> w;
-        string_split(line, w);
+    std::vector<Tok> w, alleles;
+    const char* p = raw.data;
+    const char* const end = raw.data + raw.size;
+    while (p < end) {
+        const char* le = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!le) le = end;
+        w.clear();
+        for (const char* q = p; q < le;) {
+            while (q < le && is_space(*q)) q++;
+            if (q == le) break;
+            const char* a0 = q;
+            while (q < le && !is_space(*q)) q++;
+            w.push_back(Tok{a0, (size_t)(q - a0)});
+        }
+        p = le < end ? le + 1 : end;
         if (!header && w.size() > 1) {
-            if (w[1] == "POS") {
+            if (w[1].n == 3 && memcmp(w[1].p, "POS", 3) == 0) {
                 for (size_t j = 9; j < w.size(); j++) {
-                    ids.push_back(w[j]);
-                    if (!in_tree(w[j])) {
-                        missing_samples.emplace_back(Missing_Sample(w[j]));
+                    const std::string name(w[j].p, w[j].n);
+                    n_ids++;
+                    if (!in_tree(name)) {
+                        missing_samples.emplace_back(Missing_Sample(name));
                         cols.push_back(j);
                     } else {
-                        fprintf(stderr, "WARNING: Ignoring sample %s as it is already in the tree.\n", w[j].c_str());
+                        fprintf(stderr, "WARNING: Ignoring sample %s as it is already in the tree.\n", name.c_str());
                     }
                 }
                 header = true;
             }
         } else if (header) {
-            if (w.size() != 9 + ids.size()) {
-                fprintf(stderr, "ERROR! Incorrect VCF format. Expected %zu columns but got %zu.\n", 9 + ids.size(), w.size());
+            if (w.size() != 9 + n_ids) {
+                fprintf(stderr, "ERROR! Incorrect VCF format. Expected %zu columns but got %zu.\n", 9 + n_ids, w.size());
                 exit(1);
             }
-            std::vector<std::string> alleles;
-            string_split(w[4], ',', alleles);
+            // ALT alleles: split at ',' (a trailing empty piece is dropped, like the reference's string_split)
+            alleles.clear();
+            {
+                const char* a0 = w[4].p;
+                const char* const ae = w[4].p + w[4].n;
+                for (const char* q = a0; q < ae; q++)
+                    if (*q == ',') { alleles.push_back(Tok{a0, (size_t)(q - a0)}); a0 = q + 1; }
+                if (a0 < ae) alleles.push_back(Tok{a0, (size_t)(ae - a0)});
+            }
+            if (cols.empty()) continue;   // (the reference only looks at a row's fields per new sample)
+            const std::string chrom(w[0].p, w[0].n);
+            const int position = (int)leading_int(w[1], "POS");
+            const int8_t ref_nuc = get_nuc_id(w[3].p[0]);
             for (size_t k = 0; k < cols.size(); k++) {
-                const std::string& gt = w[cols[k]];
-                Mutation m;
+                const Tok& gt = w[cols[k]];
                 // The reference leaves Mutation::mut_nuc uninitialised here (src/mutation_annotated_tree.cpp:2246) and
                 // tests it for ambiguity even when the genotype is 0 (:2271); the object reuses the stack slot of the
                 // previous iteration, so num_ambiguous (the -A sort key) counts the PREVIOUS genotype's allele for
                 // reference calls.  Reproduced, since the sample order decides the final tree.
-                m.mut_nuc = stale_mut_nuc;
-                m.chrom = w[0];
-                m.position = std::stoi(w[1]);
-                m.ref_nuc = get_nuc_id(w[3][0]);
-                m.par_nuc = m.ref_nuc;
-                bool add = false;
-                if (isdigit((unsigned char)gt[0])) {
-                    const int a = std::stoi(gt);
+                int8_t mut_nuc = stale_mut_nuc;
+                bool add = false, is_missing = false;
+                if (isdigit((unsigned char)gt.p[0])) {
+                    const long a = leading_int(gt, "genotype");
                     if (a > 0) {
-                        const std::string& al = alleles.at((size_t)a - 1);   // first character only, like the reference
-                        m.mut_nuc = get_nuc_id(al[0]);
-                        m.is_missing = (al[0] == 'N') || m.mut_nuc == 15;
+                        if ((size_t)a > alleles.size()) {
+                            fprintf(stderr, "ERROR! Incorrect VCF format: genotype %ld at position %d has no ALT allele.\n", a, position);
+                            exit(1);
+                        }
+                        const Tok& al = alleles[(size_t)a - 1];
+                        const char c0 = al.n ? al.p[0] : '\0';   // first character only, like the reference
+                        mut_nuc = get_nuc_id(c0);
+                        is_missing = (c0 == 'N') || mut_nuc == 15;
                         add = true;
                     }
                 } else {
-                    m.is_missing = true;
-                    m.mut_nuc = 15;
+                    is_missing = true;
+                    mut_nuc = 15;
                     add = true;
                 }
-                if (add) missing_samples[k].mutations.push_back(m);
-                if (m.mut_nuc & (m.mut_nuc - 1)) missing_samples[k].num_ambiguous++;
-                stale_mut_nuc = m.mut_nuc;
+                if (add) {
+                    Mutation m;
+                    m.chrom = chrom;
+                    m.position = position;
+                    m.ref_nuc = ref_nuc;
+                    m.par_nuc = ref_nuc;
+                    m.mut_nuc = mut_nuc;
+                    m.is_missing = is_missing;
+                    missing_samples[k].mutations.push_back(std::move(m));
+                }
+                if (mut_nuc & (mut_nuc - 1)) missing_samples[k].num_ambiguous++;
+                stale_mut_nuc = mut_nuc;
             }
         }
     }
+    if (getenv("UB200_LOAD_TIMING"))
+        fprintf(stderr, "[vcf] %zu new samples, %.1f MB in %.1f ms\n", missing_samples.size(), raw.size / 1e6,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
 }
 
 }  // namespace Mutation_Annotated_Tree

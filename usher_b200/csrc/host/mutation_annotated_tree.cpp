@@ -117,7 +117,8 @@ Node* Tree::create_node(const std::string& id, float len, size_t num_annotations
     return n;
 }
 Node* Tree::create_node(const std::string& id, Node* par, float len) {
-    if (all_nodes.count(id)) {
+    auto ins = all_nodes.emplace(id, nullptr);   // one hash lookup for the duplicate check and the insertion
+    if (!ins.second) {
         fprintf(stderr, "Error: %s already in the tree!\n", id.c_str());
         exit(1);
     }
@@ -127,7 +128,7 @@ Node* Tree::create_node(const std::string& id, Node* par, float len) {
     n->level = par->level + 1;
     n->branch_length = len;
     n->clade_annotations.assign(get_num_annotations(), "");
-    all_nodes[id] = n;
+    ins.first->second = n;
     par->children.push_back(n);
     return n;
 }
@@ -400,20 +401,30 @@ void string_split(const std::string& s, std::vector<std::string>& words) {
 // ')' are ignored), branch lengths are parsed but never printed back.
 Tree create_tree_from_newick_string(const std::string& nwk) {
     Tree T;
-    std::vector<std::string> toks;
-    string_split(nwk, ',', toks);
+    {   // one node per ',' piece and one per '(': size the name index once
+        size_t pieces = 1;
+        for (char c : nwk) pieces += (c == ',' || c == '(');
+        T.reserve_nodes(pieces);
+    }
     std::vector<Node*> stack;
     long depth = 0;
-    for (auto& tok : toks) {
+    std::string leaf;
+    // pieces between ',' (string_split semantics: a trailing empty piece is dropped), scanned in place
+    for (size_t a = 0; a < nwk.size();) {
+        size_t b = nwk.find(',', a);
+        const bool last = b == std::string::npos;
+        if (last) b = nwk.size();
         size_t opens = 0, closes = 0;
-        std::string leaf;
+        leaf.clear();
         bool stop = false;
-        for (char c : tok) {
+        for (size_t i = a; i < b; i++) {
+            const char c = nwk[i];
             if (c == '(') opens++;
             else if (c == ')') { closes++; stop = true; }
             else if (c == ':') stop = true;
             else if (!stop) leaf += c;
         }
+        a = last ? nwk.size() : b + 1;
         for (size_t j = 0; j < opens; j++) {
             const std::string nid = T.new_internal_node_id();
             Node* nn = stack.empty() ? T.create_node(nid, -1.0f) : T.create_node(nid, stack.back(), -1.0f);
@@ -557,6 +568,14 @@ inline void put_i32(std::string& o, uint32_t field, int32_t v) {   // proto3: de
 }  // namespace pb
 
 Tree load_mutation_annotated_tree(const std::string& filename) {   // reference :522-612
+    const bool timing = getenv("UB200_LOAD_TIMING") != nullptr;   // developer switch: phase times on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pb load] %-24s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     FileBytes raw;
     if (!raw.open(filename)) {
         fprintf(stderr, "ERROR: Could not load the mutation-annotated tree object from file: %s!\n", filename.c_str());
@@ -583,8 +602,11 @@ Tree load_mutation_annotated_tree(const std::string& filename) {   // reference 
         exit(1);
     }
     if (metas.empty()) fprintf(stderr, "WARNING: This pb does not include any metadata. Filling in default values\n");
+    lap("top-level fields");
     Tree tree = create_tree_from_newick_string(newick);
+    lap("newick -> nodes");
     auto dfs = tree.depth_first_expansion();
+    lap("depth-first expansion");
     if (lists.size() < dfs.size()) {
         fprintf(stderr, "ERROR: protobuf holds %zu mutation lists for %zu nodes\n", lists.size(), dfs.size());
         exit(1);
@@ -602,12 +624,22 @@ Tree load_mutation_annotated_tree(const std::string& filename) {   // reference 
             }
         }
         pb::Reader l = lists[i];
+        {   // entries of the list (field 1, length-delimited): size the row once
+            pb::Reader c = l;
+            size_t entries = 0;
+            while (c.more()) {
+                const uint64_t tag = c.varint();
+                entries += ((tag >> 3) == 1 && (tag & 7) == 2);
+                c.skip((uint32_t)(tag & 7));
+            }
+            node->mutations.reserve(entries);
+        }
         while (l.more()) {
             const uint64_t tag = l.varint();
             if (!((tag >> 3) == 1 && (tag & 7) == 2)) { l.skip((uint32_t)(tag & 7)); continue; }
             pb::Reader mr = l.sub();
             int32_t pos = 0, refn = 0, parn = 0;
-            std::vector<int8_t> mutv;
+            int8_t mut = 0;   // get_nuc_id(vector): the sum of 1 << code over the repeated field
             Mutation m;
             while (mr.more()) {
                 const uint64_t t2 = mr.varint();
@@ -615,8 +647,8 @@ Tree load_mutation_annotated_tree(const std::string& filename) {   // reference 
                 if (f2 == 1 && w2 == 0) pos = (int32_t)mr.varint();
                 else if (f2 == 2 && w2 == 0) refn = (int32_t)mr.varint();
                 else if (f2 == 3 && w2 == 0) parn = (int32_t)mr.varint();
-                else if (f2 == 4 && w2 == 0) mutv.push_back((int8_t)mr.varint());
-                else if (f2 == 4 && w2 == 2) { pb::Reader pk = mr.sub(); while (pk.more()) mutv.push_back((int8_t)pk.varint()); }
+                else if (f2 == 4 && w2 == 0) mut = (int8_t)(mut + (1 << (int8_t)mr.varint()));
+                else if (f2 == 4 && w2 == 2) { pb::Reader pk = mr.sub(); while (pk.more()) mut = (int8_t)(mut + (1 << (int8_t)pk.varint())); }
                 else if (f2 == 5 && w2 == 2) { pb::Reader s = mr.sub(); m.chrom.assign((const char*)s.p, (size_t)(s.end - s.p)); }
                 else mr.skip(w2);
             }
@@ -624,18 +656,21 @@ Tree load_mutation_annotated_tree(const std::string& filename) {   // reference 
             if (!m.is_masked()) {
                 m.ref_nuc = (int8_t)(1 << refn);
                 m.par_nuc = (int8_t)(1 << parn);
-                m.mut_nuc = get_nuc_id(mutv);
-                if (m.mut_nuc != m.par_nuc) node->add_mutation(m);   // :580
+                m.mut_nuc = mut;
+                if (m.mut_nuc == m.par_nuc) continue;   // :580
             } else {
                 m.ref_nuc = m.par_nuc = m.mut_nuc = 0;
-                node->add_mutation(m);
             }
+            // rows are stored sorted: append without the search when the entry belongs at the end
+            if (node->mutations.empty() || node->mutations.back().position < m.position) node->mutations.push_back(std::move(m));
+            else node->add_mutation(m);
         }
         if (!std::is_sorted(node->mutations.begin(), node->mutations.end())) {
             fprintf(stderr, "WARNING: Mutations not sorted!\n");
             std::sort(node->mutations.begin(), node->mutations.end());
         }
     }
+    lap("mutation lists, metadata");
     for (auto c : conds) {
         std::string name;
         std::vector<std::string> members;

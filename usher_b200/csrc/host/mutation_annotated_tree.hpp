@@ -75,6 +75,7 @@ class Tree {
     Node* create_node(const std::string& identifier, Node* par, float branch_length = -1.0f);
     Node* create_node(const std::string& identifier, const std::string& parent_id, float branch_length = -1.0f);
     Node* get_node(const std::string& identifier) const;
+    void reserve_nodes(size_t n) { all_nodes.reserve(n); }   // (loader hint; not in the reference's API)
     std::vector<Node*> rsearch(const std::string& nid, bool include_self = false) const;
     std::string get_clade_assignment(const Node* n, int clade_id, bool include_self = true) const;
     size_t get_num_leaves(Node* node = nullptr) const;

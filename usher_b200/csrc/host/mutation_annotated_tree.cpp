@@ -989,26 +989,53 @@ bool save_flat_mutation_annotated_tree(const FlatTree& t, const std::string& fil
         pb::put_bytes(out, 1, nwk);
     }
     auto code = [](uint8_t one_hot) { return (int32_t)(31 - __builtin_clz((unsigned)one_hot)); };
-    for (size_t i = 0; i < n; i++) {
-        std::string list;
-        for (uint64_t k = t.row_ptr[i]; k < t.row_ptr[i + 1]; k++) {
-            const ub200_mutation& m = t.muts[k];
-            std::string mm;
-            pb::put_i32(mm, 1, m.position);
-            if (m.position < 0) {
-                pb::put_i32(mm, 2, -1);
-                pb::put_i32(mm, 3, -1);
-            } else {
-                pb::put_i32(mm, 2, code(m.ref_nuc));
-                pb::put_i32(mm, 3, code(m.par_nuc));
-                std::string packed;
-                for (int b = 0; b < 4; b++) if (m.mut_nuc & (1 << b)) pb::put_varint(packed, (uint64_t)b);
-                if (!packed.empty()) pb::put_bytes(mm, 4, packed);
+    {   // the per-node mutation lists are independent fields: slices of the node range are serialised on host threads
+        // into their own buffers (reused scratch strings, no allocation per mutation) and appended in order
+        unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (t.muts.size() < (1u << 16)) nt = 1;
+        if (const char* e = getenv("UB200_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));   // tests force the split
+        std::vector<size_t> cut(nt + 1, n);
+        cut[0] = 0;
+        for (unsigned c = 1; c < nt; c++)
+            cut[c] = (size_t)(std::lower_bound(t.row_ptr.begin(), t.row_ptr.begin() + n, t.muts.size() * c / nt) - t.row_ptr.begin());
+        for (unsigned c = 1; c <= nt; c++) cut[c] = std::max(cut[c], cut[c - 1]);
+        std::vector<std::string> bufs(nt);
+        auto body = [&](unsigned c) {
+            std::string buf, list, mm, packed;
+            buf.reserve((size_t)(t.row_ptr[cut[c + 1]] - t.row_ptr[cut[c]]) * 14 + (cut[c + 1] - cut[c]) * 3 + 64);
+            for (size_t i = cut[c]; i < cut[c + 1]; i++) {
+                list.clear();
+                for (uint64_t k = t.row_ptr[i]; k < t.row_ptr[i + 1]; k++) {
+                    const ub200_mutation& m = t.muts[k];
+                    mm.clear();
+                    pb::put_i32(mm, 1, m.position);
+                    if (m.position < 0) {
+                        pb::put_i32(mm, 2, -1);
+                        pb::put_i32(mm, 3, -1);
+                    } else {
+                        pb::put_i32(mm, 2, code(m.ref_nuc));
+                        pb::put_i32(mm, 3, code(m.par_nuc));
+                        packed.clear();
+                        for (int b = 0; b < 4; b++) if (m.mut_nuc & (1 << b)) pb::put_varint(packed, (uint64_t)b);
+                        if (!packed.empty()) pb::put_bytes(mm, 4, packed);
+                    }
+                    if (!t.chrom.empty()) pb::put_bytes(mm, 5, t.chrom);
+                    pb::put_bytes(list, 1, mm);
+                }
+                pb::put_bytes(buf, 2, list);
             }
-            if (!t.chrom.empty()) pb::put_bytes(mm, 5, t.chrom);
-            pb::put_bytes(list, 1, mm);
+            bufs[c].swap(buf);
+        };
+        if (nt == 1) body(0);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned c = 0; c < nt; c++) pool.emplace_back(body, c);
+            for (auto& th : pool) th.join();
         }
-        pb::put_bytes(out, 2, list);
+        size_t total = out.size();
+        for (auto& b : bufs) total += b.size();
+        out.reserve(total + 1024);
+        for (auto& b : bufs) { out += b; std::string().swap(b); }
     }
     for (auto& c : t.condensed) {
         std::string cc;

@@ -489,6 +489,8 @@ def main():
                     "d2h_bytes_per_step": int(d2h / args.steps)},
             "gpu_launches": int(total_launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "extra": extra, "parity_at_size": parity,
+            # one-time cost outside the timed region: ub200_mat_create = host derivation + upload of the flattened tree
+            "setup": {"generate_synthetic_s": round(t_gen, 2), "mat_create_s": round(t_create, 2)},
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

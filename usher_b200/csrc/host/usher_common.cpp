@@ -31,12 +31,17 @@ void flatten(const MAT::Tree& T, Flat& f) {
     f.parent.resize(f.dfs.size());
     f.row_ptr.assign(1, 0);
     f.muts.clear();
-    std::unordered_map<const MAT::Node*, int32_t> idx;
-    idx.reserve(f.dfs.size() * 2);
-    for (size_t i = 0; i < f.dfs.size(); i++) idx[f.dfs[i]] = (int32_t)i;
+    size_t total = 0;
+    for (auto n : f.dfs) total += n->mutations.size();
+    f.muts.reserve(total);
+    f.row_ptr.reserve(f.dfs.size() + 1);
+    // pre-order: the parent of a node is the nearest node still open on the walk's stack (no pointer -> index map)
+    std::vector<std::pair<const MAT::Node*, int32_t>> open;
     for (size_t i = 0; i < f.dfs.size(); i++) {
         const MAT::Node* n = f.dfs[i];
-        f.parent[i] = n->parent ? idx[n->parent] : -1;
+        while (!open.empty() && open.back().first != n->parent) open.pop_back();
+        f.parent[i] = open.empty() ? -1 : open.back().second;
+        open.emplace_back(n, (int32_t)i);
         for (auto& m : n->mutations)
             f.muts.push_back({m.position, (uint8_t)m.ref_nuc, (uint8_t)m.par_nuc, (uint8_t)m.mut_nuc, 0});
         f.row_ptr.push_back(f.muts.size());

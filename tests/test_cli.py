@@ -49,6 +49,47 @@ def test_pb_newick_vcf_readers_match_reference(usher):
     assert nwk == str(g["current_tree"]).strip()   # the reference's -p run writes the labelled input tree
 
 
+def test_vcf_reader_ambiguity_counts_follow_the_reference_quirk(usher):
+    """num_ambiguous (the -A sort key): the reference tests Mutation::mut_nuc for ambiguity for EVERY genotype, and for a
+    reference call (GT 0) that field still holds the previous genotype's allele (src/mutation_annotated_tree.cpp:2246,
+    2271).  A sequential restatement of exactly that gives the expected counts; along the sample order of the
+    reference's own `-A` run (golden) they never decrease.  The reader splits the rows over host threads: same counts
+    and sample lists for any split."""
+    vcf = os.path.join(common.GOLDEN, "hostgold_samples.vcf")
+    code = {"A": 1, "C": 2, "G": 4, "T": 8, "R": 5, "Y": 10, "S": 6, "W": 9, "K": 12, "M": 3, "B": 14, "D": 13, "H": 11,
+            "V": 15, "N": 15}   # 'V' falls through to N in the reference's switch (missing break)
+    names, exp, stale = [], [], 0
+    for line in open(vcf):
+        w = line.split()
+        if len(w) > 1 and w[1] == "POS":
+            names = w[9:]
+            exp = [0] * len(names)
+        elif names:
+            alts = w[4].split(",")
+            for k in range(len(names)):
+                gt = w[9 + k]
+                if gt[0].isdigit():
+                    a = int(gt)
+                    nuc = code.get(alts[a - 1][0], 15) if a > 0 else stale
+                else:
+                    nuc = 15
+                exp[k] += 1 if nuc & (nuc - 1) else 0
+                stale = nuc
+    outs = []
+    for nt in ("1", "2", "5"):
+        d = tempfile.mkdtemp()
+        subprocess.check_call([usher, "-i", PB, "-v", vcf, "--dump-flat", d + "/f.txt"], stderr=subprocess.DEVNULL,
+                              env=dict(os.environ, UB200_HOST_THREADS=nt))
+        outs.append([l for l in open(d + "/f.txt") if l[:2] in ("S\t", "A\t")])
+    assert outs[0] == outs[1] == outs[2]
+    got = {l.split("\t")[1]: int(l.split("\t")[2]) for l in outs[0] if l.startswith("A\t")}
+    assert got == dict(zip(names, exp))
+    g = common.load(os.path.join(common.GOLDEN, "hostgold.npz"))
+    order = [l.split("\t")[0] for l in str(g["sort3__placement_stats.tsv"]).splitlines() if l]
+    keys = [got[n] for n in order]
+    assert keys == sorted(keys) and len(set(keys)) > 1
+
+
 def test_pb_round_trip_is_byte_identical(usher):
     d = tempfile.mkdtemp()
     subprocess.check_call([usher, "-i", PB, "--resave", d + "/re.pb"], stderr=subprocess.DEVNULL)

@@ -1290,16 +1290,7 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
         for (; i < t.n && isdigit((unsigned char)t.p[i]); i++) v = std::min<long>(v * 10 + (t.p[i] - '0'), 1L << 40);
         return neg ? -v : v;
     };
-    int8_t stale_mut_nuc = 0;   // see the genotype loop below
-    bool header = false;
-    size_t n_ids = 0;
-    std::vector<size_t> cols;
-    std::vector<Tok> w, alleles;
-    const char* p = raw.data;
-    const char* const end = raw.data + raw.size;
-    while (p < end) {
-        const char* le = (const char*)memchr(p, '\n', (size_t)(end - p));
-        if (!le) le = end;
+    auto tokenize = [&](const char* p, const char* le, std::vector<Tok>& w) {
         w.clear();
         for (const char* q = p; q < le;) {
             while (q < le && is_space(*q)) q++;
@@ -1308,9 +1299,21 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
             while (q < le && !is_space(*q)) q++;
             w.push_back(Tok{a0, (size_t)(q - a0)});
         }
-        p = le < end ? le + 1 : end;
-        if (!header && w.size() > 1) {
-            if (w[1].n == 3 && memcmp(w[1].p, "POS", 3) == 0) {
+    };
+    // ---- header: the first line whose second word is POS names the samples
+    size_t n_ids = 0;
+    std::vector<size_t> cols;
+    const char* p = raw.data;
+    const char* const end = raw.data + raw.size;
+    {
+        std::vector<Tok> w;
+        bool header = false;
+        while (p < end && !header) {
+            const char* le = (const char*)memchr(p, '\n', (size_t)(end - p));
+            if (!le) le = end;
+            tokenize(p, le, w);
+            p = le < end ? le + 1 : end;
+            if (w.size() > 1 && w[1].n == 3 && memcmp(w[1].p, "POS", 3) == 0) {
                 for (size_t j = 9; j < w.size(); j++) {
                     const std::string name(w[j].p, w[j].n);
                     n_ids++;
@@ -1323,21 +1326,58 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
                 }
                 header = true;
             }
-        } else if (header) {
+        }
+    }
+    // ---- rows: slices of whole lines on host threads.  The one thing that crosses rows is the reference's stale
+    // genotype allele (below): a slice counts, per sample, the reference calls it sees before its first non-reference
+    // genotype, and the merge adds them when the allele carried in from the slices before it is ambiguous.
+    unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if ((size_t)(end - p) < (1u << 20)) nt = 1;
+    if (const char* e = getenv("UB200_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));   // tests force the split
+    std::vector<const char*> cut(nt + 1, end);
+    cut[0] = p;
+    for (unsigned c = 1; c < nt; c++) {
+        const char* q = p + (size_t)(end - p) * c / nt;
+        q = std::max(q, cut[c - 1]);
+        const char* nl = q < end ? (const char*)memchr(q, '\n', (size_t)(end - q)) : nullptr;
+        cut[c] = nl ? nl + 1 : end;
+    }
+    struct Slice {
+        std::vector<std::vector<Mutation>> muts;   // per new sample, in row order
+        std::vector<size_t> ambiguous;             // per new sample, without the leading reference calls
+        bool seen = false;                         // a non-reference genotype was seen
+        size_t lead_rows = 0, lead_cols = 0;       // whole rows / samples of the next row before it
+        int8_t last = 0;                           // allele of the last non-reference genotype
+        std::string err;
+    };
+    std::vector<Slice> slices(nt);
+    auto scan = [&](unsigned c) {
+        Slice S;
+        S.muts.resize(cols.size());
+        S.ambiguous.assign(cols.size(), 0);
+        std::vector<Tok> w, alleles;
+        size_t rows = 0;
+        int8_t stale_mut_nuc = 0;   // see the genotype loop below
+        for (const char* q = cut[c]; q < cut[c + 1] && S.err.empty();) {
+            const char* le = (const char*)memchr(q, '\n', (size_t)(cut[c + 1] - q));
+            if (!le) le = cut[c + 1];
+            tokenize(q, le, w);
+            q = le < cut[c + 1] ? le + 1 : cut[c + 1];
             if (w.size() != 9 + n_ids) {
-                fprintf(stderr, "ERROR! Incorrect VCF format. Expected %zu columns but got %zu.\n", 9 + n_ids, w.size());
-                exit(1);
+                S.err = "ERROR! Incorrect VCF format. Expected " + std::to_string(9 + n_ids) + " columns but got " +
+                        std::to_string(w.size()) + ".";
+                break;
             }
+            if (cols.empty()) continue;   // (the reference only looks at a row's fields per new sample)
             // ALT alleles: split at ',' (a trailing empty piece is dropped, like the reference's string_split)
             alleles.clear();
             {
                 const char* a0 = w[4].p;
                 const char* const ae = w[4].p + w[4].n;
-                for (const char* q = a0; q < ae; q++)
-                    if (*q == ',') { alleles.push_back(Tok{a0, (size_t)(q - a0)}); a0 = q + 1; }
+                for (const char* x = a0; x < ae; x++)
+                    if (*x == ',') { alleles.push_back(Tok{a0, (size_t)(x - a0)}); a0 = x + 1; }
                 if (a0 < ae) alleles.push_back(Tok{a0, (size_t)(ae - a0)});
             }
-            if (cols.empty()) continue;   // (the reference only looks at a row's fields per new sample)
             const std::string chrom(w[0].p, w[0].n);
             const int position = (int)leading_int(w[1], "POS");
             const int8_t ref_nuc = get_nuc_id(w[3].p[0]);
@@ -1353,8 +1393,9 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
                     const long a = leading_int(gt, "genotype");
                     if (a > 0) {
                         if ((size_t)a > alleles.size()) {
-                            fprintf(stderr, "ERROR! Incorrect VCF format: genotype %ld at position %d has no ALT allele.\n", a, position);
-                            exit(1);
+                            S.err = "ERROR! Incorrect VCF format: genotype " + std::to_string(a) + " at position " +
+                                    std::to_string(position) + " has no ALT allele.";
+                            break;
                         }
                         const Tok& al = alleles[(size_t)a - 1];
                         const char c0 = al.n ? al.p[0] : '\0';   // first character only, like the reference
@@ -1375,12 +1416,38 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
                     m.par_nuc = ref_nuc;
                     m.mut_nuc = mut_nuc;
                     m.is_missing = is_missing;
-                    missing_samples[k].mutations.push_back(std::move(m));
+                    S.muts[k].push_back(std::move(m));
+                    if (!S.seen) { S.seen = true; S.lead_rows = rows; S.lead_cols = k; }
+                    S.last = mut_nuc;
                 }
-                if (mut_nuc & (mut_nuc - 1)) missing_samples[k].num_ambiguous++;
+                // (reference calls before the slice's first non-reference genotype carry an allele from an earlier
+                // slice: they are counted at the merge)
+                if (S.seen && (mut_nuc & (mut_nuc - 1))) S.ambiguous[k]++;
                 stale_mut_nuc = mut_nuc;
             }
+            rows++;
         }
+        if (!S.seen) { S.lead_rows = rows; S.lead_cols = 0; }
+        slices[c] = std::move(S);
+    };
+    if (nt == 1) scan(0);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned c = 0; c < nt; c++) pool.emplace_back(scan, c);
+        for (auto& th : pool) th.join();
+    }
+    int8_t carried = 0;   // the allele the reference's reused Mutation object holds when a slice starts
+    for (auto& S : slices) {
+        if (!S.err.empty()) { fprintf(stderr, "%s\n", S.err.c_str()); exit(1); }
+        const bool carried_ambiguous = (carried & (carried - 1)) != 0;
+        for (size_t k = 0; k < cols.size(); k++) {
+            if (carried_ambiguous) missing_samples[k].num_ambiguous += S.lead_rows + ((S.seen && k < S.lead_cols) ? 1 : 0);
+            missing_samples[k].num_ambiguous += S.ambiguous[k];
+            auto& dst = missing_samples[k].mutations;
+            if (dst.empty()) dst = std::move(S.muts[k]);
+            else for (auto& m : S.muts[k]) dst.push_back(std::move(m));
+        }
+        if (S.seen) carried = S.last;
     }
     if (getenv("UB200_LOAD_TIMING"))
         fprintf(stderr, "[vcf] %zu new samples, %.1f MB in %.1f ms\n", missing_samples.size(), raw.size / 1e6,

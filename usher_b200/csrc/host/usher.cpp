@@ -198,6 +198,7 @@ int main(int argc, char** argv) {
             for (auto& m : s.mutations) fprintf(f, "%d:%d:%d:%d,", m.position, m.ref_nuc, m.mut_nuc, (int)m.is_missing);
             fprintf(f, "\n");
         }
+        for (auto& s : missing) fprintf(f, "A\t%s\t%zu\n", s.name.c_str(), s.num_ambiguous);   // the -A sort key
         for (auto& name : T.condensed_order) {
             fprintf(f, "C\t%s\t", name.c_str());
             for (auto& m : T.condensed_nodes.at(name)) fprintf(f, "%s,", m.c_str());

@@ -1079,6 +1079,45 @@ void get_sample_mutation_paths(Tree* T, const std::vector<std::string>& samples,
 // MAT construction: one Fitch-Sankoff pass per VCF row over the BFS vector (reference mapper_body,
 // src/usher_mapper.cpp:6-161, driven row by row from read_vcf :2099-2179).  Serial host code: this is the
 // pre-processing stage of `usher -t tree.nh -v samples.vcf -o tree.pb`, not the placement hot path.
+// ---- VCF text: (pointer, length) views of the mapped file instead of getline + split copies
+namespace {
+struct Tok { const char* p; size_t n; };
+inline bool vcf_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f' || c == '\n'; }
+// whitespace-separated words of [p, le), like `istringstream >> word`
+inline void vcf_words(const char* p, const char* le, std::vector<Tok>& w) {
+    w.clear();
+    for (const char* q = p; q < le;) {
+        while (q < le && vcf_space(*q)) q++;
+        if (q == le) break;
+        const char* a0 = q;
+        while (q < le && !vcf_space(*q)) q++;
+        w.push_back(Tok{a0, (size_t)(q - a0)});
+    }
+}
+// pieces of a word between ',' (a trailing empty piece is dropped, like the reference's string_split)
+inline void vcf_alleles(const Tok& t, std::vector<Tok>& out) {
+    out.clear();
+    const char* a0 = t.p;
+    const char* const ae = t.p + t.n;
+    for (const char* x = a0; x < ae; x++)
+        if (*x == ',') { out.push_back(Tok{a0, (size_t)(x - a0)}); a0 = x + 1; }
+    if (a0 < ae) out.push_back(Tok{a0, (size_t)(ae - a0)});
+}
+// std::stoi on a word that starts with [+-]digits
+inline long vcf_int(const Tok& t, const char* what) {
+    size_t i = 0;
+    bool neg = false;
+    if (i < t.n && (t.p[i] == '+' || t.p[i] == '-')) neg = t.p[i++] == '-';
+    if (i >= t.n || !isdigit((unsigned char)t.p[i])) {
+        fprintf(stderr, "ERROR! Incorrect VCF format: %s '%.*s' is not a number.\n", what, (int)t.n, t.p);
+        exit(1);
+    }
+    long v = 0;
+    for (; i < t.n && isdigit((unsigned char)t.p[i]); i++) v = std::min<long>(v * 10 + (t.p[i] - '0'), 1L << 40);
+    return neg ? -v : v;
+}
+}  // namespace
+
 static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::vector<Missing_Sample>& missing_samples) {
     std::vector<Node*> bfs = T->breadth_first_expansion();
     std::unordered_map<std::string, size_t> bfs_idx;
@@ -1091,16 +1130,14 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
         is_leaf[i] = bfs[i]->is_leaf();
     }
     fprintf(stderr, "Loading VCF file.\n");
-    std::string raw;
-    if (!read_all(vcf_filename, raw)) {
+    FileBytes raw;
+    if (!raw.open(vcf_filename)) {
         fprintf(stderr, "ERROR: Could not open the VCF file: %s!\n", vcf_filename.c_str());
         exit(1);
     }
     fprintf(stderr, "Computing parsimonious assignments for input variants.\n");
-    std::istringstream in(raw);
-    std::string line;
     bool header = false;
-    std::vector<std::string> ids;
+    size_t n_ids = 0;
     std::vector<long> col_node;      // BFS index of the column's sample, or -(1+k) for missing sample k
     // Sites are parsed first; the assignment itself runs on the GPU (ub200_fs_*, one CTA per site).  The serial
     // restatement further down only runs when UB200_FS_HOST=1 asks for it.
@@ -1108,16 +1145,21 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
     std::vector<Site> sites;
     std::vector<uint32_t> var_node;
     std::vector<uint8_t> var_nuc;
-    while (std::getline(in, line)) {
-        std::vector<std::string> w;
-        string_split(line, w);
+    std::vector<Tok> w, alleles;
+    const char* const end = raw.data + raw.size;
+    for (const char* p = raw.data; p < end;) {
+        const char* le = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!le) le = end;
+        vcf_words(p, le, w);
+        p = le < end ? le + 1 : end;
         if (!header) {
-            if (w.size() > 1 && w[1] == "POS") {
+            if (w.size() > 1 && w[1].n == 3 && memcmp(w[1].p, "POS", 3) == 0) {
                 for (size_t j = 9; j < w.size(); j++) {
-                    ids.push_back(w[j]);
-                    auto it = bfs_idx.find(w[j]);
+                    const std::string name(w[j].p, w[j].n);
+                    n_ids++;
+                    auto it = bfs_idx.find(name);
                     if (it == bfs_idx.end()) {
-                        missing_samples.emplace_back(Missing_Sample(w[j]));
+                        missing_samples.emplace_back(Missing_Sample(name));
                         col_node.push_back(-(long)missing_samples.size());
                     } else {
                         col_node.push_back((long)it->second);
@@ -1127,25 +1169,29 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
             }
             continue;
         }
-        if (w.size() != 9 + ids.size()) {
+        if (w.size() != 9 + n_ids) {
             fprintf(stderr, "ERROR! Incorrect VCF format.\n");
             exit(1);
         }
         Site st;
-        st.pos = std::stoi(w[1]);
-        st.ref = get_nuc_id(w[3][0]);
-        st.chrom = w[0];
+        st.pos = (int)vcf_int(w[1], "POS");
+        st.ref = get_nuc_id(w[3].p[0]);
+        st.chrom.assign(w[0].p, w[0].n);
         st.v0 = var_node.size();
-        std::vector<std::string> alleles;
-        string_split(w[4], ',', alleles);
+        vcf_alleles(w[4], alleles);
         fprintf(stderr, "At variant site %i\n", st.pos);
-        for (size_t c = 0; c < ids.size(); c++) {
-            const std::string& gt = w[9 + c];
+        for (size_t c = 0; c < n_ids; c++) {
+            const Tok& gt = w[9 + c];
             int8_t nuc;
-            if (isdigit((unsigned char)gt[0])) {
-                const int a = std::stoi(gt);
+            if (isdigit((unsigned char)gt.p[0])) {
+                const long a = vcf_int(gt, "genotype");
                 if (a <= 0) continue;
-                nuc = get_nuc_id(alleles.at((size_t)a - 1)[0]);
+                if ((size_t)a > alleles.size()) {
+                    fprintf(stderr, "ERROR! Incorrect VCF format: genotype %ld at position %d has no ALT allele.\n", a, st.pos);
+                    exit(1);
+                }
+                const Tok& al = alleles[(size_t)a - 1];
+                nuc = get_nuc_id(al.n ? al.p[0] : '\0');   // first character only, like the reference
             } else {
                 nuc = 15;
             }
@@ -1154,13 +1200,13 @@ static void build_mat_from_vcf(Tree* T, const std::string& vcf_filename, std::ve
                 var_nuc.push_back((uint8_t)nuc);
             } else {
                 Mutation m;
-                m.chrom = w[0];
+                m.chrom = st.chrom;
                 m.position = st.pos;
                 m.ref_nuc = st.ref;
                 m.par_nuc = st.ref;   // the reference leaves par_nuc unset here (:65-82); scoring never reads it
                 m.is_missing = (nuc == 15);
                 m.mut_nuc = nuc;
-                missing_samples[(size_t)(-col_node[c] - 1)].mutations.push_back(m);
+                missing_samples[(size_t)(-col_node[c] - 1)].mutations.push_back(std::move(m));
             }
         }
         st.v1 = var_node.size();
@@ -1274,32 +1320,8 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
         exit(1);
     }
     // Same observable behaviour as the reference's getline + whitespace split + per-genotype Mutation objects, without
-    // materialising them: a 10 000-sample VCF holds 3e8 genotype tokens, almost all of them "0".  Tokens are (pointer,
+    // materialising them: a 10 000-sample VCF holds 3e8 genotype tokens, almost all of them "0".  Words are (pointer,
     // length) views of the mapped file; a Mutation is only built for a genotype that adds one.
-    struct Tok { const char* p; size_t n; };
-    auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f' || c == '\n'; };
-    auto leading_int = [](const Tok& t, const char* what) -> long {   // std::stoi on a token that starts with [+-]digits
-        size_t i = 0;
-        bool neg = false;
-        if (i < t.n && (t.p[i] == '+' || t.p[i] == '-')) neg = t.p[i++] == '-';
-        if (i >= t.n || !isdigit((unsigned char)t.p[i])) {
-            fprintf(stderr, "ERROR! Incorrect VCF format: %s '%.*s' is not a number.\n", what, (int)t.n, t.p);
-            exit(1);
-        }
-        long v = 0;
-        for (; i < t.n && isdigit((unsigned char)t.p[i]); i++) v = std::min<long>(v * 10 + (t.p[i] - '0'), 1L << 40);
-        return neg ? -v : v;
-    };
-    auto tokenize = [&](const char* p, const char* le, std::vector<Tok>& w) {
-        w.clear();
-        for (const char* q = p; q < le;) {
-            while (q < le && is_space(*q)) q++;
-            if (q == le) break;
-            const char* a0 = q;
-            while (q < le && !is_space(*q)) q++;
-            w.push_back(Tok{a0, (size_t)(q - a0)});
-        }
-    };
     // ---- header: the first line whose second word is POS names the samples
     size_t n_ids = 0;
     std::vector<size_t> cols;
@@ -1311,7 +1333,7 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
         while (p < end && !header) {
             const char* le = (const char*)memchr(p, '\n', (size_t)(end - p));
             if (!le) le = end;
-            tokenize(p, le, w);
+            vcf_words(p, le, w);
             p = le < end ? le + 1 : end;
             if (w.size() > 1 && w[1].n == 3 && memcmp(w[1].p, "POS", 3) == 0) {
                 for (size_t j = 9; j < w.size(); j++) {
@@ -1361,7 +1383,7 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
         for (const char* q = cut[c]; q < cut[c + 1] && S.err.empty();) {
             const char* le = (const char*)memchr(q, '\n', (size_t)(cut[c + 1] - q));
             if (!le) le = cut[c + 1];
-            tokenize(q, le, w);
+            vcf_words(q, le, w);
             q = le < cut[c + 1] ? le + 1 : cut[c + 1];
             if (w.size() != 9 + n_ids) {
                 S.err = "ERROR! Incorrect VCF format. Expected " + std::to_string(9 + n_ids) + " columns but got " +
@@ -1370,16 +1392,9 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
             }
             if (cols.empty()) continue;   // (the reference only looks at a row's fields per new sample)
             // ALT alleles: split at ',' (a trailing empty piece is dropped, like the reference's string_split)
-            alleles.clear();
-            {
-                const char* a0 = w[4].p;
-                const char* const ae = w[4].p + w[4].n;
-                for (const char* x = a0; x < ae; x++)
-                    if (*x == ',') { alleles.push_back(Tok{a0, (size_t)(x - a0)}); a0 = x + 1; }
-                if (a0 < ae) alleles.push_back(Tok{a0, (size_t)(ae - a0)});
-            }
+            vcf_alleles(w[4], alleles);
             const std::string chrom(w[0].p, w[0].n);
-            const int position = (int)leading_int(w[1], "POS");
+            const int position = (int)vcf_int(w[1], "POS");
             const int8_t ref_nuc = get_nuc_id(w[3].p[0]);
             for (size_t k = 0; k < cols.size(); k++) {
                 const Tok& gt = w[cols[k]];
@@ -1390,7 +1405,7 @@ void read_vcf_samples(const std::string& vcf_filename, const std::function<bool(
                 int8_t mut_nuc = stale_mut_nuc;
                 bool add = false, is_missing = false;
                 if (isdigit((unsigned char)gt.p[0])) {
-                    const long a = leading_int(gt, "genotype");
+                    const long a = vcf_int(gt, "genotype");
                     if (a > 0) {
                         if ((size_t)a > alleles.size()) {
                             S.err = "ERROR! Incorrect VCF format: genotype " + std::to_string(a) + " at position " +

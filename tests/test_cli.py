@@ -286,3 +286,32 @@ def test_compat_adapter_with_dfs_tie_index(usher):
         assert [int(v) for v in x[6].split(",")] == opt.tolist()
         best = max(opt.tolist(), key=lambda v: (leaves[v], v))
         assert x[1] == names[best] and int(x[4]) == best
+
+
+@pytest.mark.parametrize("seed,n_leaves,n_sites", [(77, 400, 120), (78, 60, 200)])
+def test_create_mat_reader_and_host_assignment_vs_reference_built_mats(usher, seed, n_leaves, n_sites):
+    """`usher -t tree.nh -v samples.vcf` on random trees with ambiguous / missing genotypes: the VCF site reader, the
+    serial restatement of mapper_body (asked for by name: no GPU here) and the mutation lists they produce, against
+    the MAT the reference itself builds from the same files (src/usher_mapper.cpp:6-161).  The GPU kernel goes through
+    the same reader in tests/test_gpu_fitch_sankoff.py."""
+    from oracle import ref
+    from test_oracle import _random_fs_case
+    if not ref.available():
+        pytest.skip("oracle/_ref/libusher_ref.so missing")
+    newick, vcf, *_ = _random_fs_case(seed, n_leaves, n_sites, p_amb=0.15)
+    d = tempfile.mkdtemp()
+    open(d + "/t.nh", "w").write(newick)
+    open(d + "/v.vcf", "w").write(vcf)
+    rt = ref.RefTree.from_newick_vcf(d + "/t.nh", d + "/v.vcf", False, 1)
+    parent, row_ptr, muts, names = rt.export()
+    rt.close()
+    r = subprocess.run([usher, "-t", d + "/t.nh", "-v", d + "/v.vcf", "--dump-flat", d + "/flat.txt"], capture_output=True,
+                       text=True, env=dict(os.environ, UB200_FS_HOST="1"))
+    assert r.returncode == 0, r.stderr[-1500:]
+    nodes = [l.rstrip("\n").split("\t") for l in open(d + "/flat.txt") if l.startswith("N\t")]
+    assert [x[1] for x in nodes] == list(names)
+    assert [x[2] for x in nodes] == ["" if p < 0 else names[p] for p in parent]
+    rp = row_ptr.astype(np.int64)
+    for i, x in enumerate(nodes):
+        exp = "".join(f"{m['position']}:{m['ref_nuc']}:{m['par_nuc']}:{m['mut_nuc']}," for m in muts[rp[i]:rp[i + 1]])
+        assert x[3] == exp, (i, x[3], exp)

@@ -263,8 +263,7 @@ static void derive3(const ub200_flat_mat& f, uint32_t target_tiles, uint32_t min
         while (at < pieces[t].words) out[at++] = pad;
     };
     {
-        unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-        if (d.m < (1u << 20)) nthr = 1;
+        const unsigned nthr = host_threads(d.m);   // (tiles are handed out one by one: uneven tiles balance themselves)
         std::atomic<size_t> next{0};
         auto worker = [&]() {
             std::vector<uint32_t> chain, seg, tmp;

@@ -841,6 +841,7 @@ bool load_flat_mutation_annotated_tree(const std::string& filename, FlatTree& t,
                 pb::Reader mr = l.sub();
                 int32_t pos = 0, refn = 0, parn = 0;
                 int8_t mut = 0;
+                bool bad_code = false;
                 const char* chrom_p = nullptr;
                 size_t chrom_n = 0;
                 while (mr.more()) {
@@ -849,12 +850,19 @@ bool load_flat_mutation_annotated_tree(const std::string& filename, FlatTree& t,
                     if (f2 == 1 && w2 == 0) pos = (int32_t)mr.varint();
                     else if (f2 == 2 && w2 == 0) refn = (int32_t)mr.varint();
                     else if (f2 == 3 && w2 == 0) parn = (int32_t)mr.varint();
-                    else if (f2 == 4 && w2 == 0) mut |= (int8_t)(1 << (int)mr.varint());
-                    else if (f2 == 4 && w2 == 2) { pb::Reader pk = mr.sub(); while (pk.more()) mut |= (int8_t)(1 << (int)pk.varint()); }
+                    else if (f2 == 4 && w2 == 0) { const uint64_t v = mr.varint(); bad_code |= v > 3; mut |= (int8_t)(1 << (int)(v & 3)); }
+                    else if (f2 == 4 && w2 == 2) {
+                        pb::Reader pk = mr.sub();
+                        while (pk.more()) { const uint64_t v = pk.varint(); bad_code |= v > 3; mut |= (int8_t)(1 << (int)(v & 3)); }
+                    }
                     else if (f2 == 5 && w2 == 2) { pb::Reader s = mr.sub(); chrom_p = (const char*)s.p; chrom_n = (size_t)(s.end - s.p); }
                     else mr.skip(w2);
                 }
                 if (!l.ok || !mr.ok) { P.err = "malformed mutation list of node " + std::to_string(i); return (size_t)-1; }
+                if (pos >= 0 && (bad_code || (uint32_t)refn > 3u || (uint32_t)parn > 3u)) {
+                    P.err = "node " + std::to_string(i) + ": nucleotide code outside 0..3 at position " + std::to_string(pos);
+                    return (size_t)-1;
+                }
                 if (!dst) {
                     if (!chrom_n) P.any_unnamed = true;
                     if (chrom_n || P.chrom_set) {

@@ -325,6 +325,8 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
         FILE* stats = fopen(stats_fn.c_str(), "w");
         std::vector<int32_t> pps_scores;   // -p: per-node scores of samples indexes[pps_first .. pps_first + pps_count)
         size_t pps_first = 0, pps_count = 0;
+        std::vector<MAT::Node*> pps_bfs;        // -p: rows go out in BFS order; the tree does not change in this mode, so
+        std::vector<uint32_t> pps_bfs_to_dfs;   // the order and its DFS indices are computed once, not per sample
         for (size_t idx = 0; idx < indexes.size(); idx++) {
             timer.Start();
             const size_t s = indexes[idx];
@@ -428,12 +430,18 @@ int usher_common(std::string dout_filename, std::string outdir, uint32_t max_tre
             }
 
             if (print_parsimony_scores) {   // :557-578, rows in BFS order
-                auto bfs = T->breadth_first_expansion();
-                std::unordered_map<const MAT::Node*, size_t> didx;
-                for (size_t i = 0; i < dev.flat.dfs.size(); i++) didx[dev.flat.dfs[i]] = i;
+                if (pps_bfs.empty()) {
+                    pps_bfs = T->breadth_first_expansion();
+                    std::unordered_map<const MAT::Node*, uint32_t> didx;
+                    didx.reserve(dev.flat.dfs.size() * 2);
+                    for (size_t i = 0; i < dev.flat.dfs.size(); i++) didx[dev.flat.dfs[i]] = (uint32_t)i;
+                    pps_bfs_to_dfs.resize(pps_bfs.size());
+                    for (size_t q = 0; q < pps_bfs.size(); q++) pps_bfs_to_dfs[q] = didx.at(pps_bfs[q]);
+                }
                 std::vector<MAT::Mutation> ex, im;
-                for (auto n : bfs) {
-                    const int sc = node_scores[didx[n]];
+                for (size_t q = 0; q < pps_bfs.size(); q++) {
+                    MAT::Node* const n = pps_bfs[q];
+                    const int sc = node_scores[pps_bfs_to_dfs[q]];
                     const bool optimal = sc == best_set_difference;
                     fprintf(parsimony_scores_file, "%s\t%s\t%d\t\t%c\t", sample.c_str(), n->identifier.c_str(), sc, optimal ? 'y' : 'n');
                     if (optimal) {

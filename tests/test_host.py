@@ -262,3 +262,38 @@ def test_leaf_counts_bfs_index_and_tie_order_against_a_plain_restatement(monkeyp
             exp = sorted(range(n), key=lambda v: (-int(leaves[v]), -int(rep[v]), v))
             assert d["key_to_node"].tolist() == exp
             assert np.array_equal(d["tiekey"][d["key_to_node"]], np.arange(n))
+
+
+def test_tree_order_errors_do_not_depend_on_the_thread_split(monkeypatch):
+    """The topology checks run on chunks of the node range: a broken parent entry anywhere in the array is reported with
+    the same status and the same message (the FIRST offending node) as by a single pass."""
+    import small_synth
+    parent, row_ptr, muts, _ = small_synth.random_mat(31, 3000, 80, 2.0)
+    n = len(parent)
+    rng = np.random.default_rng(5)
+    cases = []
+    for _ in range(12):
+        i = int(rng.integers(2, n))
+        kind = int(rng.integers(0, 3))
+        p = np.array(parent, dtype=np.int32).copy()
+        if kind == 0:
+            p[i] = i + int(rng.integers(0, 5))          # not an earlier node
+        elif kind == 1:
+            p[i] = -1                                    # a second root
+        else:
+            p[i] = int(rng.integers(0, i))               # an earlier node, most likely not on the path of i-1
+        cases.append(p)
+    two = np.array(parent, dtype=np.int32).copy()        # two errors: the first one in node order wins
+    two[n - 5] = n + 3
+    two[40] = 39 if parent[40] != 39 else 38
+    cases.append(two)
+    for p in cases:
+        seen = []
+        for nt in ("1", "5", "16"):
+            monkeypatch.setenv("UB200_HOST_THREADS", nt)
+            try:
+                capi.debug_derive(p, row_ptr, muts, target_tiles=16, min_tile_cost=64)
+                seen.append(("ok", ""))
+            except capi.UB200Error as e:
+                seen.append((e.code, str(e)))
+        assert seen[0] == seen[1] == seen[2], seen
